@@ -1,0 +1,121 @@
+/* xfeat_b200.h -- C-ABI of libxfeat_b200.so: the B200-native (sm_100a) XFeat front-end.
+ *
+ * This is the drop-in boundary for xfeatSLAM's XFeat hot path.  The
+ * reference has no C ABI today: its host code calls libtorch C++ directly.  Each entry point below
+ * names the reference interface it replaces; the reference-side binding a maintainer would add
+ * (a replacement XFextractor.cc / ORBmatcher patch) is in INTEGRATION.md and
+ * xfeatslam_b200/host/.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * xfb_status; nothing throws or calls exit(); all buffers are caller-owned; one xfb_ctx per GPU
+ * per host thread (a ctx is not re-entrant, like the reference's XFextractor).  There is NO CPU
+ * fallback: without a CUDA device xfb_create fails with XFB_ERR_CUDA.
+ */
+#ifndef XFEAT_B200_H_
+#define XFEAT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct xfb_ctx xfb_ctx;
+
+typedef enum xfb_status {
+  XFB_OK = 0,
+  XFB_ERR_ARG = -1,      /* bad argument (null pointer, size out of the range given at create) */
+  XFB_ERR_CUDA = -2,     /* CUDA runtime error; text in xfb_last_error */
+  XFB_ERR_WEIGHTS = -3,  /* malformed / incomplete weight blob */
+  XFB_ERR_EMPTY = -4,    /* empty image (the reference returns -1, src/XFextractor.cc:253-254) */
+  XFB_ERR_NOMEM = -5
+} xfb_status;
+
+#define XFB_DESC_DIM 64
+
+/* Replaces XFextractor::XFextractor (src/XFextractor.cc:75-149: weight load :133-137, device
+ * select :141-144).  weights_blob/n: the flat blob written by tools/convert_weights.py from the
+ * reference's weights/xfeat.pt (copied, the caller may free it after the call).  device: CUDA
+ * ordinal.  max_h/max_w: largest input image; max_batch: frames per xfb_extract_batch call;
+ * max_topk: largest nfeatures (<= 8192). */
+int xfb_create(xfb_ctx** out, const void* weights_blob, size_t n, int device, int max_h, int max_w, int max_batch,
+               int max_topk);
+void xfb_destroy(xfb_ctx* ctx);
+
+/* Last error text of this ctx (or of the last failed xfb_create when ctx == NULL). */
+const char* xfb_last_error(const xfb_ctx* ctx);
+
+/* Run all work of this ctx on an existing cudaStream_t (NULL = the ctx's own stream). */
+int xfb_set_stream(xfb_ctx* ctx, void* cuda_stream);
+
+/* Replaces the body of XFextractor::operator() up to the host packing loop
+ * (src/XFextractor.cc:250-316: parseInput, preprocessTensor, XFeatModel::forward, normalize,
+ * getKptsHeatmap, NMS, score, top-k, descriptor sampling, L2-normalise, valid filter).
+ *   gray   : 8-bit single channel image, h rows of `stride` bytes (CV_8UC1, :257)
+ *   topk   : nfeatures;  nms_thr: 0.05 in the reference (:277)
+ * Outputs, sorted by score descending (ties: row-major pixel index ascending):
+ *   n_valid[1]        number of keypoints with score > 0 among the top-k (<= topk)
+ *   kpt_xy[topk*2]    (x, y) integer pixel coordinates in the internally resized
+ *                     (multiple-of-32) frame, as float -- the reference never rescales them
+ *                     (src/XFextractor.cc:304-305 multiplies int64 by trunc(ratio) = 1)
+ *   score[topk], desc[topk*64]; entries >= n_valid are zero.
+ * Synchronous: results are in the host buffers on return. */
+int xfb_extract(xfb_ctx* ctx, const uint8_t* gray, int h, int w, int stride, int topk, float nms_thr, int32_t* n_valid,
+                float* kpt_xy, float* score, float* desc);
+
+/* `batch` frames of identical size per call; frame i starts at gray + i*frame_stride.  BatchNorm /
+ * InstanceNorm statistics stay per frame (the reference is batch-1, src/XFeat.cc:19 train mode),
+ * so results equal `batch` xfb_extract calls.  Output arrays are [batch] / [batch*topk*..]. */
+int xfb_extract_batch(xfb_ctx* ctx, const uint8_t* gray, int batch, size_t frame_stride, int h, int w, int stride, int topk,
+                      float nms_thr, int32_t* n_valid, float* kpt_xy, float* score, float* desc);
+
+/* Same with every pointer in DEVICE memory; asynchronous on the ctx stream (no host sync). */
+int xfb_extract_batch_device(xfb_ctx* ctx, const uint8_t* d_gray, int batch, size_t frame_stride, int h, int w, int stride,
+                             int topk, float nms_thr, int32_t* d_n_valid, float* d_kpt_xy, float* d_score, float* d_desc);
+
+/* Replaces ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2242-2250) for all pairs:
+ * out[i*n2 + j] = int(float(||A_i - B_j||^2) * 512), A [n1,64], B [n2,64] fp32 rows
+ * (cv::Mat CV_32F descriptor rows).  Bit-exact w.r.t. oracle/matcher_oracle.c. */
+int xfb_distance_matrix(xfb_ctx* ctx, const float* A, int n1, const float* B, int n2, int32_t* out);
+int xfb_distance_matrix_device(xfb_ctx* ctx, const float* d_A, int n1, const float* d_B, int n2, int32_t* d_out);
+
+/* Brute-force nearest / second-nearest search with the reference's update rule
+ * (src/ORBmatcher.cc:476-486, :884-894; lowest index wins ties), fused with the distance.
+ *   group_a/group_b : nullable; when given only pairs with equal ids compete (the vocabulary-node
+ *                     gating of SearchByBoW / SearchForTriangulation, src/ORBmatcher.cc:430-436)
+ *   init_dist       : initial best/second value (256 in SearchByBoW :450, INT_MAX in
+ *                     SearchForInitialization :860)
+ * Outputs: best_idx[n1] (-1 = none), best_dist[n1], second_dist[n1]; best_idx_rev[n2] /
+ * best_dist_rev[n2] = the same argmin taken column-wise (for mutual-NN checks, the spec of the
+ * commented-out ORBmatcher::match, src/ORBmatcher.cc:340-406).  Any output may be NULL. */
+int xfb_match(xfb_ctx* ctx, const float* A, int n1, const float* B, int n2, const int32_t* group_a, const int32_t* group_b,
+              int init_dist, int32_t* best_idx, int32_t* best_dist, int32_t* second_dist, int32_t* best_idx_rev,
+              int32_t* best_dist_rev);
+int xfb_match_device(xfb_ctx* ctx, const float* d_A, int n1, const float* d_B, int n2, const int32_t* d_group_a,
+                     const int32_t* d_group_b, int init_dist, int32_t* d_best_idx, int32_t* d_best_dist, int32_t* d_second_dist,
+                     int32_t* d_best_idx_rev, int32_t* d_best_dist_rev);
+
+/* ---- introspection (used by the parity tests and bench.py) ------------------------------- */
+
+/* Copies an intermediate of the last extract call to the host as fp32.  `name` is a reference
+ * module path ("block1.0", ..., "block5.3", "block_fusion.0", "heatmap_head.1", ... = the RAW conv
+ * output of that BasicLayer, NHWC; "xn", "pyramid_sum", "feats", "H1", "K1h").  dims[4] receives
+ * {H, W, C, 0}.  Returns the element count, or a negative xfb_status. */
+long xfb_debug_read(xfb_ctx* ctx, const char* name, int frame, float* host_out, size_t capacity, int32_t* dims);
+/* Per-(frame, channel) batch statistics (mean, 1/sqrt(var+eps)) of a BasicLayer; out [2*C]. */
+long xfb_debug_read_stats(xfb_ctx* ctx, const char* name, int frame, float* host_out, size_t capacity);
+/* Overwrites a dense map ("feats" [h,w,64] NHWC, "H1" [h,w], "K1h" [H,W]) of frame 0 and re-runs
+ * only the discrete post-processing (NMS, score, top-k, descriptors) on it, for bit-exact tests
+ * on oracle-provided inputs.  Inputs are host fp32; outputs as in xfb_extract. */
+int xfb_debug_post(xfb_ctx* ctx, int H, int W, const float* feats, const float* H1, const float* K1h, int topk, float nms_thr,
+                   int32_t* n_valid, float* kpt_xy, float* score, float* desc);
+/* Number of NMS candidates (score > 0) of `frame` in the last extract call. */
+int xfb_debug_candidates(xfb_ctx* ctx, int frame);
+/* Total number of kernels this ctx has launched so far. */
+long xfb_launch_count(const xfb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XFEAT_B200_H_ */

@@ -1,0 +1,439 @@
+// api.cu -- context management, the extract pipeline and the C-ABI of libxfeat_b200.so.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "xfb_internal.h"
+
+namespace xfb {
+
+static std::mutex g_err_mu;
+static std::string g_err;
+void set_global_error(const std::string& s) {
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  g_err = s;
+}
+
+// ---- weight blob (tools/convert_weights.py) --------------------------------------------------------
+#pragma pack(push, 1)
+struct BlobEntry {
+  char name[48];
+  uint32_t ndim;
+  uint32_t dims[4];
+  uint64_t offset;
+  uint64_t nbytes;
+};
+#pragma pack(pop)
+static_assert(sizeof(BlobEntry) == 48 + 4 + 16 + 8 + 8, "blob table entry layout");
+
+static const float* blob_find(const uint8_t* blob, size_t n, const std::string& name, size_t expect_elems) {
+  if (n < 16 || std::memcmp(blob, "XFBW", 4) != 0) return nullptr;
+  uint32_t version, count;
+  std::memcpy(&version, blob + 4, 4);
+  std::memcpy(&count, blob + 8, 4);
+  if (version != 1 || 16 + (size_t)count * sizeof(BlobEntry) > n) return nullptr;
+  for (uint32_t i = 0; i < count; ++i) {
+    BlobEntry e;
+    std::memcpy(&e, blob + 16 + (size_t)i * sizeof(BlobEntry), sizeof(e));
+    char nm[49];
+    std::memcpy(nm, e.name, 48);
+    nm[48] = 0;
+    if (name == nm) {
+      if (e.offset + e.nbytes > n || e.nbytes != expect_elems * 4 || (e.offset & 3)) return nullptr;
+      return reinterpret_cast<const float*>(blob + e.offset);
+    }
+  }
+  return nullptr;
+}
+
+static int dev_alloc(Ctx* c, void** p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+  if (e != cudaSuccess) {
+    c->err = std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e);
+    return XFB_ERR_NOMEM;
+  }
+  return XFB_OK;
+}
+#define XFB_ALLOC(ctx, ptr, bytes)                                         \
+  do {                                                                     \
+    int _r = dev_alloc((ctx), reinterpret_cast<void**>(&(ptr)), (bytes)); \
+    if (_r != XFB_OK) return _r;                                           \
+  } while (0)
+
+static int load_weights(Ctx* c, const uint8_t* blob, size_t n) {
+  for (int L = 0; L < L_NUM; ++L) {
+    const LayerSpec& sp = kLayers[L];
+    const bool is_basic = L < L_NUM_BN;
+    const std::string wname = std::string(sp.ref_name) + (is_basic ? ".layer.0.weight" : ".weight");
+    const size_t kk = (size_t)sp.ks * sp.ks, elems = (size_t)sp.cout * sp.cin * kk;
+    const float* src = blob_find(blob, n, wname, elems);
+    if (!src) { c->err = "weight blob: missing or malformed tensor " + wname; return XFB_ERR_WEIGHTS; }
+    // OIHW -> [ky*KS+kx][ci][co]
+    std::vector<float> packed(elems);
+    for (int co = 0; co < sp.cout; ++co)
+      for (int ci = 0; ci < sp.cin; ++ci)
+        for (size_t k = 0; k < kk; ++k) packed[(k * sp.cin + ci) * sp.cout + co] = src[((size_t)co * sp.cin + ci) * kk + k];
+    XFB_ALLOC(c, c->w[L], elems * 4);
+    XFB_CUDA_OK(c, cudaMemcpy(c->w[L], packed.data(), elems * 4, cudaMemcpyHostToDevice));
+    if (!is_basic) {
+      const std::string bname = std::string(sp.ref_name) + ".bias";
+      const float* bsrc = blob_find(blob, n, bname, sp.cout);
+      if (!bsrc) { c->err = "weight blob: missing or malformed tensor " + bname; return XFB_ERR_WEIGHTS; }
+      XFB_ALLOC(c, c->bias[L], (size_t)sp.cout * 4);
+      XFB_CUDA_OK(c, cudaMemcpy(c->bias[L], bsrc, (size_t)sp.cout * 4, cudaMemcpyHostToDevice));
+    }
+  }
+  return XFB_OK;
+}
+
+static int alloc_buffers(Ctx* c) {
+  const size_t B = c->max_batch;
+  const size_t H = (size_t)(c->max_h / 32) * 32, W = (size_t)(c->max_w / 32) * 32;
+  const size_t HW = H * W;
+  XFB_ALLOC(c, c->d_gray, B * (size_t)c->max_h * c->max_w);
+  XFB_ALLOC(c, c->xraw, B * HW * 4);
+  XFB_ALLOC(c, c->xn, B * HW * 4);
+  XFB_ALLOC(c, c->avg4, B * (HW / 16) * 4);
+  for (int L = 0; L < L_NUM; ++L) {
+    if (L == L_KP_3 || L == L_SKIP) continue;
+    const LayerSpec& sp = kLayers[L];
+    const size_t px = (H >> sp.lvl_out) * (W >> sp.lvl_out);
+    XFB_ALLOC(c, c->act[L], B * px * sp.cout * 4);
+    if (L < L_NUM_BN) {
+      XFB_ALLOC(c, c->bn[L].mean, B * sp.cout * 4);
+      XFB_ALLOC(c, c->bn[L].rstd, B * sp.cout * 4);
+    }
+  }
+  XFB_ALLOC(c, c->pyr, B * (HW / 64) * 64 * 4);
+  XFB_ALLOC(c, c->k1h, B * HW * 4);
+  XFB_ALLOC(c, c->in_mean, B * 4);
+  XFB_ALLOC(c, c->in_rstd, B * 4);
+  size_t pe = conv_part_elems((int)H, (int)W);
+  const size_t prep_pe = ((HW + 2047) / 2048) * 2;
+  if (prep_pe > pe) pe = prep_pe;
+  c->part_elems = pe;
+  XFB_ALLOC(c, c->part, B * pe * sizeof(double));
+  XFB_ALLOC(c, c->ticket, B * 4);
+  XFB_CUDA_OK(c, cudaMemset(c->ticket, 0, B * 4));
+  XFB_ALLOC(c, c->cand, B * HW * 8);
+  XFB_ALLOC(c, c->cand_count, B * 4);
+  XFB_ALLOC(c, c->cand_count_last, B * 4);
+  XFB_CUDA_OK(c, cudaMemset(c->cand_count, 0, B * 4));
+  XFB_CUDA_OK(c, cudaMemset(c->cand_count_last, 0, B * 4));
+  const size_t K = c->max_topk;
+  XFB_ALLOC(c, c->o_nvalid, B * 4);
+  XFB_ALLOC(c, c->o_xy, B * K * 2 * 4);
+  XFB_ALLOC(c, c->o_score, B * K * 4);
+  XFB_ALLOC(c, c->o_desc, B * K * 64 * 4);
+  return XFB_OK;
+}
+
+static int ensure_match_scratch(Ctx* c, int n1, int n2, bool want_matrix) {
+  const int n = n1 > n2 ? n1 : n2;
+  if (n > c->m_cap) {
+    float** fp[2] = {&c->m_a, &c->m_b};
+    for (auto p : fp) { if (*p) cudaFree(*p); *p = nullptr; }
+    int32_t** ip[] = {&c->m_ga, &c->m_gb, &c->m_out[0], &c->m_out[1], &c->m_out[2], &c->m_out[3], &c->m_out[4], &c->m_rowpart,
+                      &c->m_colpart, &c->m_matrix};
+    for (auto p : ip) { if (*p) cudaFree(*p); *p = nullptr; }
+    const size_t cap = (size_t)((n + 63) / 64) * 64;
+    XFB_ALLOC(c, c->m_a, cap * 64 * 4);
+    XFB_ALLOC(c, c->m_b, cap * 64 * 4);
+    XFB_ALLOC(c, c->m_ga, cap * 4);
+    XFB_ALLOC(c, c->m_gb, cap * 4);
+    for (int i = 0; i < 5; ++i) XFB_ALLOC(c, c->m_out[i], cap * 4);
+    XFB_ALLOC(c, c->m_rowpart, cap * (cap / 64) * 3 * 4);
+    XFB_ALLOC(c, c->m_colpart, cap * (cap / 64) * 2 * 4);
+    c->m_cap = (int)cap;
+  }
+  if (want_matrix && !c->m_matrix) XFB_ALLOC(c, c->m_matrix, (size_t)c->m_cap * c->m_cap * 4);
+  return XFB_OK;
+}
+
+// ---- the forward pipeline (XFeatModel::forward, src/XFeat.cc:135-173, then :273-316) -----------------
+static int run_dense(Ctx* c, const uint8_t* d_gray, size_t frame_stride, int stride) {
+  XFB_CUDA_OK(c, launch_prep(c, d_gray, frame_stride, stride));
+  static const int order1[] = {L_B1_0, L_B1_1, L_B1_2, L_B1_3, L_B2_0, L_B2_1, L_B3_0, L_B3_1, L_B3_2,
+                               L_B4_0, L_B4_1, L_B4_2, L_B5_0, L_B5_1, L_B5_2, L_B5_3};
+  for (int L : order1) XFB_CUDA_OK(c, launch_conv_layer(c, L));
+  XFB_CUDA_OK(c, launch_pyramid(c));
+  static const int order2[] = {L_F_0, L_F_1, L_F_2, L_HM_0, L_HM_1};
+  for (int L : order2) XFB_CUDA_OK(c, launch_conv_layer(c, L));
+  XFB_CUDA_OK(c, launch_heatmap_out(c));
+  static const int order3[] = {L_KP_0, L_KP_1, L_KP_2};
+  for (int L : order3) XFB_CUDA_OK(c, launch_conv_layer(c, L));
+  XFB_CUDA_OK(c, launch_keypoint_out(c));
+  return XFB_OK;
+}
+
+static int check_extract_args(Ctx* c, int batch, int h, int w, int stride, int topk) {
+  if (!c) return XFB_ERR_ARG;
+  if (h <= 0 || w <= 0 || batch <= 0) { c->err = "empty image"; return XFB_ERR_EMPTY; }
+  if (h < 32 || w < 32 || h > c->max_h || w > c->max_w || stride < w || batch > c->max_batch || topk < 1 || topk > c->max_topk) {
+    c->err = "extract: size/batch/topk outside the limits given to xfb_create (image must be >= 32x32)";
+    return XFB_ERR_ARG;
+  }
+  return XFB_OK;
+}
+
+static int extract_device(Ctx* c, const uint8_t* d_gray, int batch, size_t frame_stride, int h, int w, int stride, int topk,
+                          float nms_thr, int32_t* d_nvalid, float* d_xy, float* d_score, float* d_desc) {
+  XFB_CUDA_OK(c, cudaSetDevice(c->device));
+  c->B = batch; c->in_h = h; c->in_w = w;
+  c->H = (h / 32) * 32; c->W = (w / 32) * 32;
+  int r = run_dense(c, d_gray, frame_stride, stride);
+  if (r != XFB_OK) return r;
+  XFB_CUDA_OK(c, launch_post(c, topk, nms_thr, d_nvalid, d_xy, d_score, d_desc));
+  return XFB_OK;
+}
+
+}  // namespace xfb
+
+using namespace xfb;
+
+extern "C" {
+
+int xfb_create(xfb_ctx** out, const void* weights_blob, size_t n, int device, int max_h, int max_w, int max_batch, int max_topk) {
+  if (!out || !weights_blob || max_h < 32 || max_w < 32 || max_batch < 1 || max_topk < 1 || max_topk > 8192) {
+    set_global_error("xfb_create: bad argument");
+    return XFB_ERR_ARG;
+  }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || device < 0 || device >= ndev) {
+    set_global_error(std::string("xfb_create: no usable CUDA device (there is no CPU fallback): ") +
+                     (e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range"));
+    return XFB_ERR_CUDA;
+  }
+  xfb_ctx* c = new xfb_ctx();
+  c->device = device; c->max_h = max_h; c->max_w = max_w; c->max_batch = max_batch; c->max_topk = max_topk;
+  int r = XFB_OK;
+  do {
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { c->err = cudaGetErrorString(e); r = XFB_ERR_CUDA; break; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { c->err = cudaGetErrorString(e); r = XFB_ERR_CUDA; break; }
+    if (prop.major != 10) {
+      c->err = "libxfeat_b200 is built for sm_100a only; device reports sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+      r = XFB_ERR_CUDA;
+      break;
+    }
+    if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { c->err = cudaGetErrorString(e); r = XFB_ERR_CUDA; break; }
+    c->stream = c->own_stream;
+    if ((r = load_weights(c, static_cast<const uint8_t*>(weights_blob), n)) != XFB_OK) break;
+    if ((r = alloc_buffers(c)) != XFB_OK) break;
+  } while (0);
+  if (r != XFB_OK) {
+    set_global_error(c->err);
+    xfb_destroy(c);
+    return r;
+  }
+  *out = c;
+  return XFB_OK;
+}
+
+void xfb_destroy(xfb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+  auto fr = [](void* p) { if (p) cudaFree(p); };
+  for (int L = 0; L < L_NUM; ++L) { fr(c->w[L]); fr(c->bias[L]); fr(c->act[L]); }
+  for (int L = 0; L < L_NUM_BN; ++L) { fr(c->bn[L].mean); fr(c->bn[L].rstd); }
+  fr(c->d_gray); fr(c->xraw); fr(c->xn); fr(c->avg4); fr(c->pyr); fr(c->k1h); fr(c->in_mean); fr(c->in_rstd); fr(c->part);
+  fr(c->ticket); fr(c->cand); fr(c->cand_count); fr(c->cand_count_last); fr(c->o_nvalid); fr(c->o_xy); fr(c->o_score); fr(c->o_desc);
+  fr(c->m_a); fr(c->m_b); fr(c->m_ga); fr(c->m_gb); fr(c->m_rowpart); fr(c->m_colpart); fr(c->m_matrix);
+  for (int i = 0; i < 5; ++i) fr(c->m_out[i]);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+const char* xfb_last_error(const xfb_ctx* c) {
+  if (c) return c->err.c_str();
+  static thread_local std::string copy;
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  copy = g_err;
+  return copy.c_str();
+}
+
+int xfb_set_stream(xfb_ctx* c, void* cuda_stream) {
+  if (!c) return XFB_ERR_ARG;
+  c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+  return XFB_OK;
+}
+
+int xfb_extract_batch_device(xfb_ctx* c, const uint8_t* d_gray, int batch, size_t frame_stride, int h, int w, int stride, int topk,
+                             float nms_thr, int32_t* d_n_valid, float* d_kpt_xy, float* d_score, float* d_desc) {
+  int r = check_extract_args(c, batch, h, w, stride, topk);
+  if (r != XFB_OK) return r;
+  if (!d_gray || !d_n_valid || !d_kpt_xy || !d_score || !d_desc) { c->err = "extract: null pointer"; return XFB_ERR_ARG; }
+  return extract_device(c, d_gray, batch, frame_stride, h, w, stride, topk, nms_thr, d_n_valid, d_kpt_xy, d_score, d_desc);
+}
+
+int xfb_extract_batch(xfb_ctx* c, const uint8_t* gray, int batch, size_t frame_stride, int h, int w, int stride, int topk,
+                      float nms_thr, int32_t* n_valid, float* kpt_xy, float* score, float* desc) {
+  int r = check_extract_args(c, batch, h, w, stride, topk);
+  if (r != XFB_OK) return r;
+  if (!gray || !n_valid || !kpt_xy || !score || !desc) { c->err = "extract: null pointer"; return XFB_ERR_ARG; }
+  XFB_CUDA_OK(c, cudaSetDevice(c->device));
+  // host -> device: rows are packed to `w` bytes on the device
+  const size_t dev_fs = (size_t)h * w;
+  for (int b = 0; b < batch; ++b)
+    XFB_CUDA_OK(c, cudaMemcpy2DAsync(c->d_gray + b * dev_fs, w, gray + b * frame_stride, stride, w, h, cudaMemcpyHostToDevice, c->stream));
+  r = extract_device(c, c->d_gray, batch, dev_fs, h, w, w, topk, nms_thr, c->o_nvalid, c->o_xy, c->o_score, c->o_desc);
+  if (r != XFB_OK) return r;
+  const size_t K = topk;
+  XFB_CUDA_OK(c, cudaMemcpyAsync(n_valid, c->o_nvalid, (size_t)batch * 4, cudaMemcpyDeviceToHost, c->stream));
+  XFB_CUDA_OK(c, cudaMemcpyAsync(kpt_xy, c->o_xy, batch * K * 2 * 4, cudaMemcpyDeviceToHost, c->stream));
+  XFB_CUDA_OK(c, cudaMemcpyAsync(score, c->o_score, batch * K * 4, cudaMemcpyDeviceToHost, c->stream));
+  XFB_CUDA_OK(c, cudaMemcpyAsync(desc, c->o_desc, batch * K * 64 * 4, cudaMemcpyDeviceToHost, c->stream));
+  XFB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return XFB_OK;
+}
+
+int xfb_extract(xfb_ctx* c, const uint8_t* gray, int h, int w, int stride, int topk, float nms_thr, int32_t* n_valid, float* kpt_xy,
+                float* score, float* desc) {
+  return xfb_extract_batch(c, gray, 1, (size_t)h * (size_t)(stride > 0 ? stride : 0), h, w, stride, topk, nms_thr, n_valid, kpt_xy, score, desc);
+}
+
+int xfb_distance_matrix_device(xfb_ctx* c, const float* d_A, int n1, const float* d_B, int n2, int32_t* d_out) {
+  if (!c) return XFB_ERR_ARG;
+  if (n1 < 0 || n2 < 0 || (n1 && !d_A) || (n2 && !d_B) || (n1 && n2 && !d_out)) { c->err = "distance_matrix: bad argument"; return XFB_ERR_ARG; }
+  XFB_CUDA_OK(c, cudaSetDevice(c->device));
+  XFB_CUDA_OK(c, launch_distance_matrix(c, d_A, n1, d_B, n2, d_out));
+  return XFB_OK;
+}
+
+int xfb_distance_matrix(xfb_ctx* c, const float* A, int n1, const float* B, int n2, int32_t* out) {
+  if (!c) return XFB_ERR_ARG;
+  if (n1 < 0 || n2 < 0 || (n1 && !A) || (n2 && !B) || (n1 && n2 && !out)) { c->err = "distance_matrix: bad argument"; return XFB_ERR_ARG; }
+  if (n1 == 0 || n2 == 0) return XFB_OK;
+  XFB_CUDA_OK(c, cudaSetDevice(c->device));
+  int r = ensure_match_scratch(c, n1, n2, true);
+  if (r != XFB_OK) return r;
+  XFB_CUDA_OK(c, cudaMemcpyAsync(c->m_a, A, (size_t)n1 * 256, cudaMemcpyHostToDevice, c->stream));
+  XFB_CUDA_OK(c, cudaMemcpyAsync(c->m_b, B, (size_t)n2 * 256, cudaMemcpyHostToDevice, c->stream));
+  XFB_CUDA_OK(c, launch_distance_matrix(c, c->m_a, n1, c->m_b, n2, c->m_matrix));
+  XFB_CUDA_OK(c, cudaMemcpyAsync(out, c->m_matrix, (size_t)n1 * n2 * 4, cudaMemcpyDeviceToHost, c->stream));
+  XFB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return XFB_OK;
+}
+
+int xfb_match_device(xfb_ctx* c, const float* d_A, int n1, const float* d_B, int n2, const int32_t* d_ga, const int32_t* d_gb,
+                     int init_dist, int32_t* bi, int32_t* bd, int32_t* sd, int32_t* ri, int32_t* rd) {
+  if (!c) return XFB_ERR_ARG;
+  if (n1 < 0 || n2 < 0 || (n1 && !d_A) || (n2 && !d_B) || ((d_ga == nullptr) != (d_gb == nullptr))) { c->err = "match: bad argument"; return XFB_ERR_ARG; }
+  XFB_CUDA_OK(c, cudaSetDevice(c->device));
+  int r = ensure_match_scratch(c, n1, n2, false);
+  if (r != XFB_OK) return r;
+  XFB_CUDA_OK(c, launch_match(c, d_A, n1, d_B, n2, d_ga, d_gb, init_dist, bi, bd, sd, ri, rd));
+  return XFB_OK;
+}
+
+int xfb_match(xfb_ctx* c, const float* A, int n1, const float* B, int n2, const int32_t* ga, const int32_t* gb, int init_dist,
+              int32_t* best_idx, int32_t* best_dist, int32_t* second_dist, int32_t* best_idx_rev, int32_t* best_dist_rev) {
+  if (!c) return XFB_ERR_ARG;
+  if (n1 < 0 || n2 < 0 || (n1 && !A) || (n2 && !B) || ((ga == nullptr) != (gb == nullptr))) { c->err = "match: bad argument"; return XFB_ERR_ARG; }
+  XFB_CUDA_OK(c, cudaSetDevice(c->device));
+  int r = ensure_match_scratch(c, n1, n2, false);
+  if (r != XFB_OK) return r;
+  if (n1) XFB_CUDA_OK(c, cudaMemcpyAsync(c->m_a, A, (size_t)n1 * 256, cudaMemcpyHostToDevice, c->stream));
+  if (n2) XFB_CUDA_OK(c, cudaMemcpyAsync(c->m_b, B, (size_t)n2 * 256, cudaMemcpyHostToDevice, c->stream));
+  if (ga) {
+    if (n1) XFB_CUDA_OK(c, cudaMemcpyAsync(c->m_ga, ga, (size_t)n1 * 4, cudaMemcpyHostToDevice, c->stream));
+    if (n2) XFB_CUDA_OK(c, cudaMemcpyAsync(c->m_gb, gb, (size_t)n2 * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  XFB_CUDA_OK(c, launch_match(c, c->m_a, n1, c->m_b, n2, ga ? c->m_ga : nullptr, ga ? c->m_gb : nullptr, init_dist, c->m_out[0],
+                              c->m_out[1], c->m_out[2], c->m_out[3], c->m_out[4]));
+  int32_t* host[5] = {best_idx, best_dist, second_dist, best_idx_rev, best_dist_rev};
+  for (int i = 0; i < 5; ++i) {
+    const int cnt = i < 3 ? n1 : n2;
+    if (host[i] && cnt) XFB_CUDA_OK(c, cudaMemcpyAsync(host[i], c->m_out[i], (size_t)cnt * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  XFB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return XFB_OK;
+}
+
+// ---- introspection ------------------------------------------------------------------------------------
+static int find_layer(const char* name) {
+  for (int L = 0; L < L_NUM; ++L)
+    if (std::strcmp(kLayers[L].ref_name, name) == 0) return L;
+  return -1;
+}
+
+long xfb_debug_read(xfb_ctx* c, const char* name, int frame, float* host_out, size_t capacity, int32_t* dims) {
+  if (!c || !name || !host_out || frame < 0 || frame >= c->B) return XFB_ERR_ARG;
+  const float* src = nullptr;
+  int h = 0, w = 0, ch = 1;
+  const std::string nm(name);
+  if (nm == "xn") { src = c->xn; h = c->H; w = c->W; }
+  else if (nm == "x_pre") { src = c->xraw; h = c->H; w = c->W; }
+  else if (nm == "avg4") { src = c->avg4; h = c->H >> 2; w = c->W >> 2; }
+  else if (nm == "K1h") { src = c->k1h; h = c->H; w = c->W; }
+  else if (nm == "pyramid_sum") { src = c->pyr; h = c->H >> 3; w = c->W >> 3; ch = 64; }
+  else if (nm == "feats") { src = c->act[L_F_2]; h = c->H >> 3; w = c->W >> 3; ch = 64; }
+  else if (nm == "H1") { src = c->act[L_HM_2]; h = c->H >> 3; w = c->W >> 3; }
+  else {
+    const int L = find_layer(name);
+    if (L < 0 || L >= L_NUM_BN) { c->err = "debug_read: unknown tensor " + nm; return XFB_ERR_ARG; }
+    src = c->act[L]; h = c->H >> kLayers[L].lvl_out; w = c->W >> kLayers[L].lvl_out; ch = kLayers[L].cout;
+  }
+  const size_t elems = (size_t)h * w * ch;
+  if (dims) { dims[0] = h; dims[1] = w; dims[2] = ch; dims[3] = 0; }
+  if (elems > capacity) { c->err = "debug_read: capacity too small"; return XFB_ERR_ARG; }
+  XFB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  XFB_CUDA_OK(c, cudaMemcpy(host_out, src + (size_t)frame * elems, elems * 4, cudaMemcpyDeviceToHost));
+  return (long)elems;
+}
+
+long xfb_debug_read_stats(xfb_ctx* c, const char* name, int frame, float* host_out, size_t capacity) {
+  if (!c || !name || !host_out || frame < 0 || frame >= c->B) return XFB_ERR_ARG;
+  const float *m = nullptr, *r = nullptr;
+  int ch = 1;
+  if (std::strcmp(name, "xn") == 0) { m = c->in_mean; r = c->in_rstd; }
+  else {
+    const int L = find_layer(name);
+    if (L < 0 || L >= L_NUM_BN) { c->err = std::string("debug_read_stats: unknown layer ") + name; return XFB_ERR_ARG; }
+    m = c->bn[L].mean; r = c->bn[L].rstd; ch = kLayers[L].cout;
+  }
+  if ((size_t)2 * ch > capacity) return XFB_ERR_ARG;
+  XFB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  XFB_CUDA_OK(c, cudaMemcpy(host_out, m + (size_t)frame * ch, (size_t)ch * 4, cudaMemcpyDeviceToHost));
+  XFB_CUDA_OK(c, cudaMemcpy(host_out + ch, r + (size_t)frame * ch, (size_t)ch * 4, cudaMemcpyDeviceToHost));
+  return 2L * ch;
+}
+
+int xfb_debug_post(xfb_ctx* c, int H, int W, const float* feats, const float* H1, const float* K1h, int topk, float nms_thr,
+                   int32_t* n_valid, float* kpt_xy, float* score, float* desc) {
+  if (!c || !feats || !H1 || !K1h || !n_valid || !kpt_xy || !score || !desc) return XFB_ERR_ARG;
+  if (H % 32 || W % 32 || H < 32 || W < 32 || H > c->max_h || W > c->max_w || topk < 1 || topk > c->max_topk) { c->err = "debug_post: bad size"; return XFB_ERR_ARG; }
+  XFB_CUDA_OK(c, cudaSetDevice(c->device));
+  c->B = 1; c->H = H; c->W = W; c->in_h = H; c->in_w = W;
+  const size_t cells = (size_t)(H / 8) * (W / 8);
+  XFB_CUDA_OK(c, cudaMemcpyAsync(c->act[L_F_2], feats, cells * 64 * 4, cudaMemcpyHostToDevice, c->stream));
+  XFB_CUDA_OK(c, cudaMemcpyAsync(c->act[L_HM_2], H1, cells * 4, cudaMemcpyHostToDevice, c->stream));
+  XFB_CUDA_OK(c, cudaMemcpyAsync(c->k1h, K1h, (size_t)H * W * 4, cudaMemcpyHostToDevice, c->stream));
+  XFB_CUDA_OK(c, launch_post(c, topk, nms_thr, c->o_nvalid, c->o_xy, c->o_score, c->o_desc));
+  const size_t K = topk;
+  XFB_CUDA_OK(c, cudaMemcpyAsync(n_valid, c->o_nvalid, 4, cudaMemcpyDeviceToHost, c->stream));
+  XFB_CUDA_OK(c, cudaMemcpyAsync(kpt_xy, c->o_xy, K * 2 * 4, cudaMemcpyDeviceToHost, c->stream));
+  XFB_CUDA_OK(c, cudaMemcpyAsync(score, c->o_score, K * 4, cudaMemcpyDeviceToHost, c->stream));
+  XFB_CUDA_OK(c, cudaMemcpyAsync(desc, c->o_desc, K * 64 * 4, cudaMemcpyDeviceToHost, c->stream));
+  XFB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return XFB_OK;
+}
+
+int xfb_debug_candidates(xfb_ctx* c, int frame) {
+  if (!c || frame < 0 || frame >= c->max_batch) return XFB_ERR_ARG;
+  int v = 0;
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return XFB_ERR_CUDA;
+  if (cudaMemcpy(&v, c->cand_count_last + frame, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return XFB_ERR_CUDA;
+  return v;
+}
+
+long xfb_launch_count(const xfb_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,250 @@
+// post.cu -- discrete post-processing of XFextractor::operator() (src/XFextractor.cc:273-316):
+//   nms_score : 5x5 max-pool NMS (XFextractor::NMS, :219-248: x == local_max && x > thr) fused with the
+//               reliability score nearest(K1h)(kp) * bilinear(H1)(kp) (:280) and the (0,0) mask (:281-282);
+//               every surviving candidate is appended as one sortable 64-bit key
+//   topk      : per-frame exact top-k by an 8-pass MSB radix select + bitonic sort (:285-295).  The
+//               reference's argsort is unstable; this build's order is score descending, then row-major
+//               pixel index ascending (SURVEY.md hard part (c)) -- the key encodes exactly that.
+//   describe  : InterpolateSparse2d bilinear on the channel-normalised feature map, then L2-normalise
+//               (:273, :298-301); one warp per keypoint.
+// grid_sample geometry follows ATen's vectorised CPU kernel (the path the reference takes for fp32):
+//   g = 2*(p/(S-1)) - 1 (InterpolateSparse2d::normgrid, src/XFeat.cc:181-186),
+//   src = (g + 1) * (S_map / 2) - 0.5, zero padding, align_corners = false.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "xfb_internal.h"
+
+namespace xfb {
+
+typedef unsigned long long u64;
+
+// Rounding sequence pinned against ATen's AVX grid_sampler (tools/pin_gridsample.py): the
+// un-normalisation is ONE fma, (g + 1) * (S_map / 2) - 0.5; explicit _rn intrinsics keep nvcc from
+// re-associating or contracting anything else.
+__device__ __forceinline__ float grid_src(int p, int full, int map) {
+  const float q = __fdiv_rn((float)p, (float)(full - 1));
+  const float g = __fsub_rn(__fmul_rn(2.0f, q), 1.0f);
+  return __fmaf_rn(__fadd_rn(g, 1.0f), __fdiv_rn((float)map, 2.0f), -0.5f);
+}
+// out = fma(se_v, se, fma(sw_v, sw, fma(ne_v, ne, nw_v * nw)))  -- the contraction ATen's kernel compiles to
+__device__ __forceinline__ float bilerp4(float nwv, float nev, float swv, float sev, float nw, float ne, float sw, float se) {
+  return __fmaf_rn(sev, se, __fmaf_rn(swv, sw, __fmaf_rn(nev, ne, __fmul_rn(nwv, nw))));
+}
+
+// bilinear sample of a single-channel map with zero padding
+__device__ __forceinline__ float bilinear1(const float* map, int mh, int mw, float sx, float sy) {
+  const float x0f = floorf(sx), y0f = floorf(sy);
+  const int x0 = (int)x0f, y0 = (int)y0f;
+  const float w = __fsub_rn(sx, x0f), e = __fsub_rn(1.0f, w), n = __fsub_rn(sy, y0f), s = __fsub_rn(1.0f, n);
+  const bool xin0 = x0 >= 0 && x0 < mw, xin1 = x0 + 1 >= 0 && x0 + 1 < mw;
+  const bool yin0 = y0 >= 0 && y0 < mh, yin1 = y0 + 1 >= 0 && y0 + 1 < mh;
+  const float nw = (xin0 && yin0) ? map[(size_t)y0 * mw + x0] : 0.f;
+  const float ne = (xin1 && yin0) ? map[(size_t)y0 * mw + x0 + 1] : 0.f;
+  const float sw = (xin0 && yin1) ? map[(size_t)(y0 + 1) * mw + x0] : 0.f;
+  const float se = (xin1 && yin1) ? map[(size_t)(y0 + 1) * mw + x0 + 1] : 0.f;
+  return bilerp4(nw, ne, sw, se, __fmul_rn(s, e), __fmul_rn(s, w), __fmul_rn(n, e), __fmul_rn(n, w));
+}
+
+constexpr int NMS_T = 32;
+__global__ void __launch_bounds__(NMS_T * NMS_T) nms_score_kernel(const float* k1h, const float* h1, int H, int W, float thr,
+                                                                  u64* cand, int* cand_count) {
+  __shared__ float tile[NMS_T + 4][NMS_T + 4];
+  const int b = blockIdx.z;
+  const float* img = k1h + (size_t)b * H * W;
+  const int x0 = blockIdx.x * NMS_T, y0 = blockIdx.y * NMS_T;
+  const int tid = threadIdx.y * NMS_T + threadIdx.x;
+  for (int i = tid; i < (NMS_T + 4) * (NMS_T + 4); i += NMS_T * NMS_T) {
+    const int ty = i / (NMS_T + 4), tx = i - ty * (NMS_T + 4);
+    const int gy = y0 + ty - 2, gx = x0 + tx - 2;
+    tile[ty][tx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? img[(size_t)gy * W + gx] : -CUDART_INF_F;
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const float v = tile[threadIdx.y + 2][threadIdx.x + 2];
+  if (!(v > thr)) return;
+  float m = v;
+#pragma unroll
+  for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 5; ++dx) m = fmaxf(m, tile[threadIdx.y + dy][threadIdx.x + dx]);
+  if (v != m) return;
+  if (x == 0 && y == 0) return;  // masked to -1 by the reference, never valid
+  // nearest(K1h)(kp): grid_sample nearest at full resolution (drops the last row / column)
+  const float nx = nearbyintf(grid_src(x, W, W)), ny = nearbyintf(grid_src(y, H, H));
+  float sn = 0.f;
+  if (nx >= 0.f && nx < (float)W && ny >= 0.f && ny < (float)H) sn = img[(size_t)(int)ny * W + (int)nx];
+  const int mh = H >> 3, mw = W >> 3;
+  const float sb = bilinear1(h1 + (size_t)b * mh * mw, mh, mw, grid_src(x, W, mw), grid_src(y, H, mh));
+  const float score = __fmul_rn(sn, sb);
+  if (!(score > 0.f)) return;  // `valid = scores > 0`, src/XFextractor.cc:313
+  const unsigned int lin = (unsigned int)(y * W + x);
+  const u64 key = ((u64)__float_as_uint(score) << 32) | (u64)(0xFFFFFFFFu - lin);
+  const int pos = atomicAdd(cand_count + b, 1);
+  cand[(size_t)b * H * W + pos] = key;
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int TOPK_NT = 1024;
+__global__ void __launch_bounds__(TOPK_NT) topk_kernel(const u64* cand, int* cand_count, int* cand_count_last, int HW, int W,
+                                                       int topk, int sort_n /*pow2 >= topk*/, int32_t* n_valid, float* kpt_xy,
+                                                       float* score) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  u64* skeys = reinterpret_cast<u64*>(smem_raw);  // [sort_n]
+  __shared__ unsigned int hist[256];
+  __shared__ u64 s_prefix;
+  __shared__ int s_remaining;
+  __shared__ int s_fill;
+  const int b = blockIdx.x, t = threadIdx.x;
+  const u64* keys = cand + (size_t)b * HW;
+  const int N = cand_count[b];
+  const int K = N < topk ? N : topk;
+  u64 thresh = 0;  // select keys >= thresh
+  if (N > K) {
+    if (t == 0) { s_prefix = 0; s_remaining = K; }
+    u64 mask = 0;
+    for (int pass = 7; pass >= 0; --pass) {
+      for (int i = t; i < 256; i += TOPK_NT) hist[i] = 0;
+      __syncthreads();
+      const u64 prefix = s_prefix;
+      const int shift = pass * 8;
+      for (int i = t; i < N; i += TOPK_NT) {
+        const u64 k = keys[i];
+        if ((k & mask) == prefix) atomicAdd(&hist[(unsigned int)(k >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (t == 0) {
+        int rem = s_remaining;
+        int d = 255;
+        for (; d > 0; --d) {
+          const int hcount = (int)hist[d];
+          if (hcount >= rem) break;
+          rem -= hcount;
+        }
+        s_prefix = prefix | ((u64)d << shift);
+        s_remaining = rem;
+      }
+      mask |= (u64)255 << shift;
+      __syncthreads();
+    }
+    thresh = s_prefix;  // the K-th largest key (keys are unique)
+  }
+  if (t == 0) s_fill = 0;
+  for (int i = t; i < sort_n; i += TOPK_NT) skeys[i] = 0;
+  __syncthreads();
+  for (int i = t; i < N; i += TOPK_NT) {
+    const u64 k = keys[i];
+    if (k >= thresh) {
+      const int pos = atomicAdd(&s_fill, 1);
+      if (pos < sort_n) skeys[pos] = k;
+    }
+  }
+  __syncthreads();
+  // bitonic sort, descending
+  for (int size = 2; size <= sort_n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = t; i < (sort_n >> 1); i += TOPK_NT) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const u64 a = skeys[lo], c = skeys[hi];
+        if ((a < c) == desc) { skeys[lo] = c; skeys[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = t; i < topk; i += TOPK_NT) {
+    float sc = 0.f, fx = 0.f, fy = 0.f;
+    if (i < K) {
+      const u64 k = skeys[i];
+      sc = __uint_as_float((unsigned int)(k >> 32));
+      const unsigned int lin = 0xFFFFFFFFu - (unsigned int)(k & 0xFFFFFFFFu);
+      fx = (float)(lin % (unsigned int)W);
+      fy = (float)(lin / (unsigned int)W);
+    }
+    score[(size_t)b * topk + i] = sc;
+    kpt_xy[((size_t)b * topk + i) * 2] = fx;
+    kpt_xy[((size_t)b * topk + i) * 2 + 1] = fy;
+  }
+  if (t == 0) {
+    n_valid[b] = K;
+    cand_count_last[b] = N;
+    cand_count[b] = 0;  // re-arm for the next call
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// channel-normalised corner: feats[y][x][:] / max(||.||_2, 1e-12)  (F.normalize(M1, dim=1), :273)
+__device__ __forceinline__ float2 corner_unit(const float* fmap, int mh, int mw, int x, int y, int lane) {
+  if (x < 0 || x >= mw || y < 0 || y >= mh) return make_float2(0.f, 0.f);
+  const float2 v = *reinterpret_cast<const float2*>(fmap + ((size_t)y * mw + x) * 64 + lane * 2);
+  const float nrm = sqrtf(warp_sum(v.x * v.x + v.y * v.y));
+  const float den = fmaxf(nrm, 1e-12f);
+  return make_float2(__fdiv_rn(v.x, den), __fdiv_rn(v.y, den));
+}
+
+__global__ void __launch_bounds__(256) describe_kernel(const float* feats, int H, int W, int topk, const int32_t* n_valid,
+                                                       const float* kpt_xy, float* desc) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= topk) return;
+  float2 o = make_float2(0.f, 0.f);
+  if (i < n_valid[b]) {
+    const int mh = H >> 3, mw = W >> 3;
+    const float* fmap = feats + (size_t)b * mh * mw * 64;
+    const int px = (int)kpt_xy[((size_t)b * topk + i) * 2], py = (int)kpt_xy[((size_t)b * topk + i) * 2 + 1];
+    const float sx = grid_src(px, W, mw), sy = grid_src(py, H, mh);
+    const float x0f = floorf(sx), y0f = floorf(sy);
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const float w = __fsub_rn(sx, x0f), e = __fsub_rn(1.0f, w), n = __fsub_rn(sy, y0f), s = __fsub_rn(1.0f, n);
+    const float2 nw = corner_unit(fmap, mh, mw, x0, y0, lane);
+    const float2 ne = corner_unit(fmap, mh, mw, x0 + 1, y0, lane);
+    const float2 sw = corner_unit(fmap, mh, mw, x0, y0 + 1, lane);
+    const float2 se = corner_unit(fmap, mh, mw, x0 + 1, y0 + 1, lane);
+    const float wnw = __fmul_rn(s, e), wne = __fmul_rn(s, w), wsw = __fmul_rn(n, e), wse = __fmul_rn(n, w);
+    float2 v;
+    v.x = bilerp4(nw.x, ne.x, sw.x, se.x, wnw, wne, wsw, wse);
+    v.y = bilerp4(nw.y, ne.y, sw.y, se.y, wnw, wne, wsw, wse);
+    const float den = fmaxf(sqrtf(warp_sum(v.x * v.x + v.y * v.y)), 1e-12f);
+    o = make_float2(__fdiv_rn(v.x, den), __fdiv_rn(v.y, den));
+  }
+  *reinterpret_cast<float2*>(desc + ((size_t)b * topk + i) * 64 + lane * 2) = o;
+}
+
+static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+cudaError_t launch_post(Ctx* c, int topk, float nms_thr, int32_t* d_nvalid, float* d_xy, float* d_score, float* d_desc) {
+  const int H = c->H, W = c->W;
+  dim3 g1((W + NMS_T - 1) / NMS_T, (H + NMS_T - 1) / NMS_T, c->B);
+  nms_score_kernel<<<g1, dim3(NMS_T, NMS_T), 0, c->stream>>>(c->k1h, c->act[L_HM_2], H, W, nms_thr, c->cand, c->cand_count);
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int sort_n = next_pow2(topk < 2 ? 2 : topk);
+  const size_t smem = sizeof(u64) * (size_t)sort_n;
+  static unsigned long long attr_mask = 0;
+  if (!((attr_mask >> c->device) & 1ull)) {
+    e = cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * 8192));
+    if (e != cudaSuccess) return e;
+    attr_mask |= 1ull << c->device;
+  }
+  topk_kernel<<<c->B, TOPK_NT, smem, c->stream>>>(c->cand, c->cand_count, c->cand_count_last, H * W, W, topk, sort_n, d_nvalid, d_xy,
+                                                  d_score);
+  c->launches++;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  dim3 g3((topk + 7) / 8, c->B);
+  describe_kernel<<<g3, 256, 0, c->stream>>>(c->act[L_F_2], H, W, topk, d_nvalid, d_xy, d_desc);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+}  // namespace xfb

@@ -1,0 +1,139 @@
+// xfb_internal.h -- shared declarations of libxfeat_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "xfeat_b200.h"
+
+namespace xfb {
+
+// ---------------------------------------------------------------------------------------------
+// Layer table.  Every BasicLayer of the reference (src/XFeat.cc:41-90) in execution order.
+// ---------------------------------------------------------------------------------------------
+enum LayerId {
+  L_B1_0 = 0, L_B1_1, L_B1_2, L_B1_3,
+  L_B2_0, L_B2_1,
+  L_B3_0, L_B3_1, L_B3_2,
+  L_B4_0, L_B4_1, L_B4_2,
+  L_B5_0, L_B5_1, L_B5_2, L_B5_3,
+  L_F_0, L_F_1,
+  L_HM_0, L_HM_1,
+  L_KP_0, L_KP_1, L_KP_2,
+  L_NUM_BN,           // 23 BasicLayers (conv -> train-mode BN -> ReLU)
+  L_F_2 = L_NUM_BN,   // block_fusion.2   1x1 + bias
+  L_HM_2,             // heatmap_head.2   1x1 64->1 + bias (+ sigmoid)
+  L_KP_3,             // keypoint_head.3  1x1 64->65 + bias
+  L_SKIP,             // skip1.1          1x1 1->24 + bias
+  L_NUM
+};
+
+struct LayerSpec {
+  const char* ref_name;  // module path in the reference / weight blob
+  int cin, cout, ks, stride;
+  int lvl_in, lvl_out;   // log2 of the down-sampling factor of input / output maps
+};
+extern const LayerSpec kLayers[L_NUM];
+
+// Train-mode BatchNorm statistics of one BasicLayer output, per (frame, channel).
+struct BnStats {
+  float* mean = nullptr;  // [B][C]
+  float* rstd = nullptr;  // [B][C]   1/sqrt(biased var + 1e-5)
+};
+
+// Arguments of the generic direct-convolution kernel (conv.cu).
+struct ConvArgs {
+  const float* in;        // [B,Hin,Win,CIN] NHWC raw conv output of the producer (or plain values)
+  const float* w;         // packed [KS*KS][CIN][COUT]
+  const float* bias;      // [COUT] (OUT_BIAS modes)
+  float* out;             // [B,Hout,Wout,COUT] NHWC
+  const float* in_mean;   // [B][CIN] producer statistics (IN_BN*)
+  const float* in_rstd;
+  const float* skip_avg;  // IN_BN_SKIP: avgpool4(xn) [B,Hin,Win]
+  const float* skip_w;    // [24]
+  const float* skip_b;    // [24]
+  double* part;           // OUT_STATS: per-block partial sums [B][tiles][COUT][2]
+  unsigned int* ticket;   // [B]
+  float* out_mean;        // [B][COUT]
+  float* out_rstd;
+  int Hin, Win, Hout, Wout;
+  int full_w;             // IN_UNFOLD: width of xn
+};
+
+struct Ctx {
+  int device = 0;
+  int max_h = 0, max_w = 0, max_batch = 0, max_topk = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  long launches = 0;
+
+  // weights (device): packed [KS*KS][CIN][COUT] per layer, biases where present
+  float* w[L_NUM] = {};
+  float* bias[L_NUM] = {};
+
+  // geometry of the last extract call
+  int B = 0, H = 0, W = 0, in_h = 0, in_w = 0;
+
+  // activations (device, NHWC fp32, sized for max_batch x max dims)
+  uint8_t* d_gray = nullptr;      // staging for host-pointer entry points
+  float* xraw = nullptr;          // [B,H,W] resized, /255
+  float* xn = nullptr;            // [B,H,W] instance-normalised
+  float* avg4 = nullptr;          // [B,H/4,W/4]
+  float* act[L_NUM] = {};         // raw conv outputs per layer (L_F_2 = feats, L_HM_2 = H1, L_KP_3 unused)
+  float* pyr = nullptr;           // [B,h,w,64] x3 + up(x4) + up(x5)
+  float* k1h = nullptr;           // [B,H,W] folded keypoint heat map
+  BnStats bn[L_NUM_BN];
+  float* in_mean = nullptr;       // [B] instance-norm stats of the input
+  float* in_rstd = nullptr;
+  double* part = nullptr;         // shared partial-sum scratch
+  size_t part_elems = 0;
+  unsigned int* ticket = nullptr; // [B]
+
+  // post-processing
+  unsigned long long* cand = nullptr;  // [B][H*W] candidate keys
+  int* cand_count = nullptr;           // [B]
+  int* cand_count_last = nullptr;      // [B] copy kept for xfb_debug_candidates
+  // device outputs used by the host-pointer entry points
+  int32_t* o_nvalid = nullptr;
+  float* o_xy = nullptr;
+  float* o_score = nullptr;
+  float* o_desc = nullptr;
+
+  // matcher scratch
+  float* m_a = nullptr; float* m_b = nullptr;
+  int32_t* m_ga = nullptr; int32_t* m_gb = nullptr;
+  int32_t* m_out[5] = {};
+  int32_t* m_rowpart = nullptr; int32_t* m_colpart = nullptr;
+  int32_t* m_matrix = nullptr;
+  int m_cap = 0;
+};
+
+// error helpers -------------------------------------------------------------------------------
+void set_global_error(const std::string& s);
+#define XFB_CUDA_OK(ctx, expr)                                                                      \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                               \
+      return XFB_ERR_CUDA;                                                                           \
+    }                                                                                                \
+  } while (0)
+
+// kernel launchers (each returns a cudaError_t from cudaGetLastError) -------------------------
+cudaError_t launch_prep(Ctx* c, const uint8_t* d_gray, size_t frame_stride, int stride);
+cudaError_t launch_conv_layer(Ctx* c, int layer);       // all BasicLayers + block_fusion.2
+cudaError_t launch_pyramid(Ctx* c);
+cudaError_t launch_heatmap_out(Ctx* c);                  // heatmap_head.2 + sigmoid -> H1
+cudaError_t launch_keypoint_out(Ctx* c);                 // keypoint_head.3 + softmax + fold -> K1h
+cudaError_t launch_post(Ctx* c, int topk, float nms_thr, int32_t* d_nvalid, float* d_xy, float* d_score, float* d_desc);
+cudaError_t launch_distance_matrix(Ctx* c, const float* dA, int n1, const float* dB, int n2, int32_t* d_out);
+cudaError_t launch_match(Ctx* c, const float* dA, int n1, const float* dB, int n2, const int32_t* ga, const int32_t* gb, int init,
+                         int32_t* bi, int32_t* bd, int32_t* sd, int32_t* ri, int32_t* rd);
+size_t conv_part_elems(int H, int W);  // partial-sum scratch (doubles) needed per frame
+
+}  // namespace xfb
+
+struct xfb_ctx : public xfb::Ctx {};
