@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- XFeat extract+match frames/sec (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic VGA frames: every frame is extracted
+(top-4096 keypoints + 64-D descriptors) and brute-force matched (4096 x 4096, best / second-best /
+reverse-best) against the previous frame of the stream -- one extract + one match per frame.
+
+  value : whole-job frames/s with the input frames already resident in HBM (xfb_extract_batch_device +
+          xfb_match_frame_pairs_device), CUDA-event timed on the launching stream, max over ranks.
+  e2e   : the same metric through the host-buffer C-ABI calls a reference-side binding makes
+          (xfb_extract_batch + xfb_match_frame_pairs): pinned host frames in, host results out,
+          H2D and D2H copies inside the timed region.
+  roofline / cpu_baseline : see DESIGN.md "Measurement".
+
+--impl reference times the reference's own CPU implementation of the path (oracle/_ref/ref_xfeat =
+the reference's XFextractor compiled unchanged, all host threads; matcher = the C port in
+oracle/matcher_oracle.c, single thread like the reference's matchers) on bounded samples.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+METRIC = "xfeat_extract_match_fps_vga"
+UNIT = "frames/s"
+H, W, TOPK = 480, 640, 4096
+INT_MAX = 2 ** 31 - 1
+
+# conv MACs per frame at H x W (SURVEY.md 8a per-layer table): name -> (cin, cout, k, output downsample log2)
+LAYER_GEOM = {
+    "block1.0": (1, 4, 3, 0), "block1.1": (4, 8, 3, 1), "block1.2": (8, 8, 3, 1), "block1.3": (8, 24, 3, 2),
+    "block2.0": (24, 24, 3, 2), "block2.1": (24, 24, 3, 2), "block3.0": (24, 64, 3, 3), "block3.1": (64, 64, 3, 3),
+    "block3.2": (64, 64, 1, 3), "block4.0": (64, 64, 3, 4), "block4.1": (64, 64, 3, 4), "block4.2": (64, 64, 3, 4),
+    "block5.0": (64, 128, 3, 5), "block5.1": (128, 128, 3, 5), "block5.2": (128, 128, 3, 5), "block5.3": (128, 64, 1, 5),
+    "block_fusion.0": (64, 64, 3, 3), "block_fusion.1": (64, 64, 3, 3), "block_fusion.2": (64, 64, 1, 3),
+    "heatmap_head.0": (64, 64, 1, 3), "heatmap_head.1": (64, 64, 1, 3), "keypoint_head.0": (64, 64, 1, 3),
+    "keypoint_head.1": (64, 64, 1, 3), "keypoint_head.2": (64, 64, 1, 3),
+}
+
+
+def layer_flops(name, h, w):
+    cin, cout, k, lvl = LAYER_GEOM[name]
+    return 2.0 * cin * cout * k * k * (h >> lvl) * (w >> lvl)
+
+
+def conv_flops_per_frame(h, w):
+    f = sum(layer_flops(n, h, w) for n in LAYER_GEOM)
+    f += 2.0 * 24 * (h >> 2) * (w >> 2)              # skip1.1
+    f += 2.0 * 64 * 1 * (h >> 3) * (w >> 3)          # heatmap_head.2
+    f += 2.0 * 64 * 65 * (h >> 3) * (w >> 3)         # keypoint_head.3
+    return f
+
+
+def measured_peaks():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._pump, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(power)), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_run(n_extract, n_match, threads, topk=TOPK, h=H, w=W, warm=2):
+    """Times the reference CPU path on bounded samples.  Returns dict with per-frame / per-pair seconds."""
+    from oracle import matcher_oracle as mo
+    from xfeatslam_b200.frames import synthetic_frames
+    ref = REPO / "oracle" / "_ref" / "ref_xfeat"
+    out = {"kind": "reference" if ref.exists() else "port"}
+    frames = synthetic_frames(900, max(n_extract, 1), h, w)
+    if ref.exists():
+        with tempfile.TemporaryDirectory() as td:
+            fp = Path(td) / "frames.u8"
+            frames.tofile(fp)
+            r = subprocess.run([str(ref), "bench", str(fp), str(h), str(w), str(topk), str(n_extract), str(warm), str(threads)],
+                               check=True, capture_output=True, text=True)
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+        j = json.loads(line)
+        out["extract_s_per_frame"] = j["seconds"] / j["frames"]
+        out["extract_threads"] = j["threads"]
+    else:
+        import torch
+        from oracle import xfeat_oracle as xo
+        torch.set_num_threads(threads)
+        wts = xo.load_weights()
+        for i in range(min(warm, len(frames))):
+            xo.detect_and_compute(frames[i], wts, topk)
+        t0 = time.perf_counter()
+        for i in range(n_extract):
+            xo.detect_and_compute(frames[i], wts, topk)
+        out["extract_s_per_frame"] = (time.perf_counter() - t0) / n_extract
+        out["extract_threads"] = threads
+    rng = np.random.RandomState(0)
+    A = rng.randn(topk, 64).astype(np.float32); A /= np.linalg.norm(A, axis=1, keepdims=True)
+    B = (A[rng.permutation(topk)] + 0.05 * rng.randn(topk, 64)).astype(np.float32); B /= np.linalg.norm(B, axis=1, keepdims=True)
+    mo.lib()
+    t0 = time.perf_counter()
+    for _ in range(n_match):
+        mo.bruteforce(A, B)
+    out["match_s_per_pair"] = (time.perf_counter() - t0) / max(n_match, 1)
+    out["fps"] = 1.0 / (out["extract_s_per_frame"] + out["match_s_per_pair"])
+    return out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    ncpu = os.cpu_count() or 1
+    n_frames = max(1, args.steps + args.warmup)
+    n_match = max(1, min(args.steps, 8))
+    t0 = time.perf_counter()
+    r = cpu_reference_run(n_extract=n_frames, n_match=n_match, threads=ncpu, warm=max(args.warmup, 1))
+    wall = time.perf_counter() - t0
+    value = r["fps"]
+    sample = ("%d VGA frames through the reference XFextractor::operator() (libtorch CPU, %d threads: %.1f ms/frame) + %d brute-force "
+              "4096x4096 DescriptorDistance matches (C port, 1 thread like the reference's matchers: %.2f s/pair); fps = 1/(extract+match)"
+              % (n_frames, r["extract_threads"], r["extract_s_per_frame"] * 1e3, n_match, r["match_s_per_pair"]))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "vga_640x480_top4096_extract+match_prev", "frames_per_step": 1},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncpu, "kind": r["kind"], "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": wall,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from xfeatslam_b200.capi import XFeatB200
+    from xfeatslam_b200.frames import synthetic_frames
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the b200 arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    Bsz, K, Wm = args.batch, args.steps, args.warmup
+    POOL = 4
+
+    ctx = XFeatB200(max_h=H, max_w=W, max_batch=Bsz, max_topk=TOPK, device=local)
+    stream = torch.cuda.Stream(device=dev)
+    ctx.set_stream(stream.cuda_stream)
+
+    # frame shard of this rank: frames are independent units, frame i -> rank (i mod world)
+    host_pool = [torch.from_numpy(synthetic_frames(10000 * rank + 100 * p, Bsz, H, W)).pin_memory() for p in range(POOL)]
+    dev_pool = [t.to(dev) for t in host_pool]
+    d_nv = torch.zeros(Bsz, dtype=torch.int32, device=dev)
+    d_xy = torch.zeros(Bsz, TOPK, 2, dtype=torch.float32, device=dev)
+    d_sc = torch.zeros(Bsz, TOPK, dtype=torch.float32, device=dev)
+    d_ds = torch.zeros(Bsz, TOPK, 64, dtype=torch.float32, device=dev)
+    d_m = [torch.zeros(Bsz, TOPK, dtype=torch.int32, device=dev) for _ in range(5)]
+    pairs = np.array([[i, (i - 1) % Bsz] for i in range(Bsz)], np.int32)
+    h_nv = torch.zeros(Bsz, dtype=torch.int32).pin_memory()
+    h_xy = torch.zeros(Bsz, TOPK, 2, dtype=torch.float32).pin_memory()
+    h_sc = torch.zeros(Bsz, TOPK, dtype=torch.float32).pin_memory()
+    h_ds = torch.zeros(Bsz, TOPK, 64, dtype=torch.float32).pin_memory()
+    h_m = [torch.zeros(Bsz, TOPK, dtype=torch.int32).pin_memory() for _ in range(3)]   # best_idx, best_dist, second_dist
+
+    def step_device(i):
+        fr = dev_pool[i % POOL]
+        ctx.extract_ptrs(fr.data_ptr(), Bsz, H * W, H, W, W, TOPK, 0.05, d_nv.data_ptr(), d_xy.data_ptr(), d_sc.data_ptr(), d_ds.data_ptr(),
+                         device=True)
+        ctx.match_frame_pairs(pairs, INT_MAX, [t.data_ptr() for t in d_m], device=True)
+
+    def step_host(i):
+        fr = host_pool[i % POOL]
+        ctx.extract_ptrs(fr.data_ptr(), Bsz, H * W, H, W, W, TOPK, 0.05, h_nv.data_ptr(), h_xy.data_ptr(), h_sc.data_ptr(), h_ds.data_ptr(),
+                         device=False)
+        ctx.match_frame_pairs(pairs, INT_MAX, [h_m[0].data_ptr(), h_m[1].data_ptr(), h_m[2].data_ptr(), 0, 0], device=False)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(step_fn, profile=False):
+        for i in range(Wm):
+            step_fn(i)
+        barrier()
+        ctx.profile(profile)
+        l0 = ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for i in range(K):
+                step_fn(Wm + i)
+            e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = ctx.launch_count() - l0
+        prof = ctx.profile_read() if profile else {}
+        ctx.profile(False)
+        return ms, launches, prof
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches, prof = timed(step_device, profile=True)
+    ms_e2e, _, _ = timed(step_host)
+    clocks = sampler.stop() if rank == 0 else None
+
+    nv = d_nv.cpu().numpy()
+    matched = int((d_m[0].cpu().numpy() >= 0).sum())
+    counters = torch.tensor([K * Bsz, int(nv.sum()), matched, int(ms_dev * 1e6)], dtype=torch.int64, device=dev)
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)                      # max over ranks
+        gathered = [torch.zeros_like(counters) for _ in range(world)]
+        dist.all_gather(gathered, counters)                           # NCCL: counts/timings only
+        counters_all = torch.stack(gathered).cpu().numpy()
+    else:
+        counters_all = counters.cpu().numpy()[None]
+    ms_dev_max, ms_e2e_max = float(t[0]), float(t[1])
+    total_frames = int(counters_all[:, 0].sum())
+    value = total_frames / (ms_dev_max * 1e-3)
+    e2e_value = total_frames / (ms_e2e_max * 1e-3)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        # dominant kernel = the tag with the largest share of device time in the timed region
+        tot = sum(v[0] for v in prof.values()) or 1.0
+        name, (kms, kcnt) = max(prof.items(), key=lambda kv: kv[1][0])
+        avg_ms = kms / kcnt
+        if name in LAYER_GEOM:
+            alg = layer_flops(name, H, W) * Bsz
+            pipe = "fp32-simt"
+        elif name == "match_tile":
+            alg = 2.0 * TOPK * TOPK * 64
+            pipe = "fp64-simt (exact cv::norm restatement)"
+        else:
+            alg = 0.0
+            pipe = "n/a"
+        achieved = alg / (avg_ms * 1e-3) / 1e12
+        shares = {k: round(v[0] / tot, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:8]}
+        roofline = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"] + " cuBLAS bf16 burst",
+                    "pipe_used": pipe, "avg_launch_ms": avg_ms, "launches_timed": kcnt, "algorithmic_flops_per_launch": alg,
+                    "share_of_step": round(kms / tot, 4), "top_shares": shares,
+                    "whole_path_conv_tflops": conv_flops_per_frame(H, W) * value / max(world, 1) / 1e12}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            ncpu = os.cpu_count() or 1
+            r = cpu_reference_run(n_extract=16, n_match=3, threads=ncpu)
+            cpu = {"value": r["fps"], "unit": UNIT, "cores": ncpu, "kind": r["kind"],
+                   "sample": "16 VGA frames reference XFextractor (libtorch CPU, %d threads, %.1f ms/frame) + 3 brute-force 4096x4096 matches "
+                             "(C port, 1 thread, %.2f s/pair)" % (r["extract_threads"], r["extract_s_per_frame"] * 1e3, r["match_s_per_pair"])}
+        frame_bytes = H * W
+        out_bytes = TOPK * (8 + 4 + 256) + 4 + 3 * TOPK * 4
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_dev_max / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "vga_640x480_top4096_extract+match_prev", "frames_per_step_per_gpu": Bsz, "matches_per_frame": 1,
+                       "match_size": "4096x4096x64", "parallelism": "frame-sharded dp%d, no data-path collective" % world,
+                       "l2": "per-step working set %.1f GB >> 126 MB L2; input pool of %d distinct batches rotates" % (Bsz * 0.07, POOL)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": Bsz * frame_bytes, "d2h_bytes_per_step": Bsz * out_bytes,
+                    "ms_per_step": ms_e2e_max / K},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "counters": {"frames": total_frames, "keypoints_last_step": int(counters_all[:, 1].sum()), "matched_last_step": int(counters_all[:, 2].sum())},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="frames per step per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

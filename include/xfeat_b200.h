@@ -96,6 +96,21 @@ int xfb_match_device(xfb_ctx* ctx, const float* d_A, int n1, const float* d_B, i
                      const int32_t* d_group_b, int init_dist, int32_t* d_best_idx, int32_t* d_best_dist, int32_t* d_second_dist,
                      int32_t* d_best_idx_rev, int32_t* d_best_dist_rev);
 
+/* Matches the descriptors of two frames of the LAST xfb_extract_batch[_device] call without leaving
+ * the device (descriptors stay resident in HBM): rows = the n_valid keypoints of frame_a, columns =
+ * those of frame_b.  Output arrays are HOST buffers of `topk` entries each (entries >= n_valid are
+ * -1 / init_dist); any may be NULL.  This is the fused form of "extract, then ORBmatcher on the
+ * pair" used by bench.py's end-to-end leg. */
+int xfb_match_frames(xfb_ctx* ctx, int frame_a, int frame_b, int init_dist, int32_t* best_idx, int32_t* best_dist,
+                     int32_t* second_dist, int32_t* best_idx_rev, int32_t* best_dist_rev);
+/* n_pairs matches in one call: pairs[2*p], pairs[2*p+1] = (frame_a, frame_b) of pair p (host array);
+ * outputs are [n_pairs][topk] HOST arrays (one synchronisation at the end).  The _device form writes
+ * to DEVICE arrays and is asynchronous on the ctx stream. */
+int xfb_match_frame_pairs(xfb_ctx* ctx, const int32_t* pairs, int n_pairs, int init_dist, int32_t* best_idx, int32_t* best_dist,
+                          int32_t* second_dist, int32_t* best_idx_rev, int32_t* best_dist_rev);
+int xfb_match_frame_pairs_device(xfb_ctx* ctx, const int32_t* pairs, int n_pairs, int init_dist, int32_t* d_best_idx,
+                                 int32_t* d_best_dist, int32_t* d_second_dist, int32_t* d_best_idx_rev, int32_t* d_best_dist_rev);
+
 /* ---- introspection (used by the parity tests and bench.py) ------------------------------- */
 
 /* Copies an intermediate of the last extract call to the host as fp32.  `name` is a reference
@@ -114,6 +129,14 @@ int xfb_debug_post(xfb_ctx* ctx, int H, int W, const float* feats, const float* 
 int xfb_debug_candidates(xfb_ctx* ctx, int frame);
 /* Total number of kernels this ctx has launched so far. */
 long xfb_launch_count(const xfb_ctx* ctx);
+/* Per-kernel CUDA-event timing on the ctx stream.  enable != 0 starts recording an event pair around
+ * every kernel launch; xfb_profile_read synchronises, adds the elapsed times into ms[tag] / count[tag]
+ * (arrays of XFB_PROF_TAGS entries, caller-zeroed) and clears the recorded events.
+ * xfb_profile_tag_name(tag) names a tag (a reference module path or a stage name). */
+#define XFB_PROF_TAGS 40
+int xfb_profile_enable(xfb_ctx* ctx, int enable);
+int xfb_profile_read(xfb_ctx* ctx, float* ms, int32_t* count);
+const char* xfb_profile_tag_name(int tag);
 
 #ifdef __cplusplus
 }

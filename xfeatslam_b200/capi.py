@@ -18,6 +18,7 @@ INT_MAX = 2 ** 31 - 1
 SYMBOLS = [
     "xfb_create", "xfb_destroy", "xfb_last_error", "xfb_set_stream", "xfb_extract", "xfb_extract_batch",
     "xfb_extract_batch_device", "xfb_distance_matrix", "xfb_distance_matrix_device", "xfb_match", "xfb_match_device",
+    "xfb_match_frames", "xfb_match_frame_pairs", "xfb_match_frame_pairs_device", "xfb_profile_enable", "xfb_profile_read", "xfb_profile_tag_name",
     "xfb_debug_read", "xfb_debug_read_stats", "xfb_debug_post", "xfb_debug_candidates", "xfb_launch_count",
 ]
 
@@ -47,6 +48,13 @@ def load_library(path=LIB_PATH):
     lib.xfb_distance_matrix_device.argtypes = lib.xfb_distance_matrix.argtypes
     lib.xfb_match.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int] + [c_void_p] * 5
     lib.xfb_match_device.argtypes = lib.xfb_match.argtypes
+    lib.xfb_match_frames.argtypes = [c_void_p, c_int, c_int, c_int] + [c_void_p] * 5
+    lib.xfb_match_frame_pairs.argtypes = [c_void_p, c_void_p, c_int, c_int] + [c_void_p] * 5
+    lib.xfb_match_frame_pairs_device.argtypes = lib.xfb_match_frame_pairs.argtypes
+    lib.xfb_profile_enable.argtypes = [c_void_p, c_int]
+    lib.xfb_profile_read.argtypes = [c_void_p, c_void_p, c_void_p]
+    lib.xfb_profile_tag_name.argtypes = [c_int]
+    lib.xfb_profile_tag_name.restype = c_char_p
     lib.xfb_debug_read.argtypes = [c_void_p, c_char_p, c_int, c_void_p, c_size_t, c_void_p]
     lib.xfb_debug_read.restype = c_long
     lib.xfb_debug_read_stats.argtypes = [c_void_p, c_char_p, c_int, c_void_p, c_size_t]
@@ -146,6 +154,36 @@ class XFeatB200:
         v = lambda p: c_void_p(p) if p else None
         self._check(self.lib.xfb_match_device(self.h, v(a_ptr), n1, v(b_ptr), n2, v(ga), v(gb), int(init), v(bi), v(bd), v(sd), v(ri),
                                               v(rd)), "xfb_match_device")
+
+    def match_frames(self, fa, fb, topk, init=INT_MAX, ptrs=None):
+        """Match two frames of the last extract call on the device; host int32 arrays of `topk`."""
+        if ptrs is None:
+            outs = [np.zeros(topk, np.int32) for _ in range(5)]
+            ptrs = [_ptr(o) for o in outs]
+        else:
+            outs = None
+        self._check(self.lib.xfb_match_frames(self.h, fa, fb, int(init), *ptrs), "xfb_match_frames")
+        return outs
+
+    def match_frame_pairs(self, pairs, init, out_ptrs, device=False):
+        """pairs: int32 [n,2] host array; out_ptrs: 5 raw pointers (host, or device when device=True) or 0."""
+        pairs = np.ascontiguousarray(pairs, np.int32)
+        fn = self.lib.xfb_match_frame_pairs_device if device else self.lib.xfb_match_frame_pairs
+        v = [c_void_p(p) if p else None for p in out_ptrs]
+        self._check(fn(self.h, _ptr(pairs), pairs.shape[0], int(init), *v), "xfb_match_frame_pairs")
+
+    def profile(self, enable):
+        self._check(self.lib.xfb_profile_enable(self.h, int(bool(enable))), "xfb_profile_enable")
+
+    def profile_read(self):
+        """{tag name: (total ms, launches)} since the last read."""
+        ms = np.zeros(40, np.float32); cnt = np.zeros(40, np.int32)
+        self._check(self.lib.xfb_profile_read(self.h, _ptr(ms), _ptr(cnt)), "xfb_profile_read")
+        out = {}
+        for t in range(40):
+            if cnt[t]:
+                out[self.lib.xfb_profile_tag_name(t).decode()] = (float(ms[t]), int(cnt[t]))
+        return out
 
     # ---- introspection ----------------------------------------------------------------------------
     def debug_read(self, name, frame=0, capacity=None):

@@ -18,6 +18,29 @@ void set_global_error(const std::string& s) {
   g_err = s;
 }
 
+// ---- per-kernel event timing ---------------------------------------------------------------------------
+static cudaEvent_t prof_get_event(Ctx* c) {
+  cudaEvent_t e = nullptr;
+  if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+  else cudaEventCreate(&e);
+  return e;
+}
+void prof_begin(Ctx* c, int tag) {
+  if (!c->prof) return;
+  cudaEvent_t e = prof_get_event(c);
+  cudaEventRecord(e, c->stream);
+  c->prof_ev.push_back(e);
+  c->prof_tag.push_back(tag);
+}
+void prof_end(Ctx* c) {
+  if (!c->prof) return;
+  cudaEvent_t e = prof_get_event(c);
+  cudaEventRecord(e, c->stream);
+  c->prof_ev.push_back(e);
+}
+static const char* kStageNames[] = {"prep_stats", "prep_norm", "pyramid_sum", "heatmap_out", "keypoint_out_softmax_fold", "nms_score",
+                                    "topk_select_sort", "describe", "match_tile", "match_merge", "distance_matrix"};
+
 // ---- weight blob (tools/convert_weights.py) --------------------------------------------------------
 #pragma pack(push, 1)
 struct BlobEntry {
@@ -188,6 +211,7 @@ static int extract_device(Ctx* c, const uint8_t* d_gray, int batch, size_t frame
   int r = run_dense(c, d_gray, frame_stride, stride);
   if (r != XFB_OK) return r;
   XFB_CUDA_OK(c, launch_post(c, topk, nms_thr, d_nvalid, d_xy, d_score, d_desc));
+  c->last_topk = topk; c->last_nvalid = d_nvalid; c->last_desc = d_desc;
   return XFB_OK;
 }
 
@@ -246,7 +270,9 @@ void xfb_destroy(xfb_ctx* c) {
   fr(c->d_gray); fr(c->xraw); fr(c->xn); fr(c->avg4); fr(c->pyr); fr(c->k1h); fr(c->in_mean); fr(c->in_rstd); fr(c->part);
   fr(c->ticket); fr(c->cand); fr(c->cand_count); fr(c->cand_count_last); fr(c->o_nvalid); fr(c->o_xy); fr(c->o_score); fr(c->o_desc);
   fr(c->m_a); fr(c->m_b); fr(c->m_ga); fr(c->m_gb); fr(c->m_rowpart); fr(c->m_colpart); fr(c->m_matrix);
-  for (int i = 0; i < 5; ++i) fr(c->m_out[i]);
+  for (int i = 0; i < 5; ++i) { fr(c->m_out[i]); fr(c->m_pairs_out[i]); }
+  for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -355,6 +381,89 @@ int xfb_match(xfb_ctx* c, const float* A, int n1, const float* B, int n2, const 
   }
   XFB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return XFB_OK;
+}
+
+int xfb_match_frames(xfb_ctx* c, int fa, int fb, int init_dist, int32_t* best_idx, int32_t* best_dist, int32_t* second_dist,
+                     int32_t* best_idx_rev, int32_t* best_dist_rev) {
+  if (!c) return XFB_ERR_ARG;
+  if (!c->last_desc || fa < 0 || fb < 0 || fa >= c->B || fb >= c->B) { c->err = "match_frames: no extract result for these frames"; return XFB_ERR_ARG; }
+  XFB_CUDA_OK(c, cudaSetDevice(c->device));
+  const int K = c->last_topk;
+  int r = ensure_match_scratch(c, K, K, false);
+  if (r != XFB_OK) return r;
+  XFB_CUDA_OK(c, launch_match(c, c->last_desc + (size_t)fa * K * 64, K, c->last_desc + (size_t)fb * K * 64, K, nullptr, nullptr, init_dist,
+                              c->m_out[0], c->m_out[1], c->m_out[2], c->m_out[3], c->m_out[4], c->last_nvalid + fa, c->last_nvalid + fb));
+  int32_t* host[5] = {best_idx, best_dist, second_dist, best_idx_rev, best_dist_rev};
+  for (int i = 0; i < 5; ++i)
+    if (host[i]) XFB_CUDA_OK(c, cudaMemcpyAsync(host[i], c->m_out[i], (size_t)K * 4, cudaMemcpyDeviceToHost, c->stream));
+  XFB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return XFB_OK;
+}
+
+static int match_pairs_impl(xfb_ctx* c, const int32_t* pairs, int n_pairs, int init_dist, int32_t* o[5], bool to_host) {
+  if (!c) return XFB_ERR_ARG;
+  if (!pairs || n_pairs < 0 || !c->last_desc) { c->err = "match_frame_pairs: bad argument / no extract result"; return XFB_ERR_ARG; }
+  XFB_CUDA_OK(c, cudaSetDevice(c->device));
+  const int K = c->last_topk;
+  int r = ensure_match_scratch(c, K, K, false);
+  if (r != XFB_OK) return r;
+  if (to_host && n_pairs > c->m_pairs_cap) {
+    for (int i = 0; i < 5; ++i) { if (c->m_pairs_out[i]) cudaFree(c->m_pairs_out[i]); c->m_pairs_out[i] = nullptr; }
+    for (int i = 0; i < 5; ++i) XFB_ALLOC(c, c->m_pairs_out[i], (size_t)n_pairs * c->max_topk * 4);
+    c->m_pairs_cap = n_pairs;
+  }
+  for (int p = 0; p < n_pairs; ++p) {
+    const int fa = pairs[2 * p], fb = pairs[2 * p + 1];
+    if (fa < 0 || fb < 0 || fa >= c->B || fb >= c->B) { c->err = "match_frame_pairs: frame index out of range"; return XFB_ERR_ARG; }
+    int32_t* d[5];
+    for (int i = 0; i < 5; ++i) d[i] = to_host ? (o[i] ? c->m_pairs_out[i] + (size_t)p * K : nullptr) : (o[i] ? o[i] + (size_t)p * K : nullptr);
+    XFB_CUDA_OK(c, launch_match(c, c->last_desc + (size_t)fa * K * 64, K, c->last_desc + (size_t)fb * K * 64, K, nullptr, nullptr, init_dist,
+                                d[0], d[1], d[2], d[3], d[4], c->last_nvalid + fa, c->last_nvalid + fb));
+  }
+  if (to_host) {
+    for (int i = 0; i < 5; ++i)
+      if (o[i] && n_pairs) XFB_CUDA_OK(c, cudaMemcpyAsync(o[i], c->m_pairs_out[i], (size_t)n_pairs * K * 4, cudaMemcpyDeviceToHost, c->stream));
+    XFB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  }
+  return XFB_OK;
+}
+
+int xfb_match_frame_pairs(xfb_ctx* c, const int32_t* pairs, int n_pairs, int init_dist, int32_t* bi, int32_t* bd, int32_t* sd, int32_t* ri,
+                          int32_t* rd) {
+  int32_t* o[5] = {bi, bd, sd, ri, rd};
+  return match_pairs_impl(c, pairs, n_pairs, init_dist, o, true);
+}
+int xfb_match_frame_pairs_device(xfb_ctx* c, const int32_t* pairs, int n_pairs, int init_dist, int32_t* bi, int32_t* bd, int32_t* sd,
+                                 int32_t* ri, int32_t* rd) {
+  int32_t* o[5] = {bi, bd, sd, ri, rd};
+  return match_pairs_impl(c, pairs, n_pairs, init_dist, o, false);
+}
+
+int xfb_profile_enable(xfb_ctx* c, int enable) {
+  if (!c) return XFB_ERR_ARG;
+  c->prof = enable != 0;
+  return XFB_OK;
+}
+
+int xfb_profile_read(xfb_ctx* c, float* ms, int32_t* count) {
+  if (!c || !ms || !count) return XFB_ERR_ARG;
+  XFB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  for (size_t i = 0; i < c->prof_tag.size(); ++i) {
+    float t = 0.f;
+    XFB_CUDA_OK(c, cudaEventElapsedTime(&t, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]));
+    const int tag = c->prof_tag[i];
+    if (tag >= 0 && tag < XFB_PROF_TAGS) { ms[tag] += t; count[tag] += 1; }
+  }
+  for (cudaEvent_t e : c->prof_ev) c->prof_pool.push_back(e);
+  c->prof_ev.clear();
+  c->prof_tag.clear();
+  return XFB_OK;
+}
+
+const char* xfb_profile_tag_name(int tag) {
+  if (tag >= 0 && tag < L_NUM) return kLayers[tag].ref_name;
+  if (tag >= L_NUM && tag < P_NUM) return kStageNames[tag - L_NUM];
+  return "";
 }
 
 // ---- introspection ------------------------------------------------------------------------------------

@@ -262,7 +262,7 @@ using CfgB5x = Cfg<128, 128, 3, 1, 4, 4, 2, 16, 16>;   // 15x20     128->128
 using CfgB53 = Cfg<128, 64, 1, 1, 4, 4, 2, 8, 32>;     // 15x20     128->64 1x1
 
 template <class C, int INMODE, int OUTMODE>
-static cudaError_t run(Ctx* c, const ConvArgs& a) {
+static cudaError_t run(Ctx* c, const ConvArgs& a, int tag) {
   auto kern = conv_bn_kernel<C, INMODE, OUTMODE>;
   // the statistics fold reuses the staging buffers; make sure they are large enough
   constexpr size_t red = sizeof(double) * 2 * C::COUT * (C::NWARP > ((C::NT / C::COUT) > 0 ? (C::NT / C::COUT) : 1) ? C::NWARP : ((C::NT / C::COUT) > 0 ? (C::NT / C::COUT) : 1));
@@ -274,7 +274,9 @@ static cudaError_t run(Ctx* c, const ConvArgs& a) {
     attr_mask |= 1ull << c->device;
   }
   dim3 grid((a.Wout + C::TW - 1) / C::TW, (a.Hout + C::TH - 1) / C::TH, c->B);
+  prof_begin(c, tag);
   kern<<<grid, C::NT, smem, c->stream>>>(a);
+  prof_end(c);
   c->launches++;
   return cudaGetLastError();
 }
@@ -317,33 +319,33 @@ cudaError_t launch_conv_layer(Ctx* c, int L) {
   if (L < L_NUM_BN) { a.out_mean = c->bn[L].mean; a.out_rstd = c->bn[L].rstd; }
   auto from = [&](int P) { a.in = c->act[P]; a.in_mean = c->bn[P].mean; a.in_rstd = c->bn[P].rstd; };
   switch (L) {
-    case L_B1_0: a.in = c->xn; return run<CfgB10, IN_PLAIN, OUT_STATS>(c, a);
-    case L_B1_1: from(L_B1_0); return run<CfgB11, IN_BN, OUT_STATS>(c, a);
-    case L_B1_2: from(L_B1_1); return run<CfgB12, IN_BN, OUT_STATS>(c, a);
-    case L_B1_3: from(L_B1_2); return run<CfgB13, IN_BN, OUT_STATS>(c, a);
+    case L_B1_0: a.in = c->xn; return run<CfgB10, IN_PLAIN, OUT_STATS>(c, a, L);
+    case L_B1_1: from(L_B1_0); return run<CfgB11, IN_BN, OUT_STATS>(c, a, L);
+    case L_B1_2: from(L_B1_1); return run<CfgB12, IN_BN, OUT_STATS>(c, a, L);
+    case L_B1_3: from(L_B1_2); return run<CfgB13, IN_BN, OUT_STATS>(c, a, L);
     case L_B2_0:
       from(L_B1_3);
       a.skip_avg = c->avg4; a.skip_w = c->w[L_SKIP]; a.skip_b = c->bias[L_SKIP];
-      return run<CfgB2x, IN_BN_SKIP, OUT_STATS>(c, a);
-    case L_B2_1: from(L_B2_0); return run<CfgB2x, IN_BN, OUT_STATS>(c, a);
-    case L_B3_0: from(L_B2_1); return run<CfgB30, IN_BN, OUT_STATS>(c, a);
-    case L_B3_1: from(L_B3_0); return run<CfgC33, IN_BN, OUT_STATS>(c, a);
-    case L_B3_2: from(L_B3_1); return run<CfgC11, IN_BN, OUT_STATS>(c, a);
-    case L_B4_0: from(L_B3_2); return run<CfgB40, IN_BN, OUT_STATS>(c, a);
-    case L_B4_1: from(L_B4_0); return run<CfgB4x, IN_BN, OUT_STATS>(c, a);
-    case L_B4_2: from(L_B4_1); return run<CfgB4x, IN_BN, OUT_STATS>(c, a);
-    case L_B5_0: from(L_B4_2); return run<CfgB50, IN_BN, OUT_STATS>(c, a);
-    case L_B5_1: from(L_B5_0); return run<CfgB5x, IN_BN, OUT_STATS>(c, a);
-    case L_B5_2: from(L_B5_1); return run<CfgB5x, IN_BN, OUT_STATS>(c, a);
-    case L_B5_3: from(L_B5_2); return run<CfgB53, IN_BN, OUT_STATS>(c, a);
-    case L_F_0: a.in = c->pyr; return run<CfgC33, IN_PLAIN, OUT_STATS>(c, a);
-    case L_F_1: from(L_F_0); return run<CfgC33, IN_BN, OUT_STATS>(c, a);
-    case L_F_2: from(L_F_1); return run<CfgC11, IN_BN, OUT_BIAS>(c, a);
-    case L_HM_0: a.in = c->act[L_F_2]; return run<CfgC11, IN_PLAIN, OUT_STATS>(c, a);
-    case L_HM_1: from(L_HM_0); return run<CfgC11, IN_BN, OUT_STATS>(c, a);
-    case L_KP_0: a.in = c->xn; a.Hin = c->H >> 3; a.Win = c->W >> 3; return run<CfgC11, IN_UNFOLD, OUT_STATS>(c, a);
-    case L_KP_1: from(L_KP_0); return run<CfgC11, IN_BN, OUT_STATS>(c, a);
-    case L_KP_2: from(L_KP_1); return run<CfgC11, IN_BN, OUT_STATS>(c, a);
+      return run<CfgB2x, IN_BN_SKIP, OUT_STATS>(c, a, L);
+    case L_B2_1: from(L_B2_0); return run<CfgB2x, IN_BN, OUT_STATS>(c, a, L);
+    case L_B3_0: from(L_B2_1); return run<CfgB30, IN_BN, OUT_STATS>(c, a, L);
+    case L_B3_1: from(L_B3_0); return run<CfgC33, IN_BN, OUT_STATS>(c, a, L);
+    case L_B3_2: from(L_B3_1); return run<CfgC11, IN_BN, OUT_STATS>(c, a, L);
+    case L_B4_0: from(L_B3_2); return run<CfgB40, IN_BN, OUT_STATS>(c, a, L);
+    case L_B4_1: from(L_B4_0); return run<CfgB4x, IN_BN, OUT_STATS>(c, a, L);
+    case L_B4_2: from(L_B4_1); return run<CfgB4x, IN_BN, OUT_STATS>(c, a, L);
+    case L_B5_0: from(L_B4_2); return run<CfgB50, IN_BN, OUT_STATS>(c, a, L);
+    case L_B5_1: from(L_B5_0); return run<CfgB5x, IN_BN, OUT_STATS>(c, a, L);
+    case L_B5_2: from(L_B5_1); return run<CfgB5x, IN_BN, OUT_STATS>(c, a, L);
+    case L_B5_3: from(L_B5_2); return run<CfgB53, IN_BN, OUT_STATS>(c, a, L);
+    case L_F_0: a.in = c->pyr; return run<CfgC33, IN_PLAIN, OUT_STATS>(c, a, L);
+    case L_F_1: from(L_F_0); return run<CfgC33, IN_BN, OUT_STATS>(c, a, L);
+    case L_F_2: from(L_F_1); return run<CfgC11, IN_BN, OUT_BIAS>(c, a, L);
+    case L_HM_0: a.in = c->act[L_F_2]; return run<CfgC11, IN_PLAIN, OUT_STATS>(c, a, L);
+    case L_HM_1: from(L_HM_0); return run<CfgC11, IN_BN, OUT_STATS>(c, a, L);
+    case L_KP_0: a.in = c->xn; a.Hin = c->H >> 3; a.Win = c->W >> 3; return run<CfgC11, IN_UNFOLD, OUT_STATS>(c, a, L);
+    case L_KP_1: from(L_KP_0); return run<CfgC11, IN_BN, OUT_STATS>(c, a, L);
+    case L_KP_2: from(L_KP_1); return run<CfgC11, IN_BN, OUT_STATS>(c, a, L);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -122,14 +122,18 @@ __global__ void __launch_bounds__(256) prep_norm_kernel(const float* xraw, const
 cudaError_t launch_prep(Ctx* c, const uint8_t* d_gray, size_t frame_stride, int stride) {
   const int npix = c->H * c->W;
   dim3 g1((npix + PREP_PIX - 1) / PREP_PIX, c->B);
+  prof_begin(c, P_PREP_STATS);
   prep_stats_kernel<<<g1, PREP_NT, 0, c->stream>>>(d_gray, frame_stride, stride, c->in_h, c->in_w, c->H, c->W, c->xraw, c->part,
                                                    c->ticket, c->in_mean, c->in_rstd);
+  prof_end(c);
   c->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   dim3 blk(32, 8);
   dim3 g2(((c->W >> 2) + 31) / 32, ((c->H >> 2) + 7) / 8, c->B);
+  prof_begin(c, P_PREP_NORM);
   prep_norm_kernel<<<g2, blk, 0, c->stream>>>(c->xraw, c->in_mean, c->in_rstd, c->H, c->W, c->xn, c->avg4);
+  prof_end(c);
   c->launches++;
   return cudaGetLastError();
 }
@@ -197,9 +201,11 @@ __global__ void __launch_bounds__(256) pyramid_kernel(const float* x3, const flo
 cudaError_t launch_pyramid(Ctx* c) {
   const int h3 = c->H >> 3, w3 = c->W >> 3, h4 = c->H >> 4, w4 = c->W >> 4, h5 = c->H >> 5, w5 = c->W >> 5;
   dim3 grid((h3 * w3 * 16 + 255) / 256, c->B);
+  prof_begin(c, P_PYRAMID);
   pyramid_kernel<<<grid, 256, 0, c->stream>>>(c->act[L_B3_2], c->act[L_B4_2], c->act[L_B5_3], c->bn[L_B3_2].mean, c->bn[L_B3_2].rstd,
                                               c->bn[L_B4_2].mean, c->bn[L_B4_2].rstd, c->bn[L_B5_3].mean, c->bn[L_B5_3].rstd, h3, w3, h4,
                                               w4, h5, w5, c->pyr);
+  prof_end(c);
   c->launches++;
   return cudaGetLastError();
 }
@@ -230,8 +236,10 @@ __global__ void __launch_bounds__(256) heatmap_out_kernel(const float* in, const
 cudaError_t launch_heatmap_out(Ctx* c) {
   const int npix = (c->H >> 3) * (c->W >> 3);
   dim3 grid((npix + 7) / 8, c->B);
+  prof_begin(c, P_HEATMAP_OUT);
   heatmap_out_kernel<<<grid, 256, 0, c->stream>>>(c->act[L_HM_1], c->bn[L_HM_1].mean, c->bn[L_HM_1].rstd, c->w[L_HM_2], c->bias[L_HM_2],
                                                   npix, c->act[L_HM_2]);
+  prof_end(c);
   c->launches++;
   return cudaGetLastError();
 }
@@ -292,8 +300,10 @@ cudaError_t launch_keypoint_out(Ctx* c) {
   int blocks = (h * wd + KP_WARPS - 1) / KP_WARPS;
   if (blocks > 600) blocks = 600;
   dim3 grid(blocks, c->B);
+  prof_begin(c, P_KEYPOINT_OUT);
   keypoint_out_kernel<<<grid, KP_WARPS * 32, 0, c->stream>>>(c->act[L_KP_2], c->bn[L_KP_2].mean, c->bn[L_KP_2].rstd, c->w[L_KP_3],
                                                             c->bias[L_KP_3], h, wd, c->k1h);
+  prof_end(c);
   c->launches++;
   return cudaGetLastError();
 }

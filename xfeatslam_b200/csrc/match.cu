@@ -42,9 +42,12 @@ __device__ __forceinline__ void load_tile(float* s, const float* g, int row0, in
 }
 
 template <bool MATRIX>
-__global__ void __launch_bounds__(256) dist_tile_kernel(const float* A, int n1, const float* B, int n2, const int32_t* ga,
-                                                        const int32_t* gb, int init, int32_t* out_matrix, int32_t* rowpart,
-                                                        int32_t* colpart) {
+__global__ void __launch_bounds__(256) dist_tile_kernel(const float* A, int n1, const float* B, int n2, const int32_t* n1p,
+                                                        const int32_t* n2p, const int32_t* ga, const int32_t* gb, int init,
+                                                        int32_t* out_matrix, int32_t* rowpart, int32_t* colpart) {
+  if (n1p) n1 = min(n1, *n1p);   // device-resident counts (xfb_match_frames): n1/n2 are the capacities
+  if (n2p) n2 = min(n2, *n2p);
+  if ((int)blockIdx.y * MT >= n1 || (int)blockIdx.x * MT >= n2) return;
   __shared__ float sA[MT * MLD];
   __shared__ float sB[MT * MLD];
   __shared__ unsigned long long sCol[16][MT];
@@ -152,12 +155,17 @@ __global__ void __launch_bounds__(256) dist_tile_kernel(const float* A, int n1, 
   }
 }
 
-__global__ void match_merge_kernel(const int32_t* rowpart, const int32_t* colpart, int n1, int n2, int nct, int nrt, int init,
-                                   int32_t* bi, int32_t* bd, int32_t* sd, int32_t* ri, int32_t* rd) {
+__global__ void match_merge_kernel(const int32_t* rowpart, const int32_t* colpart, int n1cap, int n2cap, const int32_t* n1p,
+                                   const int32_t* n2p, int nct_stride, int nrt_stride, int init, int32_t* bi, int32_t* bd,
+                                   int32_t* sd, int32_t* ri, int32_t* rd) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < n1) {
+  const int n1 = n1p ? min(n1cap, *n1p) : n1cap, n2 = n2p ? min(n2cap, *n2p) : n2cap;
+  // tiles that were actually computed (a tile kernel CTA exits early beyond n1 / n2)
+  const int nct_live = (n1 > 0 && n2 > 0) ? (n2 + MT - 1) / MT : 0, nrt_live = (n1 > 0 && n2 > 0) ? (n1 + MT - 1) / MT : 0;
+  const int nct = nct_stride, nrt = nrt_stride;
+  if (g < n1cap) {
     Top2 s; s.d1 = init; s.idx = -1; s.d2 = init;
-    for (int c = 0; c < nct; ++c) {
+    for (int c = 0; c < (g < n1 ? nct_live : 0); ++c) {
       const int32_t* p = rowpart + ((size_t)g * nct + c) * 3;
       Top2 o; o.d1 = p[0]; o.idx = p[1]; o.d2 = p[2];
       if (o.idx >= 0 || o.d2 < init) s = top2_merge(s, o);
@@ -166,9 +174,9 @@ __global__ void match_merge_kernel(const int32_t* rowpart, const int32_t* colpar
     if (bd) bd[g] = s.d1;
     if (sd) sd[g] = s.d2;
   }
-  if (g < n2) {
+  if (g < n2cap) {
     int bdist = init, bidx = -1;
-    for (int r = 0; r < nrt; ++r) {
+    for (int r = 0; r < (g < n2 ? nrt_live : 0); ++r) {
       const int32_t* p = colpart + ((size_t)g * nrt + r) * 2;
       if (p[0] < bdist) { bdist = p[0]; bidx = p[1]; }
     }
@@ -180,25 +188,31 @@ __global__ void match_merge_kernel(const int32_t* rowpart, const int32_t* colpar
 cudaError_t launch_distance_matrix(Ctx* c, const float* dA, int n1, const float* dB, int n2, int32_t* d_out) {
   if (n1 <= 0 || n2 <= 0) return cudaSuccess;
   dim3 grid((n2 + MT - 1) / MT, (n1 + MT - 1) / MT);
-  dist_tile_kernel<true><<<grid, 256, 0, c->stream>>>(dA, n1, dB, n2, nullptr, nullptr, 0, d_out, nullptr, nullptr);
+  prof_begin(c, P_DIST_MATRIX);
+  dist_tile_kernel<true><<<grid, 256, 0, c->stream>>>(dA, n1, dB, n2, nullptr, nullptr, nullptr, nullptr, 0, d_out, nullptr, nullptr);
+  prof_end(c);
   c->launches++;
   return cudaGetLastError();
 }
 
 cudaError_t launch_match(Ctx* c, const float* dA, int n1, const float* dB, int n2, const int32_t* ga, const int32_t* gb, int init,
-                         int32_t* bi, int32_t* bd, int32_t* sd, int32_t* ri, int32_t* rd) {
+                         int32_t* bi, int32_t* bd, int32_t* sd, int32_t* ri, int32_t* rd, const int32_t* n1p, const int32_t* n2p) {
   if (n1 <= 0 && n2 <= 0) return cudaSuccess;
   const int nct = (n2 + MT - 1) / MT, nrt = (n1 + MT - 1) / MT;
   if (n1 > 0 && n2 > 0) {
     dim3 grid(nct, nrt);
-    dist_tile_kernel<false><<<grid, 256, 0, c->stream>>>(dA, n1, dB, n2, ga, gb, init, nullptr, c->m_rowpart, c->m_colpart);
+    prof_begin(c, P_MATCH_TILE);
+    dist_tile_kernel<false><<<grid, 256, 0, c->stream>>>(dA, n1, dB, n2, n1p, n2p, ga, gb, init, nullptr, c->m_rowpart, c->m_colpart);
+    prof_end(c);
     c->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
   const int n = n1 > n2 ? n1 : n2;
-  match_merge_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->m_rowpart, c->m_colpart, n1, n2, (n1 > 0 && n2 > 0) ? nct : 0,
-                                                             (n1 > 0 && n2 > 0) ? nrt : 0, init, bi, bd, sd, ri, rd);
+  prof_begin(c, P_MATCH_MERGE);
+  match_merge_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->m_rowpart, c->m_colpart, n1, n2, n1p, n2p, nct, nrt, init, bi, bd, sd, ri,
+                                                             rd);
+  prof_end(c);
   c->launches++;
   return cudaGetLastError();
 }

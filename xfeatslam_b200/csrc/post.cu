@@ -224,7 +224,9 @@ static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 cudaError_t launch_post(Ctx* c, int topk, float nms_thr, int32_t* d_nvalid, float* d_xy, float* d_score, float* d_desc) {
   const int H = c->H, W = c->W;
   dim3 g1((W + NMS_T - 1) / NMS_T, (H + NMS_T - 1) / NMS_T, c->B);
+  prof_begin(c, P_NMS);
   nms_score_kernel<<<g1, dim3(NMS_T, NMS_T), 0, c->stream>>>(c->k1h, c->act[L_HM_2], H, W, nms_thr, c->cand, c->cand_count);
+  prof_end(c);
   c->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
@@ -236,13 +238,17 @@ cudaError_t launch_post(Ctx* c, int topk, float nms_thr, int32_t* d_nvalid, floa
     if (e != cudaSuccess) return e;
     attr_mask |= 1ull << c->device;
   }
+  prof_begin(c, P_TOPK);
   topk_kernel<<<c->B, TOPK_NT, smem, c->stream>>>(c->cand, c->cand_count, c->cand_count_last, H * W, W, topk, sort_n, d_nvalid, d_xy,
                                                   d_score);
+  prof_end(c);
   c->launches++;
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   dim3 g3((topk + 7) / 8, c->B);
+  prof_begin(c, P_DESCRIBE);
   describe_kernel<<<g3, 256, 0, c->stream>>>(c->act[L_F_2], H, W, topk, d_nvalid, d_xy, d_desc);
+  prof_end(c);
   c->launches++;
   return cudaGetLastError();
 }

@@ -102,6 +102,17 @@ struct Ctx {
   float* o_score = nullptr;
   float* o_desc = nullptr;
 
+  // last extract geometry for xfb_match_frames
+  int last_topk = 0;
+  const int32_t* last_nvalid = nullptr;   // device
+  const float* last_desc = nullptr;       // device [B][topk][64]
+
+  // per-kernel event timing
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_ev;       // pairs
+  std::vector<int> prof_tag;
+  std::vector<cudaEvent_t> prof_pool;
+
   // matcher scratch
   float* m_a = nullptr; float* m_b = nullptr;
   int32_t* m_ga = nullptr; int32_t* m_gb = nullptr;
@@ -109,6 +120,8 @@ struct Ctx {
   int32_t* m_rowpart = nullptr; int32_t* m_colpart = nullptr;
   int32_t* m_matrix = nullptr;
   int m_cap = 0;
+  int32_t* m_pairs_out[5] = {};   // [n_pairs][topk] staging for xfb_match_frame_pairs
+  int m_pairs_cap = 0;
 };
 
 // error helpers -------------------------------------------------------------------------------
@@ -122,6 +135,13 @@ void set_global_error(const std::string& s);
     }                                                                                                \
   } while (0)
 
+// profiling tags: 0..L_NUM-1 = layers, then the stages below
+enum ProfTag { P_PREP_STATS = L_NUM, P_PREP_NORM, P_PYRAMID, P_HEATMAP_OUT, P_KEYPOINT_OUT, P_NMS, P_TOPK, P_DESCRIBE, P_MATCH_TILE,
+               P_MATCH_MERGE, P_DIST_MATRIX, P_NUM };
+static_assert(P_NUM <= XFB_PROF_TAGS, "profile tag table");
+void prof_begin(Ctx* c, int tag);
+void prof_end(Ctx* c);
+
 // kernel launchers (each returns a cudaError_t from cudaGetLastError) -------------------------
 cudaError_t launch_prep(Ctx* c, const uint8_t* d_gray, size_t frame_stride, int stride);
 cudaError_t launch_conv_layer(Ctx* c, int layer);       // all BasicLayers + block_fusion.2
@@ -131,7 +151,8 @@ cudaError_t launch_keypoint_out(Ctx* c);                 // keypoint_head.3 + so
 cudaError_t launch_post(Ctx* c, int topk, float nms_thr, int32_t* d_nvalid, float* d_xy, float* d_score, float* d_desc);
 cudaError_t launch_distance_matrix(Ctx* c, const float* dA, int n1, const float* dB, int n2, int32_t* d_out);
 cudaError_t launch_match(Ctx* c, const float* dA, int n1, const float* dB, int n2, const int32_t* ga, const int32_t* gb, int init,
-                         int32_t* bi, int32_t* bd, int32_t* sd, int32_t* ri, int32_t* rd);
+                         int32_t* bi, int32_t* bd, int32_t* sd, int32_t* ri, int32_t* rd, const int32_t* n1p = nullptr,
+                         const int32_t* n2p = nullptr);
 size_t conv_part_elems(int H, int W);  // partial-sum scratch (doubles) needed per frame
 
 }  // namespace xfb
