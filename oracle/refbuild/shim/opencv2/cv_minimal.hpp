@@ -71,6 +71,13 @@ struct KeyPoint {
         class_id(class_id_) {}
 };
 
+struct DMatch {
+  int queryIdx, trainIdx, imgIdx;
+  float distance;
+  DMatch() : queryIdx(-1), trainIdx(-1), imgIdx(-1), distance(3.4e38f) {}
+  DMatch(int q, int t, float d) : queryIdx(q), trainIdx(t), imgIdx(-1), distance(d) {}
+};
+
 class _OutputArray;
 
 // Dense 2-D matrix with shared ownership of its storage (row views alias the

@@ -1,0 +1,92 @@
+// host_dropin_driver.cc -- exercises the C++ drop-in classes (xfeatslam_b200/host) the way
+// Frame::ExtractXF (src/Frame.cc:611-618) and Tracking (src/Tracking.cc:2518) call the reference.
+// Built by tests/test_gpu_host_dropin.py against the cv stand-in header; prints nothing but writes
+// raw float files the Python test compares with the reference's golden output / the C oracle.
+//   extract <frame.u8> H W nfeatures lap0 lap1 <out_prefix>
+//   init    <descA.f32> nA <kpA.f32> <descB.f32> nB <kpB.f32> W H window ratio <out.i32>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "XFBmatcher.h"
+#include "XFextractor.h"
+
+template <typename T>
+static std::vector<T> slurp(const std::string& p, size_t n) {
+  std::vector<T> v(n);
+  std::ifstream is(p, std::ios::binary);
+  is.read(reinterpret_cast<char*>(v.data()), static_cast<std::streamsize>(n * sizeof(T)));
+  if (static_cast<size_t>(is.gcount()) != n * sizeof(T)) { std::cerr << "short read " << p << std::endl; std::exit(2); }
+  return v;
+}
+template <typename T>
+static void spit(const std::string& p, const std::vector<T>& v) {
+  std::ofstream os(p, std::ios::binary);
+  os.write(reinterpret_cast<const char*>(v.data()), static_cast<std::streamsize>(v.size() * sizeof(T)));
+}
+
+int main(int argc, char** argv) {
+  const std::string mode = argc > 1 ? argv[1] : "";
+  if (mode == "extract" && argc >= 9) {
+    const int H = std::atoi(argv[3]), W = std::atoi(argv[4]), nfeat = std::atoi(argv[5]);
+    std::vector<int> lap = {std::atoi(argv[6]), std::atoi(argv[7])};
+    auto buf = slurp<unsigned char>(argv[2], static_cast<size_t>(H) * W);
+    cv::Mat im(H, W, CV_8UC1, buf.data());
+    ORB_SLAM3::XFextractor ex(nfeat, 1.2f, 8, 20, 7);
+    std::vector<cv::KeyPoint> kps;
+    cv::Mat desc;
+    cv::Mat empty;
+    if (ex(empty, cv::Mat(), kps, desc, lap) != -1) return 3;          // empty image -> -1 (src/XFextractor.cc:253)
+    const int ret = ex(im, cv::Mat(), kps, desc, lap);
+    std::vector<float> k(kps.size() * 7), d(static_cast<size_t>(desc.rows) * desc.cols);
+    for (size_t i = 0; i < kps.size(); ++i) {
+      k[7 * i] = kps[i].pt.x; k[7 * i + 1] = kps[i].pt.y; k[7 * i + 2] = kps[i].response; k[7 * i + 3] = kps[i].size;
+      k[7 * i + 4] = kps[i].angle; k[7 * i + 5] = static_cast<float>(kps[i].octave); k[7 * i + 6] = static_cast<float>(kps[i].class_id);
+    }
+    for (int r = 0; r < desc.rows; ++r) std::memcpy(d.data() + static_cast<size_t>(r) * desc.cols, desc.ptr<float>(r), sizeof(float) * desc.cols);
+    const std::string pre = argv[8];
+    spit(pre + ".kp", k);
+    spit(pre + ".desc", d);
+    std::vector<float> meta = {static_cast<float>(ret), static_cast<float>(kps.size()), static_cast<float>(desc.rows), static_cast<float>(ex.GetLevels()),
+                               ex.GetScaleFactor(), ex.GetScaleFactors()[7], ex.GetInverseScaleSigmaSquares()[3]};
+    spit(pre + ".meta", meta);
+    return 0;
+  }
+  if (mode == "init" && argc >= 14) {
+    const int nA = std::atoi(argv[3]), nB = std::atoi(argv[6]);
+    auto dA = slurp<float>(argv[2], static_cast<size_t>(nA) * 64), kA = slurp<float>(argv[4], static_cast<size_t>(nA) * 2);
+    auto dB = slurp<float>(argv[5], static_cast<size_t>(nB) * 64), kB = slurp<float>(argv[7], static_cast<size_t>(nB) * 2);
+    const int W = std::atoi(argv[8]), H = std::atoi(argv[9]), window = std::atoi(argv[10]);
+    const float ratio = static_cast<float>(std::atof(argv[11]));
+    cv::Mat A(nA, 64, CV_32F, dA.data()), B(nB, 64, CV_32F, dB.data());
+    std::vector<cv::KeyPoint> ka(nA), kb(nB);
+    std::vector<cv::Point2f> prev(nA);
+    for (int i = 0; i < nA; ++i) { ka[i] = cv::KeyPoint(kA[2 * i], kA[2 * i + 1], 1, -1, 1.f); prev[i] = ka[i].pt; }
+    for (int i = 0; i < nB; ++i) kb[i] = cv::KeyPoint(kB[2 * i], kB[2 * i + 1], 1, -1, 1.f);
+    ORB_SLAM3::XFextractor ex(64, 1.2f, 8, 20, 7);   // only to own a context
+    cv::Mat tiny(32, 32, CV_8UC1);
+    std::memset(tiny.data, 7, 32 * 32);
+    std::vector<cv::KeyPoint> tk; cv::Mat td; std::vector<int> lap = {0, 0};
+    ex(tiny, cv::Mat(), tk, td, lap);
+    ORB_SLAM3::XFBmatcher m(ex.context(), ratio, true);
+    std::vector<int> m12;
+    const int n = m.SearchForInitialization(ka, A, kb, B, 0.f, 0.f, static_cast<float>(W), static_cast<float>(H), prev, m12, window);
+    std::vector<cv::DMatch> mm;
+    m.match(A, B, mm);
+    std::vector<int> out;
+    out.push_back(n);
+    out.insert(out.end(), m12.begin(), m12.end());
+    out.push_back(static_cast<int>(mm.size()));
+    for (auto& x : mm) { out.push_back(x.queryIdx); out.push_back(x.trainIdx); }
+    spit(argv[12], out);
+    std::vector<float> pv(static_cast<size_t>(nA) * 2);
+    for (int i = 0; i < nA; ++i) { pv[2 * i] = prev[i].x; pv[2 * i + 1] = prev[i].y; }
+    spit(argv[13], pv);
+    return 0;
+  }
+  std::cerr << "usage: extract ... | init ..." << std::endl;
+  return 1;
+}
