@@ -228,7 +228,7 @@ def run_b200(args):
     h_xy = torch.zeros(Bsz, TOPK, 2, dtype=torch.float32).pin_memory()
     h_sc = torch.zeros(Bsz, TOPK, dtype=torch.float32).pin_memory()
     h_ds = torch.zeros(Bsz, TOPK, 64, dtype=torch.float32).pin_memory()
-    h_m = [torch.zeros(Bsz, TOPK, dtype=torch.int32).pin_memory() for _ in range(3)]   # best_idx, best_dist, second_dist
+    h_m = [torch.zeros(Bsz, TOPK, dtype=torch.int32).pin_memory() for _ in range(5)]   # best_idx, best_dist, second_dist, rev_idx, rev_dist
 
     def step_device(i):
         fr = dev_pool[i % POOL]
@@ -240,7 +240,7 @@ def run_b200(args):
         fr = host_pool[i % POOL]
         ctx.extract_ptrs(fr.data_ptr(), Bsz, H * W, H, W, W, TOPK, 0.05, h_nv.data_ptr(), h_xy.data_ptr(), h_sc.data_ptr(), h_ds.data_ptr(),
                          device=False)
-        ctx.match_frame_pairs(pairs, INT_MAX, [h_m[0].data_ptr(), h_m[1].data_ptr(), h_m[2].data_ptr(), 0, 0], device=False)
+        ctx.match_frame_pairs(pairs, INT_MAX, [t.data_ptr() for t in h_m], device=False)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -301,7 +301,7 @@ def run_b200(args):
             pipe = "fp32-simt"
         elif name == "match_tile":
             alg = 2.0 * TOPK * TOPK * 64
-            pipe = "fp64-simt (exact cv::norm restatement)"
+            pipe = "tcgen05 kind::tf32 (3xTF32 split) + exact fp64 fix-up"
         else:
             alg = 0.0
             pipe = "n/a"
@@ -320,7 +320,7 @@ def run_b200(args):
                    "sample": "16 VGA frames reference XFextractor (libtorch CPU, %d threads, %.1f ms/frame) + 3 brute-force 4096x4096 matches "
                              "(C port, 1 thread, %.2f s/pair)" % (r["extract_threads"], r["extract_s_per_frame"] * 1e3, r["match_s_per_pair"])}
         frame_bytes = H * W
-        out_bytes = TOPK * (8 + 4 + 256) + 4 + 3 * TOPK * 4
+        out_bytes = TOPK * (8 + 4 + 256) + 4 + 5 * TOPK * 4
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_dev_max / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -125,6 +125,9 @@ long xfb_debug_read_stats(xfb_ctx* ctx, const char* name, int frame, float* host
  * on oracle-provided inputs.  Inputs are host fp32; outputs as in xfb_extract. */
 int xfb_debug_post(xfb_ctx* ctx, int H, int W, const float* feats, const float* H1, const float* K1h, int topk, float nms_thr,
                    int32_t* n_valid, float* kpt_xy, float* score, float* desc);
+/* Largest |t - 512*float(||a-b||^2)| over all pairs, where t is the tensor-core (3xTF32) estimate the
+ * matcher filters on: must stay well below the kernel's MATCH_EPS = 0.02 for the filter to be sound. */
+int xfb_debug_match_error(xfb_ctx* ctx, const float* A, int n1, const float* B, int n2, float* max_err);
 /* Number of NMS candidates (score > 0) of `frame` in the last extract call. */
 int xfb_debug_candidates(xfb_ctx* ctx, int frame);
 /* Total number of kernels this ctx has launched so far. */

@@ -89,3 +89,15 @@ def test_full_size_4096_properties(ctx):
     rows = rng.choice(4096, 64, replace=False)
     w = mo.bruteforce(A[rows], B)
     assert np.array_equal(bi[rows], w[0]) and np.array_equal(bd[rows], w[1]) and np.array_equal(sd[rows], w[2])
+
+
+def test_tensor_core_estimate_error_bound(ctx):
+    """The matcher filters on a 3xTF32 tensor-core estimate t of 512*d; the filter is sound while
+    |t - 512*float(S)| < MATCH_EPS = 0.02 (csrc/match_tc.cu).  Measure the actual maximum over all pairs."""
+    rng = np.random.RandomState(13)
+    A = unit(rng, 1024)
+    B = np.concatenate([related(rng, A, 512, 0.02), related(rng, A, 256, 0.3), unit(rng, 256)]).astype(np.float32)
+    B[3] = 0                                               # phantom row
+    B[4] = A[0]                                            # exact duplicate -> distance 0
+    err = ctx.match_error(A, B)
+    assert err < 0.005, err

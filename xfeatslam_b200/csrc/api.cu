@@ -39,7 +39,7 @@ void prof_end(Ctx* c) {
   c->prof_ev.push_back(e);
 }
 static const char* kStageNames[] = {"prep_stats", "prep_norm", "pyramid_sum", "heatmap_out", "keypoint_out_softmax_fold", "nms_score",
-                                    "topk_select_sort", "describe", "match_tile", "match_merge", "distance_matrix"};
+                                    "topk_select_sort", "describe", "match_tile", "match_merge", "distance_matrix", "match_prep"};
 
 // ---- weight blob (tools/convert_weights.py) --------------------------------------------------------
 #pragma pack(push, 1)
@@ -177,6 +177,99 @@ static int ensure_match_scratch(Ctx* c, int n1, int n2, bool want_matrix) {
   return XFB_OK;
 }
 
+// ---- tensor-core matcher plumbing (match_tc.cu) -------------------------------------------------------------
+static inline int pad128(int n) { return n <= 0 ? 128 : (n + 127) / 128 * 128; }
+
+static int tc_ensure_generic(Ctx* c, int n1, int n2) {
+  const int need = pad128(n1 > n2 ? n1 : n2);
+  if (need > c->tc_cap) {
+    for (int i = 0; i < 2; ++i) { if (c->tc_img[i]) cudaFree(c->tc_img[i]); if (c->tc_nrm[i]) cudaFree(c->tc_nrm[i]); c->tc_img[i] = nullptr; c->tc_nrm[i] = nullptr; }
+    for (int i = 0; i < 2; ++i) { XFB_ALLOC(c, c->tc_img[i], (size_t)need * 128 * 4); XFB_ALLOC(c, c->tc_nrm[i], (size_t)need * 4); }
+    c->tc_cap = need;
+  }
+  if (!c->tc_dbg) XFB_ALLOC(c, c->tc_dbg, 16);
+  return XFB_OK;
+}
+
+// A [n1,64], B [n2,64] device fp32; outputs device int32 (nullable)
+static int tc_match_generic(Ctx* c, const float* dA, int n1, const float* dB, int n2, const int32_t* ga, const int32_t* gb, int init,
+                            int32_t* bi, int32_t* bd, int32_t* sd, int32_t* ri, int32_t* rd) {
+  int r = tc_ensure_generic(c, n1, n2);
+  if (r != XFB_OK) return r;
+  const int p1 = pad128(n1), p2 = pad128(n2);
+  XFB_CUDA_OK(c, launch_match_prep(c, dA, 0, 1, nullptr, n1, p1, c->tc_img[0], 0, c->tc_nrm[0]));
+  XFB_CUDA_OK(c, launch_match_prep(c, dB, 0, 1, nullptr, n2, p2, c->tc_img[1], 0, c->tc_nrm[1]));
+  MatchTcArgs a = {};
+  a.init = init;
+  const bool grouped = ga && gb;
+  if (n1 > 0 && (bi || bd || sd)) {
+    a.imgA = c->tc_img[0]; a.imgB = c->tc_img[1]; a.nrmA = c->tc_nrm[0]; a.nrmB = c->tc_nrm[1]; a.rawA = dA; a.rawB = dB;
+    a.gA = ga; a.gB = gb; a.nA_host = n1; a.nB_host = n2; a.rows_padded_A = p1; a.rows_padded_B = p2; a.out_stride = n1;
+    a.best_idx = bi; a.best_dist = bd; a.second_dist = sd;
+    XFB_CUDA_OK(c, launch_match_tc(c, a, p1 / 128, 1, grouped));
+  }
+  if (n2 > 0 && (ri || rd)) {   // column-wise best == row-wise best of the transposed problem (distances are symmetric, bit for bit)
+    a.imgA = c->tc_img[1]; a.imgB = c->tc_img[0]; a.nrmA = c->tc_nrm[1]; a.nrmB = c->tc_nrm[0]; a.rawA = dB; a.rawB = dA;
+    a.gA = gb; a.gB = ga; a.nA_host = n2; a.nB_host = n1; a.rows_padded_A = p2; a.rows_padded_B = p1; a.out_stride = n2;
+    a.best_idx = ri; a.best_dist = rd; a.second_dist = nullptr;
+    XFB_CUDA_OK(c, launch_match_tc(c, a, p2 / 128, 1, grouped));
+  }
+  return XFB_OK;
+}
+
+static int tc_matrix_generic(Ctx* c, const float* dA, int n1, const float* dB, int n2, int32_t* d_out, float* dbg) {
+  int r = tc_ensure_generic(c, n1, n2);
+  if (r != XFB_OK) return r;
+  const int p1 = pad128(n1), p2 = pad128(n2);
+  XFB_CUDA_OK(c, launch_match_prep(c, dA, 0, 1, nullptr, n1, p1, c->tc_img[0], 0, c->tc_nrm[0]));
+  XFB_CUDA_OK(c, launch_match_prep(c, dB, 0, 1, nullptr, n2, p2, c->tc_img[1], 0, c->tc_nrm[1]));
+  MatchTcArgs a = {};
+  a.imgA = c->tc_img[0]; a.imgB = c->tc_img[1]; a.nrmA = c->tc_nrm[0]; a.nrmB = c->tc_nrm[1]; a.rawA = dA; a.rawB = dB;
+  a.nA_host = n1; a.nB_host = n2; a.rows_padded_A = p1; a.rows_padded_B = p2; a.matrix = d_out; a.dbg_maxerr = dbg;
+  XFB_CUDA_OK(c, launch_matrix_tc(c, a, p1 / 128));
+  return XFB_OK;
+}
+
+// frames of the last extract: pairs (host) -> outputs [n_pairs][K] (device pointers, nullable)
+static int tc_match_frames(Ctx* c, const int32_t* pairs, int n_pairs, int init, int32_t* o[5]) {
+  const int K = c->last_topk, P = pad128(K);
+  const size_t img_stride = (size_t)P * 128;
+  if (!c->tc_fimg || c->tc_frows < P) {
+    if (c->tc_fimg) cudaFree(c->tc_fimg);
+    if (c->tc_fnrm) cudaFree(c->tc_fnrm);
+    c->tc_fimg = nullptr; c->tc_fnrm = nullptr;
+    const int PM = pad128(c->max_topk);
+    XFB_ALLOC(c, c->tc_fimg, (size_t)c->max_batch * PM * 128 * 4);
+    XFB_ALLOC(c, c->tc_fnrm, (size_t)c->max_batch * PM * 4);
+    c->tc_frows = PM;
+    c->tc_fvalid = false;
+  }
+  if (!c->tc_fvalid) {
+    XFB_CUDA_OK(c, launch_match_prep(c, c->last_desc, (size_t)K * 64, c->B, c->last_nvalid, K, P, c->tc_fimg, img_stride, c->tc_fnrm));
+    c->tc_fvalid = true;
+  }
+  for (int p0 = 0; p0 < n_pairs; p0 += 64) {
+    const int np = (n_pairs - p0) < 64 ? (n_pairs - p0) : 64;
+    MatchTcArgs a = {};
+    a.imgA = a.imgB = c->tc_fimg; a.nrmA = a.nrmB = c->tc_fnrm; a.rawA = a.rawB = c->last_desc;
+    a.nA_dev = a.nB_dev = c->last_nvalid; a.nA_host = a.nB_host = K; a.rows_padded_A = a.rows_padded_B = P;
+    a.img_stride_A = a.img_stride_B = img_stride; a.raw_stride_A = a.raw_stride_B = (size_t)K * 64;
+    a.init = init; a.out_stride = K;
+    if (o[0] || o[1] || o[2]) {
+      for (int p = 0; p < np; ++p) { a.pairs[2 * p] = pairs[2 * (p0 + p)]; a.pairs[2 * p + 1] = pairs[2 * (p0 + p) + 1]; }
+      a.best_idx = o[0] ? o[0] + (size_t)p0 * K : nullptr; a.best_dist = o[1] ? o[1] + (size_t)p0 * K : nullptr;
+      a.second_dist = o[2] ? o[2] + (size_t)p0 * K : nullptr;
+      XFB_CUDA_OK(c, launch_match_tc(c, a, P / 128, np, false));
+    }
+    if (o[3] || o[4]) {
+      for (int p = 0; p < np; ++p) { a.pairs[2 * p] = pairs[2 * (p0 + p) + 1]; a.pairs[2 * p + 1] = pairs[2 * (p0 + p)]; }
+      a.best_idx = o[3] ? o[3] + (size_t)p0 * K : nullptr; a.best_dist = o[4] ? o[4] + (size_t)p0 * K : nullptr; a.second_dist = nullptr;
+      XFB_CUDA_OK(c, launch_match_tc(c, a, P / 128, np, false));
+    }
+  }
+  return XFB_OK;
+}
+
 // ---- the forward pipeline (XFeatModel::forward, src/XFeat.cc:135-173, then :273-316) -----------------
 static int run_dense(Ctx* c, const uint8_t* d_gray, size_t frame_stride, int stride) {
   XFB_CUDA_OK(c, launch_prep(c, d_gray, frame_stride, stride));
@@ -211,7 +304,7 @@ static int extract_device(Ctx* c, const uint8_t* d_gray, int batch, size_t frame
   int r = run_dense(c, d_gray, frame_stride, stride);
   if (r != XFB_OK) return r;
   XFB_CUDA_OK(c, launch_post(c, topk, nms_thr, d_nvalid, d_xy, d_score, d_desc));
-  c->last_topk = topk; c->last_nvalid = d_nvalid; c->last_desc = d_desc;
+  c->last_topk = topk; c->last_nvalid = d_nvalid; c->last_desc = d_desc; c->tc_fvalid = false;
   return XFB_OK;
 }
 
@@ -271,6 +364,8 @@ void xfb_destroy(xfb_ctx* c) {
   fr(c->ticket); fr(c->cand); fr(c->cand_count); fr(c->cand_count_last); fr(c->o_nvalid); fr(c->o_xy); fr(c->o_score); fr(c->o_desc);
   fr(c->m_a); fr(c->m_b); fr(c->m_ga); fr(c->m_gb); fr(c->m_rowpart); fr(c->m_colpart); fr(c->m_matrix);
   for (int i = 0; i < 5; ++i) { fr(c->m_out[i]); fr(c->m_pairs_out[i]); }
+  for (int i = 0; i < 2; ++i) { fr(c->tc_img[i]); fr(c->tc_nrm[i]); }
+  fr(c->tc_fimg); fr(c->tc_fnrm); fr(c->tc_pairs); fr(c->tc_dbg);
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -329,8 +424,8 @@ int xfb_distance_matrix_device(xfb_ctx* c, const float* d_A, int n1, const float
   if (!c) return XFB_ERR_ARG;
   if (n1 < 0 || n2 < 0 || (n1 && !d_A) || (n2 && !d_B) || (n1 && n2 && !d_out)) { c->err = "distance_matrix: bad argument"; return XFB_ERR_ARG; }
   XFB_CUDA_OK(c, cudaSetDevice(c->device));
-  XFB_CUDA_OK(c, launch_distance_matrix(c, d_A, n1, d_B, n2, d_out));
-  return XFB_OK;
+  if (n1 == 0 || n2 == 0) return XFB_OK;
+  return tc_matrix_generic(c, d_A, n1, d_B, n2, d_out, nullptr);
 }
 
 int xfb_distance_matrix(xfb_ctx* c, const float* A, int n1, const float* B, int n2, int32_t* out) {
@@ -342,7 +437,8 @@ int xfb_distance_matrix(xfb_ctx* c, const float* A, int n1, const float* B, int 
   if (r != XFB_OK) return r;
   XFB_CUDA_OK(c, cudaMemcpyAsync(c->m_a, A, (size_t)n1 * 256, cudaMemcpyHostToDevice, c->stream));
   XFB_CUDA_OK(c, cudaMemcpyAsync(c->m_b, B, (size_t)n2 * 256, cudaMemcpyHostToDevice, c->stream));
-  XFB_CUDA_OK(c, launch_distance_matrix(c, c->m_a, n1, c->m_b, n2, c->m_matrix));
+  r = tc_matrix_generic(c, c->m_a, n1, c->m_b, n2, c->m_matrix, nullptr);
+  if (r != XFB_OK) return r;
   XFB_CUDA_OK(c, cudaMemcpyAsync(out, c->m_matrix, (size_t)n1 * n2 * 4, cudaMemcpyDeviceToHost, c->stream));
   XFB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return XFB_OK;
@@ -355,8 +451,7 @@ int xfb_match_device(xfb_ctx* c, const float* d_A, int n1, const float* d_B, int
   XFB_CUDA_OK(c, cudaSetDevice(c->device));
   int r = ensure_match_scratch(c, n1, n2, false);
   if (r != XFB_OK) return r;
-  XFB_CUDA_OK(c, launch_match(c, d_A, n1, d_B, n2, d_ga, d_gb, init_dist, bi, bd, sd, ri, rd));
-  return XFB_OK;
+  return tc_match_generic(c, d_A, n1, d_B, n2, d_ga, d_gb, init_dist, bi, bd, sd, ri, rd);
 }
 
 int xfb_match(xfb_ctx* c, const float* A, int n1, const float* B, int n2, const int32_t* ga, const int32_t* gb, int init_dist,
@@ -372,8 +467,10 @@ int xfb_match(xfb_ctx* c, const float* A, int n1, const float* B, int n2, const 
     if (n1) XFB_CUDA_OK(c, cudaMemcpyAsync(c->m_ga, ga, (size_t)n1 * 4, cudaMemcpyHostToDevice, c->stream));
     if (n2) XFB_CUDA_OK(c, cudaMemcpyAsync(c->m_gb, gb, (size_t)n2 * 4, cudaMemcpyHostToDevice, c->stream));
   }
-  XFB_CUDA_OK(c, launch_match(c, c->m_a, n1, c->m_b, n2, ga ? c->m_ga : nullptr, ga ? c->m_gb : nullptr, init_dist, c->m_out[0],
-                              c->m_out[1], c->m_out[2], c->m_out[3], c->m_out[4]));
+  r = tc_match_generic(c, c->m_a, n1, c->m_b, n2, ga ? c->m_ga : nullptr, ga ? c->m_gb : nullptr, init_dist, best_idx ? c->m_out[0] : nullptr,
+                       best_dist ? c->m_out[1] : nullptr, second_dist ? c->m_out[2] : nullptr, best_idx_rev ? c->m_out[3] : nullptr,
+                       best_dist_rev ? c->m_out[4] : nullptr);
+  if (r != XFB_OK) return r;
   int32_t* host[5] = {best_idx, best_dist, second_dist, best_idx_rev, best_dist_rev};
   for (int i = 0; i < 5; ++i) {
     const int cnt = i < 3 ? n1 : n2;
@@ -383,49 +480,37 @@ int xfb_match(xfb_ctx* c, const float* A, int n1, const float* B, int n2, const 
   return XFB_OK;
 }
 
-int xfb_match_frames(xfb_ctx* c, int fa, int fb, int init_dist, int32_t* best_idx, int32_t* best_dist, int32_t* second_dist,
-                     int32_t* best_idx_rev, int32_t* best_dist_rev) {
-  if (!c) return XFB_ERR_ARG;
-  if (!c->last_desc || fa < 0 || fb < 0 || fa >= c->B || fb >= c->B) { c->err = "match_frames: no extract result for these frames"; return XFB_ERR_ARG; }
-  XFB_CUDA_OK(c, cudaSetDevice(c->device));
-  const int K = c->last_topk;
-  int r = ensure_match_scratch(c, K, K, false);
-  if (r != XFB_OK) return r;
-  XFB_CUDA_OK(c, launch_match(c, c->last_desc + (size_t)fa * K * 64, K, c->last_desc + (size_t)fb * K * 64, K, nullptr, nullptr, init_dist,
-                              c->m_out[0], c->m_out[1], c->m_out[2], c->m_out[3], c->m_out[4], c->last_nvalid + fa, c->last_nvalid + fb));
-  int32_t* host[5] = {best_idx, best_dist, second_dist, best_idx_rev, best_dist_rev};
-  for (int i = 0; i < 5; ++i)
-    if (host[i]) XFB_CUDA_OK(c, cudaMemcpyAsync(host[i], c->m_out[i], (size_t)K * 4, cudaMemcpyDeviceToHost, c->stream));
-  XFB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
-  return XFB_OK;
-}
-
 static int match_pairs_impl(xfb_ctx* c, const int32_t* pairs, int n_pairs, int init_dist, int32_t* o[5], bool to_host) {
   if (!c) return XFB_ERR_ARG;
   if (!pairs || n_pairs < 0 || !c->last_desc) { c->err = "match_frame_pairs: bad argument / no extract result"; return XFB_ERR_ARG; }
   XFB_CUDA_OK(c, cudaSetDevice(c->device));
   const int K = c->last_topk;
-  int r = ensure_match_scratch(c, K, K, false);
-  if (r != XFB_OK) return r;
+  for (int p = 0; p < n_pairs; ++p) {
+    const int fa = pairs[2 * p], fb = pairs[2 * p + 1];
+    if (fa < 0 || fb < 0 || fa >= c->B || fb >= c->B) { c->err = "match_frame_pairs: frame index out of range"; return XFB_ERR_ARG; }
+  }
   if (to_host && n_pairs > c->m_pairs_cap) {
     for (int i = 0; i < 5; ++i) { if (c->m_pairs_out[i]) cudaFree(c->m_pairs_out[i]); c->m_pairs_out[i] = nullptr; }
     for (int i = 0; i < 5; ++i) XFB_ALLOC(c, c->m_pairs_out[i], (size_t)n_pairs * c->max_topk * 4);
     c->m_pairs_cap = n_pairs;
   }
-  for (int p = 0; p < n_pairs; ++p) {
-    const int fa = pairs[2 * p], fb = pairs[2 * p + 1];
-    if (fa < 0 || fb < 0 || fa >= c->B || fb >= c->B) { c->err = "match_frame_pairs: frame index out of range"; return XFB_ERR_ARG; }
-    int32_t* d[5];
-    for (int i = 0; i < 5; ++i) d[i] = to_host ? (o[i] ? c->m_pairs_out[i] + (size_t)p * K : nullptr) : (o[i] ? o[i] + (size_t)p * K : nullptr);
-    XFB_CUDA_OK(c, launch_match(c, c->last_desc + (size_t)fa * K * 64, K, c->last_desc + (size_t)fb * K * 64, K, nullptr, nullptr, init_dist,
-                                d[0], d[1], d[2], d[3], d[4], c->last_nvalid + fa, c->last_nvalid + fb));
-  }
+  int32_t* d[5];
+  for (int i = 0; i < 5; ++i) d[i] = o[i] ? (to_host ? c->m_pairs_out[i] : o[i]) : nullptr;
+  int r = tc_match_frames(c, pairs, n_pairs, init_dist, d);
+  if (r != XFB_OK) return r;
   if (to_host) {
     for (int i = 0; i < 5; ++i)
       if (o[i] && n_pairs) XFB_CUDA_OK(c, cudaMemcpyAsync(o[i], c->m_pairs_out[i], (size_t)n_pairs * K * 4, cudaMemcpyDeviceToHost, c->stream));
     XFB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   }
   return XFB_OK;
+}
+
+int xfb_match_frames(xfb_ctx* c, int fa, int fb, int init_dist, int32_t* best_idx, int32_t* best_dist, int32_t* second_dist,
+                     int32_t* best_idx_rev, int32_t* best_dist_rev) {
+  const int32_t pair[2] = {fa, fb};
+  int32_t* o[5] = {best_idx, best_dist, second_dist, best_idx_rev, best_dist_rev};
+  return match_pairs_impl(c, pair, 1, init_dist, o, true);
 }
 
 int xfb_match_frame_pairs(xfb_ctx* c, const int32_t* pairs, int n_pairs, int init_dist, int32_t* bi, int32_t* bd, int32_t* sd, int32_t* ri,
@@ -437,6 +522,23 @@ int xfb_match_frame_pairs_device(xfb_ctx* c, const int32_t* pairs, int n_pairs, 
                                  int32_t* ri, int32_t* rd) {
   int32_t* o[5] = {bi, bd, sd, ri, rd};
   return match_pairs_impl(c, pairs, n_pairs, init_dist, o, false);
+}
+
+int xfb_debug_match_error(xfb_ctx* c, const float* A, int n1, const float* B, int n2, float* max_err) {
+  if (!c || !A || !B || !max_err || n1 <= 0 || n2 <= 0) return XFB_ERR_ARG;
+  XFB_CUDA_OK(c, cudaSetDevice(c->device));
+  int r = ensure_match_scratch(c, n1, n2, true);
+  if (r != XFB_OK) return r;
+  r = tc_ensure_generic(c, n1, n2);
+  if (r != XFB_OK) return r;
+  XFB_CUDA_OK(c, cudaMemcpyAsync(c->m_a, A, (size_t)n1 * 256, cudaMemcpyHostToDevice, c->stream));
+  XFB_CUDA_OK(c, cudaMemcpyAsync(c->m_b, B, (size_t)n2 * 256, cudaMemcpyHostToDevice, c->stream));
+  XFB_CUDA_OK(c, cudaMemsetAsync(c->tc_dbg, 0, 4, c->stream));
+  r = tc_matrix_generic(c, c->m_a, n1, c->m_b, n2, c->m_matrix, c->tc_dbg);
+  if (r != XFB_OK) return r;
+  XFB_CUDA_OK(c, cudaMemcpyAsync(max_err, c->tc_dbg, 4, cudaMemcpyDeviceToHost, c->stream));
+  XFB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return XFB_OK;
 }
 
 int xfb_profile_enable(xfb_ctx* c, int enable) {

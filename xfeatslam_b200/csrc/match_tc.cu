@@ -1,0 +1,410 @@
+// match_tc.cu -- brute-force 64-D descriptor matching on the 5th-gen tensor cores (tcgen05 / TMEM).
+//
+// What must come out is the reference's INTEGER distance (ORBmatcher::DescriptorDistance,
+// src/ORBmatcher.cc:2242-2250: int(float(||a-b||^2) * 512), fp32 subtract + fp64 accumulate) and the
+// best / second-best scan of src/ORBmatcher.cc:476-486 (strict '<', ascending index), bit-exact w.r.t.
+// oracle/matcher_oracle.c.  ||a-b||^2 has no GEMM form that rounds like that, so the kernel is a
+// FILTER + EXACT FIX-UP:
+//
+//   1. tensor cores: dot(a_i, b_j) for a 128-row tile against all columns, 128 columns at a time, as a
+//      3xTF32 split product (a = hi + lo exactly; hi*hi + hi*lo + lo*hi; |error| ~ 1e-6), fp32
+//      accumulators in TMEM;   t_ij = 512 (|a_i|^2 + |b_j|^2 - 2 dot)  ~  512 * d_ij  within +-MATCH_EPS.
+//   2. epilogue (one thread per row = one TMEM lane, columns scanned in ascending order, i.e. exactly the
+//      reference's scan): a pair can only change (best, second) if t_ij - EPS < second; for those few,
+//      D = floor(t) when t is farther than EPS from an integer, else the exact fp64 re-evaluation.
+//
+// Warp roles (576 threads): warp 0 = loader (cp.async.bulk of pre-tiled operand images + mbarrier
+// complete_tx), warp 1 = TMEM allocator + single-thread tcgen05.mma issuer, warps 2..17 = epilogue
+// (tcgen05.ld 32x32b; 4 warps per TMEM lane quadrant, each owning a 32-column slice of every 128-column
+// block, merged at the end in the total order (distance, index)).  The hot loop is branch-free: u = dot -
+// |b|^2/2, a max over the 32 columns, and ONE compare against the per-row bound tau.  smem: A tile 64 KB + 2 x 64 KB B stages; TMEM: 2 x 128
+// fp32 accumulator columns.  Operand images are written by match_prep_kernel directly in the canonical
+// K-major no-swizzle UMMA layout ([k-chunk 16 B][8-row group][8 rows][16 B]; LBO = 2048 B, SBO = 128 B), so
+// the loader needs no tensor map: one contiguous 64 KB bulk copy per 128-row block.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "xfb_internal.h"
+
+namespace xfb {
+
+constexpr int TC_ROWS = 128;                 // rows (or columns) per operand block
+constexpr int TC_BLOCK_FLOATS = 128 * 64;    // one hi or lo image of a block
+constexpr int TC_IMG_BYTES = 2 * TC_BLOCK_FLOATS * 4;   // hi + lo = 64 KB
+constexpr float MATCH_EPS = 0.02f;           // bound on |t - 512*float(S)| used by the filter (measured max ~1e-3, see xfb_debug_match_error)
+constexpr int TC_PARTS = 4;                  // 32-column slices per block = epilogue threads per row
+constexpr int TC_EPI_WARPS = 4 * TC_PARTS;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // loader warp + MMA warp + epilogue warps
+constexpr uint32_t TC_LBO = 2048, TC_SBO = 128;
+
+// ---- operand images ---------------------------------------------------------------------------------------
+// element (r, k) of a block -> float index inside the hi (or lo) image
+__host__ __device__ __forceinline__ int img_index(int r, int k) { return ((k >> 2) * 16 + (r >> 3)) * 32 + (r & 7) * 4 + (k & 3); }
+
+// One thread per (row, 4 consecutive k).  Rows >= n (per set) are zero-filled up to the padded row count.
+__global__ void __launch_bounds__(256) match_prep_kernel(const float* desc, size_t set_stride, const int32_t* n_dev, int n_host,
+                                                         int rows_padded, float* img, size_t img_set_stride, float* nrm) {
+  const int set = blockIdx.y;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;   // row * 16 + kq
+  const int row = g >> 4, kq = g & 15;
+  if (row >= rows_padded) return;
+  const int n = n_dev ? min(n_host, n_dev[set]) : n_host;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row < n) v = *reinterpret_cast<const float4*>(desc + (size_t)set * set_stride + (size_t)row * 64 + kq * 4);
+  float4 hi, lo;
+  hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = v.x - hi.x;   // exact split: hi has 11 significant bits
+  hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = v.y - hi.y;
+  hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = v.z - hi.z;
+  hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
+  const int blk = row >> 7, r = row & 127;
+  float* base = img + (size_t)set * img_set_stride + (size_t)blk * (2 * TC_BLOCK_FLOATS);
+  const int idx = img_index(r, kq * 4);
+  *reinterpret_cast<float4*>(base + idx) = hi;
+  *reinterpret_cast<float4*>(base + TC_BLOCK_FLOATS + idx) = lo;
+  // |a|^2: fp64 accumulate across the 16 threads of a row (lanes kq = 0..15 are contiguous in a half warp)
+  double s = (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+#pragma unroll
+  for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off, 16);
+  if (kq == 0) nrm[(size_t)set * rows_padded + row] = (float)s;
+}
+
+// ---- PTX helpers --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  // K-major, SWIZZLE_NONE: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version(1) <<46
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(TC_LBO >> 4) << 16) | ((uint64_t)(TC_SBO >> 4) << 32) | (1ull << 46);
+}
+// kind::tf32, D = F32, A/B = TF32 K-major, M = 128, N = 128
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
+      "%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]), "=r"(u[10]),
+        "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]),
+        "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]),
+        "=r"(u[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+
+__device__ __noinline__ int exact_distance(const float* sA_hi, const float* sA_lo, int r, const float* brow) {
+  double s = 0.0;
+#pragma unroll 4
+  for (int kq = 0; kq < 16; ++kq) {
+    const int idx = img_index(r, kq * 4);
+    const float4 h = *reinterpret_cast<const float4*>(sA_hi + idx);
+    const float4 l = *reinterpret_cast<const float4*>(sA_lo + idx);
+    const float4 b = *reinterpret_cast<const float4*>(brow + kq * 4);
+    float d;
+    d = (h.x + l.x) - b.x; s = fma((double)d, (double)d, s);   // hi + lo == a exactly
+    d = (h.y + l.y) - b.y; s = fma((double)d, (double)d, s);
+    d = (h.z + l.z) - b.z; s = fma((double)d, (double)d, s);
+    d = (h.w + l.w) - b.w; s = fma((double)d, (double)d, s);
+  }
+  return (int)(__double2float_rn(s) * 512.0f);
+}
+__device__ __noinline__ float exact_scaled(const float* sA_hi, const float* sA_lo, int r, const float* brow) {
+  double s = 0.0;
+  for (int k = 0; k < 64; ++k) {
+    const int idx = img_index(r, k);
+    const float d = (sA_hi[idx] + sA_lo[idx]) - brow[k];
+    s = fma((double)d, (double)d, s);
+  }
+  return __double2float_rn(s) * 512.0f;
+}
+
+// Candidate handling for one 32-column slice (rare path).  `u[e] = dot - |b|^2/2` was computed by the caller.
+struct RowState { int b1, bidx, b2; float thr, tau; };
+__device__ __forceinline__ void row_state_refresh(RowState& st, float base) {
+  st.thr = (st.b2 == 0x7fffffff) ? CUDART_INF_F : (float)st.b2 + MATCH_EPS;
+  // t < thr  <=>  dot - |b|^2/2 > (base - thr)/1024 ; the extra 1e-3 covers the re-association rounding
+  st.tau = (st.b2 == 0x7fffffff) ? -CUDART_INF_F : (base - st.thr - 1e-3f) * (1.0f / 1024.0f);
+}
+
+template <bool MATRIX, bool GROUPED>
+__global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(const MatchTcArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  float* sA = reinterpret_cast<float*>(smem_raw);                     // [hi 32 KB][lo 32 KB]
+  float* sB0 = sA + 2 * TC_BLOCK_FLOATS;                              // 2 stages x 64 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB0 + 2 * 2 * TC_BLOCK_FLOATS);
+  uint64_t* bar_a = bars + 0;          // A tile landed
+  uint64_t* bar_full = bars + 1;       // [2] B stage landed
+  uint64_t* bar_empty = bars + 3;      // [2] B stage consumed by the tensor core
+  uint64_t* bar_accf = bars + 5;       // [2] accumulator ready
+  uint64_t* bar_acce = bars + 7;       // [2] accumulator drained by the epilogue
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 9);
+  int* sTop = reinterpret_cast<int*>(bars + 10);                      // [TC_PARTS][128][3] per-slice row results
+  int* sBound = sTop + TC_PARTS * TC_ROWS * 3;                        // [128] best known upper bound of each row's second-best
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.y;
+  const int setA = a.pairs[2 * pair], setB = a.pairs[2 * pair + 1];
+  const int nA = a.nA_dev ? min(a.nA_host, a.nA_dev[setA]) : a.nA_host;
+  const int nB = a.nB_dev ? min(a.nB_host, a.nB_dev[setB]) : a.nB_host;
+  const int row0 = blockIdx.x * TC_ROWS;
+  const int nblk = (row0 < nA) ? (nB + TC_ROWS - 1) / TC_ROWS : 0;    // column blocks to visit
+  const float* imgA = a.imgA + (size_t)setA * a.img_stride_A + (size_t)blockIdx.x * (2 * TC_BLOCK_FLOATS);
+  const float* imgB = a.imgB + (size_t)setB * a.img_stride_B;
+
+  if (threadIdx.x < TC_ROWS) sBound[threadIdx.x] = a.init;
+  if (threadIdx.x == 0) {
+    mbar_init(bar_a, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); mbar_init(bar_accf + s, 1); mbar_init(bar_acce + s, TC_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===== loader =====
+    if (lane == 0 && nblk > 0) {
+      mbar_expect_tx(bar_a, TC_IMG_BYTES);
+      bulk_g2s(sA, imgA, TC_IMG_BYTES, bar_a);
+      for (int c = 0; c < nblk; ++c) {
+        const int s = c & 1;
+        if (c >= 2) mbar_wait(bar_empty + s, ((c >> 1) - 1) & 1);
+        mbar_expect_tx(bar_full + s, TC_IMG_BYTES);
+        bulk_g2s(sB0 + (size_t)s * 2 * TC_BLOCK_FLOATS, imgB + (size_t)c * (2 * TC_BLOCK_FLOATS), TC_IMG_BYTES, bar_full + s);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0 && nblk > 0) {
+      mbar_wait(bar_a, 0);
+      const uint32_t a_hi = smem_u32(sA), a_lo = smem_u32(sA + TC_BLOCK_FLOATS);
+      for (int c = 0; c < nblk; ++c) {
+        const int s = c & 1;
+        mbar_wait(bar_full + s, (c >> 1) & 1);
+        if (c >= 2) mbar_wait(bar_acce + s, ((c >> 1) - 1) & 1);
+        tc_fence_after();
+        const uint32_t b_hi = smem_u32(sB0 + (size_t)s * 2 * TC_BLOCK_FLOATS), b_lo = b_hi + TC_BLOCK_FLOATS * 4;
+        const uint32_t d = tmem_base + (uint32_t)s * 128u;
+#pragma unroll
+        for (int k8 = 0; k8 < 8; ++k8) {
+          const uint32_t ko = (uint32_t)k8 * 2u * TC_LBO;   // 8 tf32 = 2 k-chunks of 16 B
+          umma_tf32(d, umma_desc(a_hi + ko), umma_desc(b_hi + ko), k8 > 0 ? 1u : 0u);
+          umma_tf32(d, umma_desc(a_hi + ko), umma_desc(b_lo + ko), 1u);
+          umma_tf32(d, umma_desc(a_lo + ko), umma_desc(b_hi + ko), 1u);
+        }
+        umma_commit(bar_empty + s);   // smem stage may be refilled once these MMAs have read it
+        umma_commit(bar_accf + s);    // accumulator complete
+      }
+    }
+  } else {
+    // ===== epilogue: TC_PARTS threads per row, each scanning its 32-column slice of every block =====
+    const int quad = warp & 3;                       // TMEM lane quadrant this warp may access (hardware: warp id % 4)
+    const int part = (warp - 2) >> 2;                // which 32-column slice of each 128-column block
+    const int r = quad * 32 + lane;                  // row inside the tile
+    const int row = row0 + r;
+    const bool row_ok = row < nA;
+    RowState st;
+    st.b1 = a.init; st.b2 = a.init; st.bidx = -1;
+    float base = 0.f;
+    int grp = 0;
+    if (row_ok) {
+      base = 512.0f * a.nrmA[(size_t)setA * a.rows_padded_A + row];
+      if (GROUPED) grp = a.gA[row];
+    }
+    row_state_refresh(st, base);
+    if (!row_ok) st.tau = CUDART_INF_F;              // padded rows never take the candidate path
+    const float* nrmB = a.nrmB + (size_t)setB * a.rows_padded_B;
+    const float* rawB = a.rawB + (size_t)setB * a.raw_stride_B;
+    const float* sA_hi = sA;
+    const float* sA_lo = sA + TC_BLOCK_FLOATS;
+    float dbg_max = 0.f;
+    if (nblk > 0) mbar_wait(bar_a, 0);               // the fix-up reads the A tile from shared memory
+#pragma unroll 1
+    for (int c = 0; c < nblk; ++c) {
+      const int s = c & 1;
+      mbar_wait(bar_accf + s, (c >> 1) & 1);
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)s * 128u + (uint32_t)part * 32u, v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acce + s);      // values are in registers: release the accumulator early
+      const int j0 = c * TC_ROWS + part * 32;
+      // hot path: u = dot - |b|^2/2, group maxima, one branch per 32 columns
+      float mg[8];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 nb = *reinterpret_cast<const float4*>(nrmB + j0 + 4 * g);
+        v[4 * g + 0] = fmaf(-0.5f, nb.x, v[4 * g + 0]); v[4 * g + 1] = fmaf(-0.5f, nb.y, v[4 * g + 1]);
+        v[4 * g + 2] = fmaf(-0.5f, nb.z, v[4 * g + 2]); v[4 * g + 3] = fmaf(-0.5f, nb.w, v[4 * g + 3]);
+        mg[g] = fmaxf(fmaxf(v[4 * g], v[4 * g + 1]), fmaxf(v[4 * g + 2], v[4 * g + 3]));
+      }
+      const float m = fmaxf(fmaxf(fmaxf(mg[0], mg[1]), fmaxf(mg[2], mg[3])), fmaxf(fmaxf(mg[4], mg[5]), fmaxf(mg[6], mg[7])));
+      if (MATRIX) {
+        if (row_ok) {
+#pragma unroll 1
+          for (int e = 0; e < 32; ++e) {
+            const int j = j0 + e;
+            if (j >= nB) break;
+            float ue = v[0];
+#pragma unroll
+            for (int q = 1; q < 32; ++q) ue = (q == e) ? v[q] : ue;
+            const float t = fmaf(-1024.0f, ue, base);
+            const float f = floorf(t), fr = t - f;
+            int D;
+            if (fr > MATCH_EPS && fr < 1.0f - MATCH_EPS && t > 0.5f) D = (int)f;
+            else D = exact_distance(sA_hi, sA_lo, r, rawB + (size_t)j * 64);
+            a.matrix[(size_t)row * nB + j] = D;
+            if (a.dbg_maxerr) dbg_max = fmaxf(dbg_max, fabsf(t - exact_scaled(sA_hi, sA_lo, r, rawB + (size_t)j * 64)));
+          }
+        }
+      } else {
+        // tighten the bound with what the other column slices of this row have found.  Ties must pass
+        // (another slice may hold a higher column index with the same distance): shared bound is b2 + 1.
+        const int shared_b2 = sBound[r];
+        float tau = st.tau;
+        if (shared_b2 != 0x7fffffff) tau = fmaxf(tau, (base - ((float)shared_b2 + 1.0f + MATCH_EPS) - 1e-3f) * (1.0f / 1024.0f));
+        if (m > tau) {
+          // candidate path (a few events per row per match): descend through the group maxima
+          bool improved = false;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (mg[g] > tau) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int e = 4 * g + q;
+                if (v[e] > tau) {
+                  const int j = j0 + e;
+                  if (j < nB && (!GROUPED || grp == a.gB[j])) {
+                    const float t = fmaf(-1024.0f, v[e], base);     // = 512 (|a|^2 + |b|^2 - 2 dot)
+                    const float f = floorf(t), fr = t - f;
+                    int D;
+                    if (fr > MATCH_EPS && fr < 1.0f - MATCH_EPS && t > 0.5f) D = (int)f;
+                    else D = exact_distance(sA_hi, sA_lo, r, rawB + (size_t)j * 64);
+                    if (D < st.b1) { st.b2 = st.b1; st.b1 = D; st.bidx = j; improved = true; }
+                    else if (D < st.b2) { st.b2 = D; improved = true; }
+                  }
+                }
+              }
+            }
+          }
+          if (improved) {
+            row_state_refresh(st, base);
+            if (st.b2 < shared_b2) atomicMin(&sBound[r], st.b2);
+          }
+        }
+      }
+    }
+    if (!MATRIX) {
+      sTop[(part * TC_ROWS + r) * 3 + 0] = st.b1;
+      sTop[(part * TC_ROWS + r) * 3 + 1] = st.bidx;
+      sTop[(part * TC_ROWS + r) * 3 + 2] = st.b2;
+    } else if (a.dbg_maxerr) {
+      atomicMax(reinterpret_cast<unsigned int*>(a.dbg_maxerr), __float_as_uint(dbg_max));   // non-negative floats order as uints
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (!MATRIX && threadIdx.x < TC_ROWS) {
+    // merge the column slices of each row in the total order (distance, index) -- order independent, exact
+    const int r = threadIdx.x, row = row0 + r;
+    int b1 = sTop[r * 3], bidx = sTop[r * 3 + 1], b2 = sTop[r * 3 + 2];
+#pragma unroll
+    for (int p = 1; p < TC_PARTS; ++p) {
+      const int o1 = sTop[(p * TC_ROWS + r) * 3], oi = sTop[(p * TC_ROWS + r) * 3 + 1], o2 = sTop[(p * TC_ROWS + r) * 3 + 2];
+      if (b1 < o1 || (b1 == o1 && (unsigned)bidx <= (unsigned)oi)) { b2 = min(b2, o1); }
+      else { b2 = min(o2, b1); b1 = o1; bidx = oi; }
+    }
+    if (row < a.out_stride) {
+      const bool row_ok = row < nA;
+      const size_t o = (size_t)pair * a.out_stride + row;
+      if (a.best_idx) a.best_idx[o] = row_ok ? bidx : -1;
+      if (a.best_dist) a.best_dist[o] = row_ok ? b1 : a.init;
+      if (a.second_dist) a.second_dist[o] = row_ok ? b2 : a.init;
+    }
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+constexpr size_t TC_SMEM = (size_t)3 * TC_IMG_BYTES + 10 * 8 + (size_t)TC_PARTS * TC_ROWS * 3 * 4 + TC_ROWS * 4 + 16;
+
+template <bool MATRIX, bool GROUPED>
+static cudaError_t launch_tc(Ctx* c, const MatchTcArgs& a, int row_tiles, int n_pairs, int tag) {
+  auto kern = match_tc_kernel<MATRIX, GROUPED>;
+  static unsigned long long attr_mask = 0;
+  if (!((attr_mask >> c->device) & 1ull)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_mask |= 1ull << c->device;
+  }
+  prof_begin(c, tag);
+  kern<<<dim3(row_tiles, n_pairs), TC_THREADS, TC_SMEM, c->stream>>>(a);
+  prof_end(c);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_match_prep(Ctx* c, const float* desc, size_t set_stride, int n_sets, const int32_t* n_dev, int n_host, int rows_padded,
+                              float* img, size_t img_set_stride, float* nrm) {
+  dim3 grid((rows_padded * 16 + 255) / 256, n_sets);
+  prof_begin(c, P_MATCH_PREP);
+  match_prep_kernel<<<grid, 256, 0, c->stream>>>(desc, set_stride, n_dev, n_host, rows_padded, img, img_set_stride, nrm);
+  prof_end(c);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_match_tc(Ctx* c, const MatchTcArgs& a, int row_tiles, int n_pairs, bool grouped) {
+  return grouped ? launch_tc<false, true>(c, a, row_tiles, n_pairs, P_MATCH_TILE) : launch_tc<false, false>(c, a, row_tiles, n_pairs, P_MATCH_TILE);
+}
+cudaError_t launch_matrix_tc(Ctx* c, const MatchTcArgs& a, int row_tiles) { return launch_tc<true, false>(c, a, row_tiles, 1, P_DIST_MATRIX); }
+
+}  // namespace xfb

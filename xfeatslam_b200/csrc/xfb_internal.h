@@ -122,6 +122,17 @@ struct Ctx {
   int m_cap = 0;
   int32_t* m_pairs_out[5] = {};   // [n_pairs][topk] staging for xfb_match_frame_pairs
   int m_pairs_cap = 0;
+  // tensor-core matcher operand images (match_tc.cu): [set][block][hi 32 KB | lo 32 KB], norms [set][rows_padded]
+  float* tc_img[2] = {};          // generic A / B sets (xfb_match, xfb_distance_matrix)
+  float* tc_nrm[2] = {};
+  int tc_cap = 0;                 // rows (multiple of 128) the generic images hold
+  float* tc_fimg = nullptr;       // per-frame images of the last extract (xfb_match_frame*)
+  float* tc_fnrm = nullptr;
+  int tc_frows = 0;               // padded rows per frame of tc_fimg
+  bool tc_fvalid = false;         // images match the last extract result
+  int32_t* tc_pairs = nullptr;    // device copy of (pairs, swapped pairs)
+  int tc_pairs_cap = 0;
+  float* tc_dbg = nullptr;
 };
 
 // error helpers -------------------------------------------------------------------------------
@@ -135,9 +146,28 @@ void set_global_error(const std::string& s);
     }                                                                                                \
   } while (0)
 
+// Arguments of the tensor-core matcher (match_tc.cu).  A "set" is one descriptor array (one frame).
+struct MatchTcArgs {
+  const float* imgA; const float* imgB;   // operand images of set 0; per-pair offsets below
+  const float* nrmA; const float* nrmB;   // |.|^2, [set][rows_padded]
+  const float* rawA; const float* rawB;   // original fp32 rows [set][set_stride] for the exact fix-up
+  int32_t pairs[128];                     // up to 64 (set of A, set of B) pairs per launch, by value
+  const int32_t* nA_dev; const int32_t* nB_dev;   // per-set valid counts (device) or nullptr
+  const int32_t* gA; const int32_t* gB;   // group ids (single-pair mode only) or nullptr
+  int nA_host, nB_host;                   // valid counts / capacities
+  int rows_padded_A, rows_padded_B;       // multiples of 128
+  size_t img_stride_A, img_stride_B;      // floats per set
+  size_t raw_stride_A, raw_stride_B;      // floats per set
+  int init;
+  int out_stride;                         // entries per pair in the outputs
+  int32_t* best_idx; int32_t* best_dist; int32_t* second_dist;   // any may be null
+  int32_t* matrix;                        // MATRIX mode: [nA][nB] exact distances
+  float* dbg_maxerr;                      // MATRIX mode + debug: max |t - 512*float(S)|
+};
+
 // profiling tags: 0..L_NUM-1 = layers, then the stages below
 enum ProfTag { P_PREP_STATS = L_NUM, P_PREP_NORM, P_PYRAMID, P_HEATMAP_OUT, P_KEYPOINT_OUT, P_NMS, P_TOPK, P_DESCRIBE, P_MATCH_TILE,
-               P_MATCH_MERGE, P_DIST_MATRIX, P_NUM };
+               P_MATCH_MERGE, P_DIST_MATRIX, P_MATCH_PREP, P_NUM };
 static_assert(P_NUM <= XFB_PROF_TAGS, "profile tag table");
 void prof_begin(Ctx* c, int tag);
 void prof_end(Ctx* c);
@@ -153,6 +183,10 @@ cudaError_t launch_distance_matrix(Ctx* c, const float* dA, int n1, const float*
 cudaError_t launch_match(Ctx* c, const float* dA, int n1, const float* dB, int n2, const int32_t* ga, const int32_t* gb, int init,
                          int32_t* bi, int32_t* bd, int32_t* sd, int32_t* ri, int32_t* rd, const int32_t* n1p = nullptr,
                          const int32_t* n2p = nullptr);
+cudaError_t launch_match_prep(Ctx* c, const float* desc, size_t set_stride, int n_sets, const int32_t* n_dev, int n_host, int rows_padded,
+                              float* img, size_t img_set_stride, float* nrm);
+cudaError_t launch_match_tc(Ctx* c, const MatchTcArgs& a, int row_tiles, int n_pairs, bool grouped);
+cudaError_t launch_matrix_tc(Ctx* c, const MatchTcArgs& a, int row_tiles);
 size_t conv_part_elems(int H, int W);  // partial-sum scratch (doubles) needed per frame
 
 }  // namespace xfb
