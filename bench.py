@@ -307,10 +307,11 @@ def run_b200(args):
             pipe = "n/a"
         achieved = alg / (avg_ms * 1e-3) / 1e12
         shares = {k: round(v[0] / tot, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:8]}
+        all_ms = {k: round(v[0] / K, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
         roofline = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"] + " cuBLAS bf16 burst",
                     "pipe_used": pipe, "avg_launch_ms": avg_ms, "launches_timed": kcnt, "algorithmic_flops_per_launch": alg,
-                    "share_of_step": round(kms / tot, 4), "top_shares": shares,
+                    "share_of_step": round(kms / tot, 4), "top_shares": shares, "kernel_ms_per_step": all_ms,
                     "whole_path_conv_tflops": conv_flops_per_frame(H, W) * value / max(world, 1) / 1e12}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:

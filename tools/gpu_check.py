@@ -109,8 +109,25 @@ def match_check():
     print("match grouped equal:", [bool(np.array_equal(g, w)) for g, w in zip(got, want)])
 
 
+def ab_check(H=480, W=640):
+    """tcgen05 conv path vs the FP32 SIMT conv path on the same frame, layer by layer."""
+    frame = synthetic_frame(2, H, W)
+    ctx = XFeatB200(max_h=H, max_w=W, max_batch=1, max_topk=1024)
+    ctx.force_simt(True)
+    o_s = ctx.extract(frame, 1024)
+    simt = {L: ctx.debug_read(L) for L in LAYERS}
+    simt["feats"] = ctx.debug_read("feats")
+    ctx.force_simt(False)
+    o_t = ctx.extract(frame, 1024)
+    for L in LAYERS + ["feats"]:
+        report("tc-vs-simt " + L, ctx.debug_read(L), simt[L])
+    print("keypoints equal:", np.array_equal(o_s["kpts"], o_t["kpts"]), " desc maxabs %.3e" % np.abs(o_s["desc"] - o_t["desc"]).max())
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "match":
         match_check()
+    elif len(sys.argv) > 1 and sys.argv[1] == "ab":
+        ab_check(*[int(x) for x in sys.argv[2:4]])
     else:
         main()

@@ -19,7 +19,7 @@ SYMBOLS = [
     "xfb_create", "xfb_destroy", "xfb_last_error", "xfb_set_stream", "xfb_extract", "xfb_extract_batch",
     "xfb_extract_batch_device", "xfb_distance_matrix", "xfb_distance_matrix_device", "xfb_match", "xfb_match_device",
     "xfb_match_frames", "xfb_match_frame_pairs", "xfb_match_frame_pairs_device", "xfb_profile_enable", "xfb_profile_read", "xfb_profile_tag_name",
-    "xfb_debug_match_error", "xfb_debug_read", "xfb_debug_read_stats", "xfb_debug_post", "xfb_debug_candidates", "xfb_launch_count",
+    "xfb_debug_match_error", "xfb_debug_force_simt", "xfb_debug_read", "xfb_debug_read_stats", "xfb_debug_post", "xfb_debug_candidates", "xfb_launch_count",
 ]
 
 _lib = None
@@ -56,6 +56,7 @@ def load_library(path=LIB_PATH):
     lib.xfb_profile_tag_name.argtypes = [c_int]
     lib.xfb_profile_tag_name.restype = c_char_p
     lib.xfb_debug_match_error.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]
+    lib.xfb_debug_force_simt.argtypes = [c_void_p, c_int]
     lib.xfb_debug_read.argtypes = [c_void_p, c_char_p, c_int, c_void_p, c_size_t, c_void_p]
     lib.xfb_debug_read.restype = c_long
     lib.xfb_debug_read_stats.argtypes = [c_void_p, c_char_p, c_int, c_void_p, c_size_t]
@@ -217,6 +218,9 @@ class XFeatB200:
         e = np.zeros(1, np.float32)
         self._check(self.lib.xfb_debug_match_error(self.h, _ptr(A), A.shape[0], _ptr(B), B.shape[0], _ptr(e)), "xfb_debug_match_error")
         return float(e[0])
+
+    def force_simt(self, enable):
+        self._check(self.lib.xfb_debug_force_simt(self.h, int(bool(enable))), "xfb_debug_force_simt")
 
     def candidates(self, frame=0):
         return self._check(self.lib.xfb_debug_candidates(self.h, frame), "xfb_debug_candidates")

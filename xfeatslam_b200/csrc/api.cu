@@ -102,6 +102,12 @@ static int load_weights(Ctx* c, const uint8_t* blob, size_t n) {
         for (size_t k = 0; k < kk; ++k) packed[(k * sp.cin + ci) * sp.cout + co] = src[((size_t)co * sp.cin + ci) * kk + k];
     XFB_ALLOC(c, c->w[L], elems * 4);
     XFB_CUDA_OK(c, cudaMemcpy(c->w[L], packed.data(), elems * 4, cudaMemcpyHostToDevice));
+    if (conv_tc_handles(L)) {
+      std::vector<float> img;
+      conv_tc_pack_weights(L, src, sp.cout, sp.cin, sp.ks, img);
+      XFB_ALLOC(c, c->wimg[L], img.size() * 4);
+      XFB_CUDA_OK(c, cudaMemcpy(c->wimg[L], img.data(), img.size() * 4, cudaMemcpyHostToDevice));
+    }
     if (!is_basic) {
       const std::string bname = std::string(sp.ref_name) + ".bias";
       const float* bsrc = blob_find(blob, n, bname, sp.cout);
@@ -136,6 +142,7 @@ static int alloc_buffers(Ctx* c) {
   XFB_ALLOC(c, c->in_mean, B * 4);
   XFB_ALLOC(c, c->in_rstd, B * 4);
   size_t pe = conv_part_elems((int)H, (int)W);
+  if (conv_tc_part_elems((int)H, (int)W) > pe) pe = conv_tc_part_elems((int)H, (int)W);
   const size_t prep_pe = ((HW + 2047) / 2048) * 2;
   if (prep_pe > pe) pe = prep_pe;
   c->part_elems = pe;
@@ -275,13 +282,14 @@ static int run_dense(Ctx* c, const uint8_t* d_gray, size_t frame_stride, int str
   XFB_CUDA_OK(c, launch_prep(c, d_gray, frame_stride, stride));
   static const int order1[] = {L_B1_0, L_B1_1, L_B1_2, L_B1_3, L_B2_0, L_B2_1, L_B3_0, L_B3_1, L_B3_2,
                                L_B4_0, L_B4_1, L_B4_2, L_B5_0, L_B5_1, L_B5_2, L_B5_3};
-  for (int L : order1) XFB_CUDA_OK(c, launch_conv_layer(c, L));
+  auto conv = [&](int L) { return (conv_tc_handles(L) && !c->force_simt) ? launch_conv_tc_layer(c, L) : launch_conv_layer(c, L); };
+  for (int L : order1) XFB_CUDA_OK(c, conv(L));
   XFB_CUDA_OK(c, launch_pyramid(c));
   static const int order2[] = {L_F_0, L_F_1, L_F_2, L_HM_0, L_HM_1};
-  for (int L : order2) XFB_CUDA_OK(c, launch_conv_layer(c, L));
+  for (int L : order2) XFB_CUDA_OK(c, conv(L));
   XFB_CUDA_OK(c, launch_heatmap_out(c));
   static const int order3[] = {L_KP_0, L_KP_1, L_KP_2};
-  for (int L : order3) XFB_CUDA_OK(c, launch_conv_layer(c, L));
+  for (int L : order3) XFB_CUDA_OK(c, conv(L));
   XFB_CUDA_OK(c, launch_keypoint_out(c));
   return XFB_OK;
 }
@@ -358,7 +366,7 @@ void xfb_destroy(xfb_ctx* c) {
   cudaSetDevice(c->device);
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
   auto fr = [](void* p) { if (p) cudaFree(p); };
-  for (int L = 0; L < L_NUM; ++L) { fr(c->w[L]); fr(c->bias[L]); fr(c->act[L]); }
+  for (int L = 0; L < L_NUM; ++L) { fr(c->w[L]); fr(c->bias[L]); fr(c->act[L]); fr(c->wimg[L]); }
   for (int L = 0; L < L_NUM_BN; ++L) { fr(c->bn[L].mean); fr(c->bn[L].rstd); }
   fr(c->d_gray); fr(c->xraw); fr(c->xn); fr(c->avg4); fr(c->pyr); fr(c->k1h); fr(c->in_mean); fr(c->in_rstd); fr(c->part);
   fr(c->ticket); fr(c->cand); fr(c->cand_count); fr(c->cand_count_last); fr(c->o_nvalid); fr(c->o_xy); fr(c->o_score); fr(c->o_desc);
@@ -646,5 +654,11 @@ int xfb_debug_candidates(xfb_ctx* c, int frame) {
 }
 
 long xfb_launch_count(const xfb_ctx* c) { return c ? c->launches : 0; }
+
+int xfb_debug_force_simt(xfb_ctx* c, int enable) {
+  if (!c) return XFB_ERR_ARG;
+  c->force_simt = enable != 0;
+  return XFB_OK;
+}
 
 }  // extern "C"

@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include "tc_ptx.cuh"
 #include "xfb_internal.h"
 
 namespace xfb {
@@ -36,6 +37,8 @@ constexpr int TC_PARTS = 4;                  // 32-column slices per block = epi
 constexpr int TC_EPI_WARPS = 4 * TC_PARTS;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // loader warp + MMA warp + epilogue warps
 constexpr uint32_t TC_LBO = 2048, TC_SBO = 128;
+constexpr uint32_t TC_IDESC = umma_idesc_tf32(128, 128);
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) { return umma_desc_kmajor(smem_addr, TC_LBO, TC_SBO); }
 
 // ---- operand images ---------------------------------------------------------------------------------------
 // element (r, k) of a block -> float index inside the hi (or lo) image
@@ -67,70 +70,6 @@ __global__ void __launch_bounds__(256) match_prep_kernel(const float* desc, size
   for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off, 16);
   if (kq == 0) nrm[(size_t)set * rows_padded + row] = (float)s;
 }
-
-// ---- PTX helpers --------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-  // K-major, SWIZZLE_NONE: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version(1) <<46
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(TC_LBO >> 4) << 16) | ((uint64_t)(TC_SBO >> 4) << 32) | (1ull << 46);
-}
-// kind::tf32, D = F32, A/B = TF32 K-major, M = 128, N = 128
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t* u = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
-      "%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]), "=r"(u[10]),
-        "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]),
-        "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]),
-        "=r"(u[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 
 __device__ __noinline__ int exact_distance(const float* sA_hi, const float* sA_lo, int r, const float* brow) {
   double s = 0.0;
@@ -198,8 +137,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(const MatchTcAr
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    tmem_alloc(s_tmem, 256u);
   }
   tc_fence_before();
   __syncthreads();
@@ -233,9 +171,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(const MatchTcAr
 #pragma unroll
         for (int k8 = 0; k8 < 8; ++k8) {
           const uint32_t ko = (uint32_t)k8 * 2u * TC_LBO;   // 8 tf32 = 2 k-chunks of 16 B
-          umma_tf32(d, umma_desc(a_hi + ko), umma_desc(b_hi + ko), k8 > 0 ? 1u : 0u);
-          umma_tf32(d, umma_desc(a_hi + ko), umma_desc(b_lo + ko), 1u);
-          umma_tf32(d, umma_desc(a_lo + ko), umma_desc(b_hi + ko), 1u);
+          umma_tf32(d, umma_desc(a_hi + ko), umma_desc(b_hi + ko), TC_IDESC, k8 > 0 ? 1u : 0u);
+          umma_tf32(d, umma_desc(a_hi + ko), umma_desc(b_lo + ko), TC_IDESC, 1u);
+          umma_tf32(d, umma_desc(a_lo + ko), umma_desc(b_hi + ko), TC_IDESC, 1u);
         }
         umma_commit(bar_empty + s);   // smem stage may be refilled once these MMAs have read it
         umma_commit(bar_accf + s);    // accumulator complete
@@ -370,7 +308,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(const MatchTcAr
   }
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    tmem_dealloc(tmem_base, 256u);
   }
 }
 

@@ -73,6 +73,8 @@ struct Ctx {
   // weights (device): packed [KS*KS][CIN][COUT] per layer, biases where present
   float* w[L_NUM] = {};
   float* bias[L_NUM] = {};
+  float* wimg[L_NUM] = {};        // tensor-core layers: per-tap hi/lo UMMA operand images (conv_tc.cu)
+  bool force_simt = false;        // debug: run every conv on the FP32 SIMT kernels (A/B parity tests)
 
   // geometry of the last extract call
   int B = 0, H = 0, W = 0, in_h = 0, in_w = 0;
@@ -187,7 +189,11 @@ cudaError_t launch_match_prep(Ctx* c, const float* desc, size_t set_stride, int 
                               float* img, size_t img_set_stride, float* nrm);
 cudaError_t launch_match_tc(Ctx* c, const MatchTcArgs& a, int row_tiles, int n_pairs, bool grouped);
 cudaError_t launch_matrix_tc(Ctx* c, const MatchTcArgs& a, int row_tiles);
-size_t conv_part_elems(int H, int W);  // partial-sum scratch (doubles) needed per frame
+size_t conv_part_elems(int H, int W);
+size_t conv_tc_part_elems(int H, int W);
+bool conv_tc_handles(int layer);
+void conv_tc_pack_weights(int layer, const float* oihw, int cout, int cin, int ks, std::vector<float>& img);
+cudaError_t launch_conv_tc_layer(Ctx* c, int layer);  // partial-sum scratch (doubles) needed per frame
 
 }  // namespace xfb
 
