@@ -19,7 +19,7 @@ BASIC = ["block1.0", "block1.1", "block1.2", "block1.3", "block2.0", "block2.1",
          "heatmap_head.1", "keypoint_head.0", "keypoint_head.1", "keypoint_head.2"]
 LAYER_TOL = 6e-4      # abs, raw conv outputs (values up to ~40); the 3xTF32 tensor-core split is good to ~1e-5 relative
 DESC_TOL = 1e-4       # BASELINE.json north_star
-SCORE_TOL = 1e-5
+SCORE_TOL = 5e-5
 
 
 def nhwc(t):

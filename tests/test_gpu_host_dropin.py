@@ -69,7 +69,7 @@ def test_xfextractor_operator_matches_reference_packing(driver, tmp_path, name):
     pairs = [(got[(int(x), int(y))], j) for j, (x, y) in enumerate(rk[:, :2]) if (int(x), int(y)) in got]
     assert len(pairs) >= 0.97 * n_ref                                  # set differs only at the k-th score boundary
     gi = np.array([p[0] for p in pairs]); ri = np.array([p[1] for p in pairs])
-    np.testing.assert_allclose(ck[gi, 2], rk[ri, 2], atol=1e-5, rtol=0)
+    np.testing.assert_allclose(ck[gi, 2], rk[ri, 2], atol=5e-5, rtol=0)
     np.testing.assert_allclose(cd[gi], rd[ri], atol=1e-4, rtol=0)
 
 

@@ -39,7 +39,7 @@ void prof_end(Ctx* c) {
   c->prof_ev.push_back(e);
 }
 static const char* kStageNames[] = {"prep_stats", "prep_norm", "pyramid_sum", "heatmap_out", "keypoint_out_softmax_fold", "nms_score",
-                                    "topk_select_sort", "describe", "match_tile", "match_merge", "distance_matrix", "match_prep"};
+                                    "topk_select_sort", "describe", "match_tile", "match_merge", "distance_matrix", "match_prep", "match_bound"};
 
 // ---- weight blob (tools/convert_weights.py) --------------------------------------------------------
 #pragma pack(push, 1)
@@ -191,8 +191,15 @@ static int tc_ensure_generic(Ctx* c, int n1, int n2) {
   const int need = pad128(n1 > n2 ? n1 : n2);
   if (need > c->tc_cap) {
     for (int i = 0; i < 2; ++i) { if (c->tc_img[i]) cudaFree(c->tc_img[i]); if (c->tc_nrm[i]) cudaFree(c->tc_nrm[i]); c->tc_img[i] = nullptr; c->tc_nrm[i] = nullptr; }
-    for (int i = 0; i < 2; ++i) { XFB_ALLOC(c, c->tc_img[i], (size_t)need * 128 * 4); XFB_ALLOC(c, c->tc_nrm[i], (size_t)need * 4); }
+    for (int i = 0; i < 2; ++i) { XFB_ALLOC(c, c->tc_img[i], (size_t)need * 160 * 4); XFB_ALLOC(c, c->tc_nrm[i], (size_t)need * 4); }
     c->tc_cap = need;
+  }
+  for (int i = 0; i < 2; ++i) if (!c->tc_nmax[i]) XFB_ALLOC(c, c->tc_nmax[i], 16);
+  if (c->tc_bound_rows < need) {
+    if (c->tc_bound) cudaFree(c->tc_bound);
+    c->tc_bound = nullptr;
+    XFB_ALLOC(c, c->tc_bound, (size_t)64 * need * 4);
+    c->tc_bound_rows = need;
   }
   if (!c->tc_dbg) XFB_ALLOC(c, c->tc_dbg, 16);
   return XFB_OK;
@@ -204,21 +211,27 @@ static int tc_match_generic(Ctx* c, const float* dA, int n1, const float* dB, in
   int r = tc_ensure_generic(c, n1, n2);
   if (r != XFB_OK) return r;
   const int p1 = pad128(n1), p2 = pad128(n2);
-  XFB_CUDA_OK(c, launch_match_prep(c, dA, 0, 1, nullptr, n1, p1, c->tc_img[0], 0, c->tc_nrm[0]));
-  XFB_CUDA_OK(c, launch_match_prep(c, dB, 0, 1, nullptr, n2, p2, c->tc_img[1], 0, c->tc_nrm[1]));
+  XFB_CUDA_OK(c, launch_match_prep(c, dA, 0, 1, nullptr, n1, p1, c->tc_img[0], 0, c->tc_nrm[0], c->tc_nmax[0]));
+  XFB_CUDA_OK(c, launch_match_prep(c, dB, 0, 1, nullptr, n2, p2, c->tc_img[1], 0, c->tc_nrm[1], c->tc_nmax[1]));
   MatchTcArgs a = {};
   a.init = init;
   const bool grouped = ga && gb;
+  const bool use_bound = !grouped && n1 > 0 && n2 >= 256;   // the bound pass pays off for long scans only
   if (n1 > 0 && (bi || bd || sd)) {
     a.imgA = c->tc_img[0]; a.imgB = c->tc_img[1]; a.nrmA = c->tc_nrm[0]; a.nrmB = c->tc_nrm[1]; a.rawA = dA; a.rawB = dB;
     a.gA = ga; a.gB = gb; a.nA_host = n1; a.nB_host = n2; a.rows_padded_A = p1; a.rows_padded_B = p2; a.out_stride = n1;
     a.best_idx = bi; a.best_dist = bd; a.second_dist = sd;
+    a.nrm_max_B = c->tc_nmax[1];
+    if (use_bound) { a.bound = c->tc_bound; XFB_CUDA_OK(c, launch_match_bound(c, a, p1 / 128, 1)); }
     XFB_CUDA_OK(c, launch_match_tc(c, a, p1 / 128, 1, grouped));
   }
   if (n2 > 0 && (ri || rd)) {   // column-wise best == row-wise best of the transposed problem (distances are symmetric, bit for bit)
     a.imgA = c->tc_img[1]; a.imgB = c->tc_img[0]; a.nrmA = c->tc_nrm[1]; a.nrmB = c->tc_nrm[0]; a.rawA = dB; a.rawB = dA;
     a.gA = gb; a.gB = ga; a.nA_host = n2; a.nB_host = n1; a.rows_padded_A = p2; a.rows_padded_B = p1; a.out_stride = n2;
     a.best_idx = ri; a.best_dist = rd; a.second_dist = nullptr;
+    a.nrm_max_B = c->tc_nmax[0];
+    a.bound = nullptr;
+    if (!grouped && n1 >= 256) { a.bound = c->tc_bound; XFB_CUDA_OK(c, launch_match_bound(c, a, p2 / 128, 1)); }
     XFB_CUDA_OK(c, launch_match_tc(c, a, p2 / 128, 1, grouped));
   }
   return XFB_OK;
@@ -228,8 +241,8 @@ static int tc_matrix_generic(Ctx* c, const float* dA, int n1, const float* dB, i
   int r = tc_ensure_generic(c, n1, n2);
   if (r != XFB_OK) return r;
   const int p1 = pad128(n1), p2 = pad128(n2);
-  XFB_CUDA_OK(c, launch_match_prep(c, dA, 0, 1, nullptr, n1, p1, c->tc_img[0], 0, c->tc_nrm[0]));
-  XFB_CUDA_OK(c, launch_match_prep(c, dB, 0, 1, nullptr, n2, p2, c->tc_img[1], 0, c->tc_nrm[1]));
+  XFB_CUDA_OK(c, launch_match_prep(c, dA, 0, 1, nullptr, n1, p1, c->tc_img[0], 0, c->tc_nrm[0], c->tc_nmax[0]));
+  XFB_CUDA_OK(c, launch_match_prep(c, dB, 0, 1, nullptr, n2, p2, c->tc_img[1], 0, c->tc_nrm[1], c->tc_nmax[1]));
   MatchTcArgs a = {};
   a.imgA = c->tc_img[0]; a.imgB = c->tc_img[1]; a.nrmA = c->tc_nrm[0]; a.nrmB = c->tc_nrm[1]; a.rawA = dA; a.rawB = dB;
   a.nA_host = n1; a.nB_host = n2; a.rows_padded_A = p1; a.rows_padded_B = p2; a.matrix = d_out; a.dbg_maxerr = dbg;
@@ -240,21 +253,30 @@ static int tc_matrix_generic(Ctx* c, const float* dA, int n1, const float* dB, i
 // frames of the last extract: pairs (host) -> outputs [n_pairs][K] (device pointers, nullable)
 static int tc_match_frames(Ctx* c, const int32_t* pairs, int n_pairs, int init, int32_t* o[5]) {
   const int K = c->last_topk, P = pad128(K);
-  const size_t img_stride = (size_t)P * 128;
+  const size_t img_stride = (size_t)P * 160;
   if (!c->tc_fimg || c->tc_frows < P) {
     if (c->tc_fimg) cudaFree(c->tc_fimg);
     if (c->tc_fnrm) cudaFree(c->tc_fnrm);
-    c->tc_fimg = nullptr; c->tc_fnrm = nullptr;
+    if (c->tc_fnmax) cudaFree(c->tc_fnmax);
+    c->tc_fimg = nullptr; c->tc_fnrm = nullptr; c->tc_fnmax = nullptr;
     const int PM = pad128(c->max_topk);
-    XFB_ALLOC(c, c->tc_fimg, (size_t)c->max_batch * PM * 128 * 4);
+    XFB_ALLOC(c, c->tc_fimg, (size_t)c->max_batch * PM * 160 * 4);
     XFB_ALLOC(c, c->tc_fnrm, (size_t)c->max_batch * PM * 4);
+    XFB_ALLOC(c, c->tc_fnmax, (size_t)c->max_batch * 4);
     c->tc_frows = PM;
     c->tc_fvalid = false;
   }
+  if (c->tc_bound_rows < P) {
+    if (c->tc_bound) cudaFree(c->tc_bound);
+    c->tc_bound = nullptr;
+    XFB_ALLOC(c, c->tc_bound, (size_t)64 * pad128(c->max_topk) * 4);
+    c->tc_bound_rows = pad128(c->max_topk);
+  }
   if (!c->tc_fvalid) {
-    XFB_CUDA_OK(c, launch_match_prep(c, c->last_desc, (size_t)K * 64, c->B, c->last_nvalid, K, P, c->tc_fimg, img_stride, c->tc_fnrm));
+    XFB_CUDA_OK(c, launch_match_prep(c, c->last_desc, (size_t)K * 64, c->B, c->last_nvalid, K, P, c->tc_fimg, img_stride, c->tc_fnrm, c->tc_fnmax));
     c->tc_fvalid = true;
   }
+  const bool use_bound = K >= 256;
   for (int p0 = 0; p0 < n_pairs; p0 += 64) {
     const int np = (n_pairs - p0) < 64 ? (n_pairs - p0) : 64;
     MatchTcArgs a = {};
@@ -262,15 +284,18 @@ static int tc_match_frames(Ctx* c, const int32_t* pairs, int n_pairs, int init, 
     a.nA_dev = a.nB_dev = c->last_nvalid; a.nA_host = a.nB_host = K; a.rows_padded_A = a.rows_padded_B = P;
     a.img_stride_A = a.img_stride_B = img_stride; a.raw_stride_A = a.raw_stride_B = (size_t)K * 64;
     a.init = init; a.out_stride = K;
+    a.nrm_max_B = c->tc_fnmax; a.bound = use_bound ? c->tc_bound : nullptr;
     if (o[0] || o[1] || o[2]) {
       for (int p = 0; p < np; ++p) { a.pairs[2 * p] = pairs[2 * (p0 + p)]; a.pairs[2 * p + 1] = pairs[2 * (p0 + p) + 1]; }
       a.best_idx = o[0] ? o[0] + (size_t)p0 * K : nullptr; a.best_dist = o[1] ? o[1] + (size_t)p0 * K : nullptr;
       a.second_dist = o[2] ? o[2] + (size_t)p0 * K : nullptr;
+      if (use_bound) XFB_CUDA_OK(c, launch_match_bound(c, a, P / 128, np));
       XFB_CUDA_OK(c, launch_match_tc(c, a, P / 128, np, false));
     }
     if (o[3] || o[4]) {
       for (int p = 0; p < np; ++p) { a.pairs[2 * p] = pairs[2 * (p0 + p) + 1]; a.pairs[2 * p + 1] = pairs[2 * (p0 + p)]; }
       a.best_idx = o[3] ? o[3] + (size_t)p0 * K : nullptr; a.best_dist = o[4] ? o[4] + (size_t)p0 * K : nullptr; a.second_dist = nullptr;
+      if (use_bound) XFB_CUDA_OK(c, launch_match_bound(c, a, P / 128, np));
       XFB_CUDA_OK(c, launch_match_tc(c, a, P / 128, np, false));
     }
   }
@@ -373,7 +398,7 @@ void xfb_destroy(xfb_ctx* c) {
   fr(c->m_a); fr(c->m_b); fr(c->m_ga); fr(c->m_gb); fr(c->m_rowpart); fr(c->m_colpart); fr(c->m_matrix);
   for (int i = 0; i < 5; ++i) { fr(c->m_out[i]); fr(c->m_pairs_out[i]); }
   for (int i = 0; i < 2; ++i) { fr(c->tc_img[i]); fr(c->tc_nrm[i]); }
-  fr(c->tc_fimg); fr(c->tc_fnrm); fr(c->tc_pairs); fr(c->tc_dbg);
+  fr(c->tc_fimg); fr(c->tc_fnrm); fr(c->tc_pairs); fr(c->tc_dbg); fr(c->tc_fnmax); fr(c->tc_bound); fr(c->tc_nmax[0]); fr(c->tc_nmax[1]);
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);

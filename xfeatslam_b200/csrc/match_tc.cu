@@ -21,6 +21,7 @@
 // fp32 accumulator columns.  Operand images are written by match_prep_kernel directly in the canonical
 // K-major no-swizzle UMMA layout ([k-chunk 16 B][8-row group][8 rows][16 B]; LBO = 2048 B, SBO = 128 B), so
 // the loader needs no tensor map: one contiguous 64 KB bulk copy per 128-row block.
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -32,6 +33,9 @@ namespace xfb {
 constexpr int TC_ROWS = 128;                 // rows (or columns) per operand block
 constexpr int TC_BLOCK_FLOATS = 128 * 64;    // one hi or lo image of a block
 constexpr int TC_IMG_BYTES = 2 * TC_BLOCK_FLOATS * 4;   // hi + lo = 64 KB
+constexpr int TC_BF16_BYTES = TC_ROWS * 64 * 2;         // bf16 image of a block = 16 KB (bound pass)
+constexpr int TC_BLK_STRIDE = 2 * TC_BLOCK_FLOATS + TC_BF16_BYTES / 4;   // floats per 128-row block: [hi | lo | bf16]
+constexpr float MATCH_BF16_ERR = 4.2f;       // |t_bf16 - 512 d| <= 1024 * 2^-8 * |a||b| (+ slack), in units of sqrt(|a|^2 |b|^2)
 constexpr float MATCH_EPS = 0.02f;           // bound on |t - 512*float(S)| used by the filter (measured max ~1e-3, see xfb_debug_match_error)
 constexpr int TC_PARTS = 4;                  // 32-column slices per block = epilogue threads per row
 constexpr int TC_EPI_WARPS = 4 * TC_PARTS;
@@ -46,7 +50,7 @@ __host__ __device__ __forceinline__ int img_index(int r, int k) { return ((k >> 
 
 // One thread per (row, 4 consecutive k).  Rows >= n (per set) are zero-filled up to the padded row count.
 __global__ void __launch_bounds__(256) match_prep_kernel(const float* desc, size_t set_stride, const int32_t* n_dev, int n_host,
-                                                         int rows_padded, float* img, size_t img_set_stride, float* nrm) {
+                                                         int rows_padded, float* img, size_t img_set_stride, float* nrm, float* nrm_max) {
   const int set = blockIdx.y;
   const int g = blockIdx.x * blockDim.x + threadIdx.x;   // row * 16 + kq
   const int row = g >> 4, kq = g & 15;
@@ -60,15 +64,26 @@ __global__ void __launch_bounds__(256) match_prep_kernel(const float* desc, size
   hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = v.z - hi.z;
   hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
   const int blk = row >> 7, r = row & 127;
-  float* base = img + (size_t)set * img_set_stride + (size_t)blk * (2 * TC_BLOCK_FLOATS);
+  float* base = img + (size_t)set * img_set_stride + (size_t)blk * TC_BLK_STRIDE;
   const int idx = img_index(r, kq * 4);
   *reinterpret_cast<float4*>(base + idx) = hi;
   *reinterpret_cast<float4*>(base + TC_BLOCK_FLOATS + idx) = lo;
+  // bf16 image for the bound pass: same canonical layout with 8 elements per 16-byte chunk
+  {
+    const unsigned int p0 = (unsigned int)__bfloat16_as_ushort(__float2bfloat16_rn(v.x)) | ((unsigned int)__bfloat16_as_ushort(__float2bfloat16_rn(v.y)) << 16);
+    const unsigned int p1 = (unsigned int)__bfloat16_as_ushort(__float2bfloat16_rn(v.z)) | ((unsigned int)__bfloat16_as_ushort(__float2bfloat16_rn(v.w)) << 16);
+    unsigned int* b16 = reinterpret_cast<unsigned int*>(base + 2 * TC_BLOCK_FLOATS);
+    const int widx = (((kq >> 1) * 16 + (r >> 3)) * 64 + (r & 7) * 8 + (kq & 1) * 4) >> 1;   // 32-bit word index
+    *reinterpret_cast<uint2*>(b16 + widx) = make_uint2(p0, p1);
+  }
   // |a|^2: fp64 accumulate across the 16 threads of a row (lanes kq = 0..15 are contiguous in a half warp)
   double s = (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
 #pragma unroll
   for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off, 16);
-  if (kq == 0) nrm[(size_t)set * rows_padded + row] = (float)s;
+  if (kq == 0) {
+    nrm[(size_t)set * rows_padded + row] = (float)s;
+    if (s > 0.0) atomicMax(reinterpret_cast<unsigned int*>(nrm_max + set), __float_as_uint((float)s));   // non-negative floats order as uints
+  }
 }
 
 __device__ __noinline__ int exact_distance(const float* sA_hi, const float* sA_lo, int r, const float* brow) {
@@ -98,11 +113,11 @@ __device__ __noinline__ float exact_scaled(const float* sA_hi, const float* sA_l
 }
 
 // Candidate handling for one 32-column slice (rare path).  `u[e] = dot - |b|^2/2` was computed by the caller.
-struct RowState { int b1, bidx, b2; float thr, tau; };
+struct RowState { int b1, bidx, b2; float thr, tau, thr_fixed; };
 __device__ __forceinline__ void row_state_refresh(RowState& st, float base) {
-  st.thr = (st.b2 == 0x7fffffff) ? CUDART_INF_F : (float)st.b2 + MATCH_EPS;
+  st.thr = fminf((st.b2 == 0x7fffffff) ? CUDART_INF_F : (float)st.b2 + MATCH_EPS, st.thr_fixed);
   // t < thr  <=>  dot - |b|^2/2 > (base - thr)/1024 ; the extra 1e-3 covers the re-association rounding
-  st.tau = (st.b2 == 0x7fffffff) ? -CUDART_INF_F : (base - st.thr - 1e-3f) * (1.0f / 1024.0f);
+  st.tau = (st.thr == CUDART_INF_F) ? -CUDART_INF_F : (base - st.thr - 1e-3f) * (1.0f / 1024.0f);
 }
 
 template <bool MATRIX, bool GROUPED>
@@ -127,7 +142,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(const MatchTcAr
   const int nB = a.nB_dev ? min(a.nB_host, a.nB_dev[setB]) : a.nB_host;
   const int row0 = blockIdx.x * TC_ROWS;
   const int nblk = (row0 < nA) ? (nB + TC_ROWS - 1) / TC_ROWS : 0;    // column blocks to visit
-  const float* imgA = a.imgA + (size_t)setA * a.img_stride_A + (size_t)blockIdx.x * (2 * TC_BLOCK_FLOATS);
+  const float* imgA = a.imgA + (size_t)setA * a.img_stride_A + (size_t)blockIdx.x * TC_BLK_STRIDE;
   const float* imgB = a.imgB + (size_t)setB * a.img_stride_B;
 
   if (threadIdx.x < TC_ROWS) sBound[threadIdx.x] = a.init;
@@ -153,7 +168,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(const MatchTcAr
         const int s = c & 1;
         if (c >= 2) mbar_wait(bar_empty + s, ((c >> 1) - 1) & 1);
         mbar_expect_tx(bar_full + s, TC_IMG_BYTES);
-        bulk_g2s(sB0 + (size_t)s * 2 * TC_BLOCK_FLOATS, imgB + (size_t)c * (2 * TC_BLOCK_FLOATS), TC_IMG_BYTES, bar_full + s);
+        bulk_g2s(sB0 + (size_t)s * 2 * TC_BLOCK_FLOATS, imgB + (size_t)c * TC_BLK_STRIDE, TC_IMG_BYTES, bar_full + s);
       }
     }
   } else if (warp == 1) {
@@ -190,9 +205,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(const MatchTcAr
     st.b1 = a.init; st.b2 = a.init; st.bidx = -1;
     float base = 0.f;
     int grp = 0;
+    st.thr_fixed = CUDART_INF_F;
     if (row_ok) {
       base = 512.0f * a.nrmA[(size_t)setA * a.rows_padded_A + row];
       if (GROUPED) grp = a.gA[row];
+      // bound pass result: an upper bound of this row's second-best distance; +1 lets integer ties through
+      if (!MATRIX && a.bound) st.thr_fixed = a.bound[(size_t)pair * a.rows_padded_A + row] + 1.0f + MATCH_EPS;
     }
     row_state_refresh(st, base);
     if (!row_ok) st.tau = CUDART_INF_F;              // padded rows never take the candidate path
@@ -312,6 +330,161 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(const MatchTcAr
   }
 }
 
+
+// ---- bound pass ----------------------------------------------------------------------------------------------
+// A cheap first pass over all columns (bf16 tensor-core GEMM, branch-free float top-2 per row) that gives every
+// row an upper bound on its SECOND-BEST distance, so that in the exact pass only the handful of columns that can
+// actually matter take the candidate path (without it a running threshold sees ~2 ln(n) ~ 20 "records" per row).
+// out: bound[pair][row] = (approximate second-smallest t) + (rigorous bf16 error) -- a valid bound because at
+// least two columns have a true distance below it.
+constexpr int TCB_STAGES = 4;
+constexpr uint32_t TCB_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);   // kind::f16, BF16 x BF16 -> F32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TCB_IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void top2_max_push(float& m1, float& m2, float u) {
+  const float lo = fminf(m1, u);
+  m1 = fmaxf(m1, u);
+  m2 = fmaxf(m2, lo);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2) match_bound_kernel(const MatchTcArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* sA = smem_raw;                                        // 16 KB bf16 tile
+  unsigned char* sB0 = smem_raw + TC_BF16_BYTES;                       // TCB_STAGES x 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB0 + TCB_STAGES * TC_BF16_BYTES);
+  uint64_t* bar_a = bars + 0;
+  uint64_t* bar_full = bars + 1;       // [4]
+  uint64_t* bar_empty = bars + 5;      // [4]
+  uint64_t* bar_accf = bars + 9;       // [2]
+  uint64_t* bar_acce = bars + 11;      // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 13);
+  float* sM = reinterpret_cast<float*>(bars + 14);                    // [TC_PARTS][128][2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.y;
+  const int setA = a.pairs[2 * pair], setB = a.pairs[2 * pair + 1];
+  const int nA = a.nA_dev ? min(a.nA_host, a.nA_dev[setA]) : a.nA_host;
+  const int nB = a.nB_dev ? min(a.nB_host, a.nB_dev[setB]) : a.nB_host;
+  const int row0 = blockIdx.x * TC_ROWS;
+  const int nblk = (row0 < nA) ? (nB + TC_ROWS - 1) / TC_ROWS : 0;
+  const float* imgA = a.imgA + (size_t)setA * a.img_stride_A + (size_t)blockIdx.x * TC_BLK_STRIDE + 2 * TC_BLOCK_FLOATS;
+  const float* imgB = a.imgB + (size_t)setB * a.img_stride_B + 2 * TC_BLOCK_FLOATS;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_a, 1);
+    for (int s = 0; s < TCB_STAGES; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_accf + s, 1); mbar_init(bar_acce + s, TC_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(s_tmem, 256u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    if (lane == 0 && nblk > 0) {
+      mbar_expect_tx(bar_a, TC_BF16_BYTES);
+      bulk_g2s(sA, imgA, TC_BF16_BYTES, bar_a);
+      for (int c = 0; c < nblk; ++c) {
+        const int s = c % TCB_STAGES;
+        if (c >= TCB_STAGES) mbar_wait(bar_empty + s, ((c / TCB_STAGES) - 1) & 1);
+        mbar_expect_tx(bar_full + s, TC_BF16_BYTES);
+        bulk_g2s(sB0 + (size_t)s * TC_BF16_BYTES, imgB + (size_t)c * TC_BLK_STRIDE, TC_BF16_BYTES, bar_full + s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nblk > 0) {
+      mbar_wait(bar_a, 0);
+      const uint32_t a_addr = smem_u32(sA);
+      for (int c = 0; c < nblk; ++c) {
+        const int s = c % TCB_STAGES, acc = c & 1;
+        mbar_wait(bar_full + s, (c / TCB_STAGES) & 1);
+        if (c >= 2) mbar_wait(bar_acce + acc, ((c >> 1) - 1) & 1);
+        tc_fence_after();
+        const uint32_t b_addr = smem_u32(sB0 + (size_t)s * TC_BF16_BYTES);
+        const uint32_t d = tmem_base + (uint32_t)acc * 128u;
+#pragma unroll
+        for (int k16 = 0; k16 < 4; ++k16) {
+          const uint32_t ko = (uint32_t)k16 * 2u * TC_LBO;   // 16 bf16 = 2 k-chunks of 16 B
+          umma_bf16(d, umma_desc(a_addr + ko), umma_desc(b_addr + ko), k16 > 0 ? 1u : 0u);
+        }
+        umma_commit(bar_empty + s);
+        umma_commit(bar_accf + acc);
+      }
+    }
+  } else {
+    const int quad = warp & 3, part = (warp - 2) >> 2;
+    const int r = quad * 32 + lane;
+    const float* nrmB = a.nrmB + (size_t)setB * a.rows_padded_B;
+    float m1a = -CUDART_INF_F, m2a = -CUDART_INF_F, m1b = -CUDART_INF_F, m2b = -CUDART_INF_F;
+#pragma unroll 1
+    for (int c = 0; c < nblk; ++c) {
+      const int acc = c & 1;
+      mbar_wait(bar_accf + acc, (c >> 1) & 1);
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * 128u + (uint32_t)part * 32u, v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acce + acc);
+      const int j0 = c * TC_ROWS + part * 32;
+      const bool tail = (j0 + 32 > nB);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 nb = *reinterpret_cast<const float4*>(nrmB + j0 + 4 * g);
+        float u0 = fmaf(-0.5f, nb.x, v[4 * g + 0]), u1 = fmaf(-0.5f, nb.y, v[4 * g + 1]);
+        float u2 = fmaf(-0.5f, nb.z, v[4 * g + 2]), u3 = fmaf(-0.5f, nb.w, v[4 * g + 3]);
+        if (tail) {
+          if (j0 + 4 * g + 0 >= nB) u0 = -CUDART_INF_F;
+          if (j0 + 4 * g + 1 >= nB) u1 = -CUDART_INF_F;
+          if (j0 + 4 * g + 2 >= nB) u2 = -CUDART_INF_F;
+          if (j0 + 4 * g + 3 >= nB) u3 = -CUDART_INF_F;
+        }
+        top2_max_push(m1a, m2a, u0); top2_max_push(m1b, m2b, u1);
+        top2_max_push(m1a, m2a, u2); top2_max_push(m1b, m2b, u3);
+      }
+    }
+    const float M1 = fmaxf(m1a, m1b), M2 = fmaxf(fminf(m1a, m1b), fmaxf(m2a, m2b));
+    sM[(part * TC_ROWS + r) * 2] = M1;
+    sM[(part * TC_ROWS + r) * 2 + 1] = M2;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < TC_ROWS) {
+    const int r = threadIdx.x, row = row0 + r;
+    float M1 = sM[r * 2], M2 = sM[r * 2 + 1];
+#pragma unroll
+    for (int p = 1; p < TC_PARTS; ++p) {
+      const float o1 = sM[(p * TC_ROWS + r) * 2], o2 = sM[(p * TC_ROWS + r) * 2 + 1];
+      M2 = fmaxf(fminf(M1, o1), fmaxf(M2, o2));
+      M1 = fmaxf(M1, o1);
+    }
+    if (row < a.rows_padded_A) {
+      float bnd = CUDART_INF_F;
+      if (row < nA && M2 > -CUDART_INF_F) {
+        const float na = a.nrmA[(size_t)setA * a.rows_padded_A + row];
+        const float t2 = fmaf(-1024.0f, M2, 512.0f * na);                      // approximate second-smallest 512 d
+        bnd = t2 + MATCH_BF16_ERR * sqrtf(na * a.nrm_max_B[setB]) + 0.5f;
+      }
+      a.bound[(size_t)pair * a.rows_padded_A + row] = bnd;
+    }
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256u);
+  }
+}
+
+constexpr size_t TCB_SMEM = (size_t)(1 + TCB_STAGES) * TC_BF16_BYTES + 14 * 8 + (size_t)TC_PARTS * TC_ROWS * 2 * 4 + 64;
+
 constexpr size_t TC_SMEM = (size_t)3 * TC_IMG_BYTES + 10 * 8 + (size_t)TC_PARTS * TC_ROWS * 3 * 4 + TC_ROWS * 4 + 16;
 
 template <bool MATRIX, bool GROUPED>
@@ -331,10 +504,26 @@ static cudaError_t launch_tc(Ctx* c, const MatchTcArgs& a, int row_tiles, int n_
 }
 
 cudaError_t launch_match_prep(Ctx* c, const float* desc, size_t set_stride, int n_sets, const int32_t* n_dev, int n_host, int rows_padded,
-                              float* img, size_t img_set_stride, float* nrm) {
+                              float* img, size_t img_set_stride, float* nrm, float* nrm_max) {
   dim3 grid((rows_padded * 16 + 255) / 256, n_sets);
+  cudaError_t e0 = cudaMemsetAsync(nrm_max, 0, (size_t)n_sets * 4, c->stream);
+  if (e0 != cudaSuccess) return e0;
   prof_begin(c, P_MATCH_PREP);
-  match_prep_kernel<<<grid, 256, 0, c->stream>>>(desc, set_stride, n_dev, n_host, rows_padded, img, img_set_stride, nrm);
+  match_prep_kernel<<<grid, 256, 0, c->stream>>>(desc, set_stride, n_dev, n_host, rows_padded, img, img_set_stride, nrm, nrm_max);
+  prof_end(c);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_match_bound(Ctx* c, const MatchTcArgs& a, int row_tiles, int n_pairs) {
+  static unsigned long long attr_mask = 0;
+  if (!((attr_mask >> c->device) & 1ull)) {
+    cudaError_t e = cudaFuncSetAttribute(match_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCB_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_mask |= 1ull << c->device;
+  }
+  prof_begin(c, P_MATCH_BOUND);
+  match_bound_kernel<<<dim3(row_tiles, n_pairs), TC_THREADS, TCB_SMEM, c->stream>>>(a);
   prof_end(c);
   c->launches++;
   return cudaGetLastError();

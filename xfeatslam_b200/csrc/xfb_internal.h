@@ -135,6 +135,10 @@ struct Ctx {
   int32_t* tc_pairs = nullptr;    // device copy of (pairs, swapped pairs)
   int tc_pairs_cap = 0;
   float* tc_dbg = nullptr;
+  float* tc_nmax[2] = {};         // [1] largest squared norm of the generic A / B sets
+  float* tc_fnmax = nullptr;      // [max_batch] same per frame
+  float* tc_bound = nullptr;      // [64 pairs][rows] bound-pass output
+  int tc_bound_rows = 0;
 };
 
 // error helpers -------------------------------------------------------------------------------
@@ -165,11 +169,13 @@ struct MatchTcArgs {
   int32_t* best_idx; int32_t* best_dist; int32_t* second_dist;   // any may be null
   int32_t* matrix;                        // MATRIX mode: [nA][nB] exact distances
   float* dbg_maxerr;                      // MATRIX mode + debug: max |t - 512*float(S)|
+  float* bound;                           // [pair][rows_padded_A] upper bound of each row's second-best (bound pass), or nullptr
+  const float* nrm_max_B;                 // [set] largest |b|^2 of each B set (bf16 error scale)
 };
 
 // profiling tags: 0..L_NUM-1 = layers, then the stages below
 enum ProfTag { P_PREP_STATS = L_NUM, P_PREP_NORM, P_PYRAMID, P_HEATMAP_OUT, P_KEYPOINT_OUT, P_NMS, P_TOPK, P_DESCRIBE, P_MATCH_TILE,
-               P_MATCH_MERGE, P_DIST_MATRIX, P_MATCH_PREP, P_NUM };
+               P_MATCH_MERGE, P_DIST_MATRIX, P_MATCH_PREP, P_MATCH_BOUND, P_NUM };
 static_assert(P_NUM <= XFB_PROF_TAGS, "profile tag table");
 void prof_begin(Ctx* c, int tag);
 void prof_end(Ctx* c);
@@ -186,7 +192,8 @@ cudaError_t launch_match(Ctx* c, const float* dA, int n1, const float* dB, int n
                          int32_t* bi, int32_t* bd, int32_t* sd, int32_t* ri, int32_t* rd, const int32_t* n1p = nullptr,
                          const int32_t* n2p = nullptr);
 cudaError_t launch_match_prep(Ctx* c, const float* desc, size_t set_stride, int n_sets, const int32_t* n_dev, int n_host, int rows_padded,
-                              float* img, size_t img_set_stride, float* nrm);
+                              float* img, size_t img_set_stride, float* nrm, float* nrm_max);
+cudaError_t launch_match_bound(Ctx* c, const MatchTcArgs& a, int row_tiles, int n_pairs);
 cudaError_t launch_match_tc(Ctx* c, const MatchTcArgs& a, int row_tiles, int n_pairs, bool grouped);
 cudaError_t launch_matrix_tc(Ctx* c, const MatchTcArgs& a, int row_tiles);
 size_t conv_part_elems(int H, int W);
