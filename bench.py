@@ -10,9 +10,9 @@ reverse-best) against the previous frame of the stream -- one extract + one matc
 
   value : whole-job frames/s with the input frames already resident in HBM (xfb_extract_batch_device +
           xfb_match_frame_pairs_device), CUDA-event timed on the launching stream, max over ranks.
-  e2e   : the same metric through the host-buffer C-ABI calls a reference-side binding makes
-          (xfb_extract_batch + xfb_match_frame_pairs): pinned host frames in, host results out,
-          H2D and D2H copies inside the timed region.
+  e2e   : the same metric through the host-buffer C-ABI (xfb_submit / xfb_wait, two batches in flight):
+          pinned host frames in, every result (keypoints, scores, descriptors, five match arrays) back in
+          host memory, H2D and D2H copies inside the timed region (host clock around device sync).
   roofline / cpu_baseline : see DESIGN.md "Measurement".
 
 --impl reference times the reference's own CPU implementation of the path (oracle/_ref/ref_xfeat =
@@ -224,11 +224,10 @@ def run_b200(args):
     d_ds = torch.zeros(Bsz, TOPK, 64, dtype=torch.float32, device=dev)
     d_m = [torch.zeros(Bsz, TOPK, dtype=torch.int32, device=dev) for _ in range(5)]
     pairs = np.array([[i, (i - 1) % Bsz] for i in range(Bsz)], np.int32)
-    h_nv = torch.zeros(Bsz, dtype=torch.int32).pin_memory()
-    h_xy = torch.zeros(Bsz, TOPK, 2, dtype=torch.float32).pin_memory()
-    h_sc = torch.zeros(Bsz, TOPK, dtype=torch.float32).pin_memory()
-    h_ds = torch.zeros(Bsz, TOPK, 64, dtype=torch.float32).pin_memory()
-    h_m = [torch.zeros(Bsz, TOPK, dtype=torch.int32).pin_memory() for _ in range(5)]   # best_idx, best_dist, second_dist, rev_idx, rev_dist
+    # two pinned host output sets: xfb_submit keeps two batches in flight (copies overlap compute)
+    h_out = [{"nv": torch.zeros(Bsz, dtype=torch.int32).pin_memory(), "xy": torch.zeros(Bsz, TOPK, 2, dtype=torch.float32).pin_memory(),
+              "sc": torch.zeros(Bsz, TOPK, dtype=torch.float32).pin_memory(), "ds": torch.zeros(Bsz, TOPK, 64, dtype=torch.float32).pin_memory(),
+              "m": [torch.zeros(Bsz, TOPK, dtype=torch.int32).pin_memory() for _ in range(5)]} for _ in range(2)]
 
     def step_device(i):
         fr = dev_pool[i % POOL]
@@ -236,11 +235,11 @@ def run_b200(args):
                          device=True)
         ctx.match_frame_pairs(pairs, INT_MAX, [t.data_ptr() for t in d_m], device=True)
 
-    def step_host(i):
-        fr = host_pool[i % POOL]
-        ctx.extract_ptrs(fr.data_ptr(), Bsz, H * W, H, W, W, TOPK, 0.05, h_nv.data_ptr(), h_xy.data_ptr(), h_sc.data_ptr(), h_ds.data_ptr(),
-                         device=False)
-        ctx.match_frame_pairs(pairs, INT_MAX, [t.data_ptr() for t in h_m], device=False)
+    def submit_host(i):
+        """End-to-end step through the host-buffer C-ABI: pinned frames in, every result back in host memory."""
+        fr, o, slot = host_pool[i % POOL], h_out[i % 2], i % 2
+        ctx.submit(slot, fr.data_ptr(), Bsz, H * W, H, W, W, TOPK, 0.05, o["nv"].data_ptr(), o["xy"].data_ptr(), o["sc"].data_ptr(),
+                   o["ds"].data_ptr(), pairs=pairs, init=INT_MAX, match_ptrs=[t.data_ptr() for t in o["m"]])
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -267,11 +266,27 @@ def run_b200(args):
         ctx.profile(False)
         return ms, launches, prof
 
+    def timed_e2e():
+        """K submissions, two in flight; the timed region starts before the first H2D copy and ends when the
+        last result is in host memory (xfb_wait), measured on the host clock around device synchronisation."""
+        for i in range(Wm):
+            submit_host(i)
+        ctx.wait(0); ctx.wait(1)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            submit_host(Wm + i)          # xfb_submit waits for this slot's previous results first
+        ctx.wait(0); ctx.wait(1)
+        torch.cuda.synchronize(dev)
+        ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        return ms
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms_dev, launches, prof = timed(step_device, profile=True)
-    ms_e2e, _, _ = timed(step_host)
+    ms_e2e = timed_e2e()
     clocks = sampler.stop() if rank == 0 else None
 
     nv = d_nv.cpu().numpy()

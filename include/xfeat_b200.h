@@ -111,6 +111,20 @@ int xfb_match_frame_pairs(xfb_ctx* ctx, const int32_t* pairs, int n_pairs, int i
 int xfb_match_frame_pairs_device(xfb_ctx* ctx, const int32_t* pairs, int n_pairs, int init_dist, int32_t* d_best_idx,
                                  int32_t* d_best_dist, int32_t* d_second_dist, int32_t* d_best_idx_rev, int32_t* d_best_dist_rev);
 
+/* ---- pipelined form for frame streams ------------------------------------------------------
+ * xfb_submit enqueues one batch: host->device copy of the frames, extraction, (optionally) the frame-pair
+ * matches of xfb_match_frame_pairs, and the device->host copies of every requested output -- on three CUDA
+ * streams (copy-in, compute, copy-out) chained by events, and returns immediately.  Two slots (0, 1) can
+ * be in flight, so the copies of batch i+1 / i-1 overlap the kernels of batch i.  xfb_wait blocks until
+ * the slot's outputs are in the caller's buffers.  Host buffers should be pinned (cudaHostAlloc /
+ * cudaHostRegister) for the copies to be truly asynchronous; all buffers stay caller-owned and must
+ * remain valid until xfb_wait(slot) returns.  Match outputs are [n_pairs][topk]; any may be NULL. */
+int xfb_submit(xfb_ctx* ctx, int slot, const uint8_t* gray, int batch, size_t frame_stride, int h, int w, int stride, int topk,
+               float nms_thr, int32_t* n_valid, float* kpt_xy, float* score, float* desc, const int32_t* pairs, int n_pairs,
+               int init_dist, int32_t* best_idx, int32_t* best_dist, int32_t* second_dist, int32_t* best_idx_rev,
+               int32_t* best_dist_rev);
+int xfb_wait(xfb_ctx* ctx, int slot);
+
 /* ---- introspection (used by the parity tests and bench.py) ------------------------------- */
 
 /* Copies an intermediate of the last extract call to the host as fp32.  `name` is a reference

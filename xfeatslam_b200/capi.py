@@ -18,7 +18,7 @@ INT_MAX = 2 ** 31 - 1
 SYMBOLS = [
     "xfb_create", "xfb_destroy", "xfb_last_error", "xfb_set_stream", "xfb_extract", "xfb_extract_batch",
     "xfb_extract_batch_device", "xfb_distance_matrix", "xfb_distance_matrix_device", "xfb_match", "xfb_match_device",
-    "xfb_match_frames", "xfb_match_frame_pairs", "xfb_match_frame_pairs_device", "xfb_profile_enable", "xfb_profile_read", "xfb_profile_tag_name",
+    "xfb_submit", "xfb_wait", "xfb_match_frames", "xfb_match_frame_pairs", "xfb_match_frame_pairs_device", "xfb_profile_enable", "xfb_profile_read", "xfb_profile_tag_name",
     "xfb_debug_match_error", "xfb_debug_force_simt", "xfb_debug_read", "xfb_debug_read_stats", "xfb_debug_post", "xfb_debug_candidates", "xfb_launch_count",
 ]
 
@@ -48,6 +48,9 @@ def load_library(path=LIB_PATH):
     lib.xfb_distance_matrix_device.argtypes = lib.xfb_distance_matrix.argtypes
     lib.xfb_match.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int] + [c_void_p] * 5
     lib.xfb_match_device.argtypes = lib.xfb_match.argtypes
+    lib.xfb_submit.argtypes = [c_void_p, c_int, c_void_p, c_int, c_size_t, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_int, c_int] + [c_void_p] * 5
+    lib.xfb_wait.argtypes = [c_void_p, c_int]
     lib.xfb_match_frames.argtypes = [c_void_p, c_int, c_int, c_int] + [c_void_p] * 5
     lib.xfb_match_frame_pairs.argtypes = [c_void_p, c_void_p, c_int, c_int] + [c_void_p] * 5
     lib.xfb_match_frame_pairs_device.argtypes = lib.xfb_match_frame_pairs.argtypes
@@ -166,6 +169,18 @@ class XFeatB200:
             outs = None
         self._check(self.lib.xfb_match_frames(self.h, fa, fb, int(init), *ptrs), "xfb_match_frames")
         return outs
+
+    def submit(self, slot, gray_ptr, batch, frame_stride, H, W, stride, topk, nms_thr, nv_ptr, xy_ptr, sc_ptr, ds_ptr, pairs=None, init=INT_MAX,
+               match_ptrs=(0, 0, 0, 0, 0)):
+        """Pipelined extract (+ frame-pair matches): host pointers (pinned), returns immediately; see xfb_wait."""
+        v = lambda q: c_void_p(q) if q else None
+        npairs = 0 if pairs is None else int(pairs.shape[0])
+        pp = None if pairs is None else _ptr(np.ascontiguousarray(pairs, np.int32))
+        self._check(self.lib.xfb_submit(self.h, slot, c_void_p(gray_ptr), batch, frame_stride, H, W, stride, topk, nms_thr, v(nv_ptr), v(xy_ptr),
+                                        v(sc_ptr), v(ds_ptr), pp, npairs, int(init), *[v(q) for q in match_ptrs]), "xfb_submit")
+
+    def wait(self, slot):
+        self._check(self.lib.xfb_wait(self.h, slot), "xfb_wait")
 
     def match_frame_pairs(self, pairs, init, out_ptrs, device=False):
         """pairs: int32 [n,2] host array; out_ptrs: 5 raw pointers (host, or device when device=True) or 0."""

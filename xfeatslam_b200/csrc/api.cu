@@ -399,6 +399,15 @@ void xfb_destroy(xfb_ctx* c) {
   for (int i = 0; i < 5; ++i) { fr(c->m_out[i]); fr(c->m_pairs_out[i]); }
   for (int i = 0; i < 2; ++i) { fr(c->tc_img[i]); fr(c->tc_nrm[i]); }
   fr(c->tc_fimg); fr(c->tc_fnrm); fr(c->tc_pairs); fr(c->tc_dbg); fr(c->tc_fnmax); fr(c->tc_bound); fr(c->tc_nmax[0]); fr(c->tc_nmax[1]);
+  for (auto& s : c->slots) {
+    fr(s.d_gray); fr(s.nvalid); fr(s.xy); fr(s.score); fr(s.desc);
+    for (int i = 0; i < 5; ++i) fr(s.m[i]);
+    if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+    if (s.ev_comp) cudaEventDestroy(s.ev_comp);
+    if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
+  }
+  if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+  if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -555,6 +564,84 @@ int xfb_match_frame_pairs_device(xfb_ctx* c, const int32_t* pairs, int n_pairs, 
                                  int32_t* ri, int32_t* rd) {
   int32_t* o[5] = {bi, bd, sd, ri, rd};
   return match_pairs_impl(c, pairs, n_pairs, init_dist, o, false);
+}
+
+static int slot_ensure(xfb_ctx* c, Ctx::Slot& s, int n_pairs) {
+  if (!s.d_gray) {
+    const size_t B = c->max_batch, K = c->max_topk;
+    XFB_ALLOC(c, s.d_gray, B * (size_t)c->max_h * c->max_w);
+    XFB_ALLOC(c, s.nvalid, B * 4);
+    XFB_ALLOC(c, s.xy, B * K * 2 * 4);
+    XFB_ALLOC(c, s.score, B * K * 4);
+    XFB_ALLOC(c, s.desc, B * K * 64 * 4);
+    XFB_CUDA_OK(c, cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+    XFB_CUDA_OK(c, cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming));
+    XFB_CUDA_OK(c, cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming));
+  }
+  if (n_pairs > s.m_cap) {
+    for (int i = 0; i < 5; ++i) { if (s.m[i]) cudaFree(s.m[i]); s.m[i] = nullptr; }
+    for (int i = 0; i < 5; ++i) XFB_ALLOC(c, s.m[i], (size_t)n_pairs * c->max_topk * 4);
+    s.m_cap = n_pairs;
+  }
+  if (!c->s_h2d) XFB_CUDA_OK(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+  if (!c->s_d2h) XFB_CUDA_OK(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+  return XFB_OK;
+}
+
+int xfb_wait(xfb_ctx* c, int slot) {
+  if (!c || slot < 0 || slot > 1) return XFB_ERR_ARG;
+  Ctx::Slot& s = c->slots[slot];
+  if (s.pending) {
+    XFB_CUDA_OK(c, cudaEventSynchronize(s.ev_d2h));
+    s.pending = false;
+  }
+  return XFB_OK;
+}
+
+int xfb_submit(xfb_ctx* c, int slot, const uint8_t* gray, int batch, size_t frame_stride, int h, int w, int stride, int topk, float nms_thr,
+               int32_t* n_valid, float* kpt_xy, float* score, float* desc, const int32_t* pairs, int n_pairs, int init_dist, int32_t* bi,
+               int32_t* bd, int32_t* sd, int32_t* ri, int32_t* rd) {
+  int r = check_extract_args(c, batch, h, w, stride, topk);
+  if (r != XFB_OK) return r;
+  if (slot < 0 || slot > 1 || !gray || !n_valid || !kpt_xy || !score || !desc || n_pairs < 0 || (n_pairs && !pairs)) {
+    c->err = "submit: bad argument";
+    return XFB_ERR_ARG;
+  }
+  for (int p = 0; p < n_pairs; ++p)
+    if (pairs[2 * p] < 0 || pairs[2 * p + 1] < 0 || pairs[2 * p] >= batch || pairs[2 * p + 1] >= batch) { c->err = "submit: pair index out of range"; return XFB_ERR_ARG; }
+  XFB_CUDA_OK(c, cudaSetDevice(c->device));
+  if ((r = xfb_wait(c, slot)) != XFB_OK) return r;             // the slot's previous outputs must have been delivered
+  Ctx::Slot& s = c->slots[slot];
+  if ((r = slot_ensure(c, s, n_pairs)) != XFB_OK) return r;
+  // copy-in stream
+  const size_t dev_fs = (size_t)h * w;
+  for (int b = 0; b < batch; ++b)
+    XFB_CUDA_OK(c, cudaMemcpy2DAsync(s.d_gray + b * dev_fs, w, gray + b * frame_stride, stride, w, h, cudaMemcpyHostToDevice, c->s_h2d));
+  XFB_CUDA_OK(c, cudaEventRecord(s.ev_h2d, c->s_h2d));
+  // compute stream
+  XFB_CUDA_OK(c, cudaStreamWaitEvent(c->stream, s.ev_h2d, 0));
+  r = extract_device(c, s.d_gray, batch, dev_fs, h, w, w, topk, nms_thr, s.nvalid, s.xy, s.score, s.desc);
+  if (r != XFB_OK) return r;
+  int32_t* host_m[5] = {bi, bd, sd, ri, rd};
+  if (n_pairs) {
+    int32_t* d[5];
+    for (int i = 0; i < 5; ++i) d[i] = host_m[i] ? s.m[i] : nullptr;
+    if ((r = tc_match_frames(c, pairs, n_pairs, init_dist, d)) != XFB_OK) return r;
+  }
+  XFB_CUDA_OK(c, cudaEventRecord(s.ev_comp, c->stream));
+  // copy-out stream
+  XFB_CUDA_OK(c, cudaStreamWaitEvent(c->s_d2h, s.ev_comp, 0));
+  const size_t K = topk;
+  XFB_CUDA_OK(c, cudaMemcpyAsync(n_valid, s.nvalid, (size_t)batch * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+  XFB_CUDA_OK(c, cudaMemcpyAsync(kpt_xy, s.xy, batch * K * 2 * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+  XFB_CUDA_OK(c, cudaMemcpyAsync(score, s.score, batch * K * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+  XFB_CUDA_OK(c, cudaMemcpyAsync(desc, s.desc, batch * K * 64 * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+  for (int i = 0; i < 5; ++i)
+    if (n_pairs && host_m[i]) XFB_CUDA_OK(c, cudaMemcpyAsync(host_m[i], s.m[i], (size_t)n_pairs * K * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+  XFB_CUDA_OK(c, cudaEventRecord(s.ev_d2h, c->s_d2h));
+  // the next compute that reuses this slot's device buffers waits in xfb_submit -> xfb_wait(slot); nothing else aliases them
+  s.pending = true;
+  return XFB_OK;
 }
 
 int xfb_debug_match_error(xfb_ctx* c, const float* A, int n1, const float* B, int n2, float* max_err) {

@@ -17,8 +17,9 @@
 // even/odd columns) so that consecutive output pixels are again 16 B apart.  Weights are pre-split and
 // pre-tiled per (channel phase, tap) at xfb_create and streamed with cp.async.bulk through an mbarrier ring.
 //
-// Warp roles (192 threads): warps 0-3 stage the input tile, later run the epilogue (TMEM lane quadrant =
-// warp id); warp 4 = weight loader; warp 5 = TMEM allocator + single-thread MMA issuer.
+// Warp roles (320 threads): warps 0-7 stage the input tile (4 independent 16-byte loads in flight per
+// thread), later run the epilogue (TMEM lane quadrant = warp id % 4, two warps per quadrant split the
+// columns); warp 8 = weight loader; warp 9 = TMEM allocator + single-thread MMA issuer.
 #include <cuda_runtime.h>
 
 #include <cstring>
@@ -60,7 +61,7 @@ struct TcCfg {
   static constexpr int NSTAGE_FIT = (int)((232448 - SMEM_MAIN - SMEM_TAIL) / (sizeof(float) * W_UNIT_FLOATS));
   static constexpr int NSTAGE = UNITS < 3 ? UNITS : (NSTAGE_FIT < 3 ? NSTAGE_FIT : 3);
   static constexpr size_t SMEM_BYTES = SMEM_MAIN + sizeof(float) * NSTAGE * W_UNIT_FLOATS + SMEM_TAIL;
-  static constexpr int NSLICE = (128 / COUT >= 4) ? 4 : ((128 / COUT >= 2) ? 2 : 1);
+  static constexpr int NSLICE = (256 / COUT >= 8) ? 8 : ((256 / COUT >= 4) ? 4 : ((256 / COUT >= 2) ? 2 : 1));
   static_assert(CSTAGE % 8 == 0 && CIN % CSTAGE == 0 && COUT % 4 == 0 && NP <= 256, "shape");
   static_assert(S == 1 || KS == 3, "stride 2 is implemented for 3x3 only");
   static_assert(NSTAGE >= 1 && SMEM_BYTES <= 232448, "shared memory budget");
@@ -78,7 +79,9 @@ struct ConvTcArgs {
   int full_w;             // TIN_UNFOLD: width of xn
 };
 
-constexpr int CTC_THREADS = 192;
+constexpr int CTC_PROD = 256;               // producer / epilogue threads (8 warps)
+constexpr int CTC_THREADS = CTC_PROD + 64;  // + weight-loader warp + MMA warp
+constexpr int CTC_UNR = 4;                  // independent global loads in flight per producer thread
 
 template <class C, int INMODE, int OUTMODE>
 __global__ void __launch_bounds__(CTC_THREADS, 1) conv_tc_kernel(const ConvTcArgs a) {
@@ -104,63 +107,83 @@ __global__ void __launch_bounds__(CTC_THREADS, 1) conv_tc_kernel(const ConvTcArg
   const int oy0 = blockIdx.y * C::TH, ox0 = blockIdx.x * C::TW;
 
   if (t == 0) {
-    mbar_init(bar_in, 128);
+    mbar_init(bar_in, CTC_PROD);
     mbar_init(bar_free, 1);
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_wfull + s, 1); mbar_init(bar_wempty + s, 1); }
     mbar_init(bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) tmem_alloc(s_tmem, C::TMEM_COLS);
+  if (warp == 9) tmem_alloc(s_tmem, C::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ===== stage the halo tile: BN + ReLU of the producer, exact hi/lo split, channel-chunk planes =====
     const float* in_b = (INMODE == TIN_UNFOLD) ? a.in + (size_t)b * (a.Hin * 8) * a.full_w : a.in + (size_t)b * a.Hin * a.Win * CIN;
+    constexpr int ITEMS = NSUB * NPIX * KCS;
     for (int ph = 0; ph < NPHASE; ++ph) {
       if (ph > 0) mbar_wait(bar_free, (ph - 1) & 1);      // the previous phase's MMAs are done with the buffer
-      for (int idx = t; idx < NSUB * NPIX * KCS; idx += 128) {
-        const int kc = idx % KCS;
-        const int rest = idx / KCS;
-        const int pix = rest % NPIX, sub = rest / NPIX;
-        int iy, ix;
-        if (C::S == 1) { iy = oy0 - C::PAD + pix / WT; ix = ox0 - C::PAD + pix % WT; }
-        else { iy = 2 * (oy0 - 1 + pix / WT) + (sub >> 1); ix = 2 * (ox0 - 1 + pix % WT) + (sub & 1); }
-        const int ch = ph * C::CSTAGE + kc * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win) {
-          if (INMODE == TIN_UNFOLD) {
-            // XFeatModel::unfold2d(x, 8), src/XFeat.cc:124-133: channel c = (y % 8) * 8 + x % 8
-            v = *reinterpret_cast<const float4*>(in_b + (size_t)(iy * 8 + (ch >> 3)) * a.full_w + ix * 8 + (ch & 7));
-          } else {
-            v = *reinterpret_cast<const float4*>(in_b + ((size_t)iy * a.Win + ix) * CIN + ch);
-            if (INMODE == TIN_BN || INMODE == TIN_BN_SKIP) {
-              const float4 m = *reinterpret_cast<const float4*>(a.in_mean + b * CIN + ch);
-              const float4 r = *reinterpret_cast<const float4*>(a.in_rstd + b * CIN + ch);
-              v.x = fmaxf((v.x - m.x) * r.x, 0.f); v.y = fmaxf((v.y - m.y) * r.y, 0.f);
-              v.z = fmaxf((v.z - m.z) * r.z, 0.f); v.w = fmaxf((v.w - m.w) * r.w, 0.f);
-            }
-            if (INMODE == TIN_BN_SKIP) {
-              // x1 + skip1(x), src/XFeat.cc:153; skip1 = AvgPool2d(4,4) + Conv2d(1,24,1) (:36-39)
-              const float av = a.skip_avg[((size_t)b * a.Hin + iy) * a.Win + ix];
-              const float4 sw = *reinterpret_cast<const float4*>(a.skip_w + ch);
-              const float4 sb = *reinterpret_cast<const float4*>(a.skip_b + ch);
-              v.x += av * sw.x + sb.x; v.y += av * sw.y + sb.y; v.z += av * sw.z + sb.z; v.w += av * sw.w + sb.w;
+      for (int base = 0; base < ITEMS; base += CTC_PROD * CTC_UNR) {
+        float4 v[CTC_UNR];
+        float av[CTC_UNR];
+        int off[CTC_UNR], chn[CTC_UNR];
+        // issue all loads of this batch first (memory-level parallelism), then transform and store
+#pragma unroll
+        for (int u = 0; u < CTC_UNR; ++u) {
+          const int idx = base + u * CTC_PROD + t;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          av[u] = 0.f;
+          off[u] = -1;
+          chn[u] = -1;
+          if (idx < ITEMS) {
+            const int kc = idx % KCS;
+            const int rest = idx / KCS;
+            const int pix = rest % NPIX, sub = rest / NPIX;
+            int iy, ix;
+            if (C::S == 1) { iy = oy0 - C::PAD + pix / WT; ix = ox0 - C::PAD + pix % WT; }
+            else { iy = 2 * (oy0 - 1 + pix / WT) + (sub >> 1); ix = 2 * (ox0 - 1 + pix % WT) + (sub & 1); }
+            const int ch = ph * C::CSTAGE + kc * 4;
+            off[u] = sub * C::SUB_FLOATS + kc * PS + pix * 4;
+            if (iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win) {
+              chn[u] = ch;
+              if (INMODE == TIN_UNFOLD) {
+                // XFeatModel::unfold2d(x, 8), src/XFeat.cc:124-133: channel c = (y % 8) * 8 + x % 8
+                v[u] = *reinterpret_cast<const float4*>(in_b + (size_t)(iy * 8 + (ch >> 3)) * a.full_w + ix * 8 + (ch & 7));
+              } else {
+                v[u] = *reinterpret_cast<const float4*>(in_b + ((size_t)iy * a.Win + ix) * CIN + ch);
+                if (INMODE == TIN_BN_SKIP) av[u] = a.skip_avg[((size_t)b * a.Hin + iy) * a.Win + ix];
+              }
             }
           }
         }
-        float4 hi, lo;
-        tf32_split(v.x, hi.x, lo.x); tf32_split(v.y, hi.y, lo.y); tf32_split(v.z, hi.z, lo.z); tf32_split(v.w, hi.w, lo.w);
-        const int o = sub * C::SUB_FLOATS + kc * PS + pix * 4;
-        *reinterpret_cast<float4*>(sInHi + o) = hi;
-        *reinterpret_cast<float4*>(sInLo + o) = lo;
+#pragma unroll
+        for (int u = 0; u < CTC_UNR; ++u) {
+          if (off[u] < 0) continue;
+          float4 x = v[u];
+          if (chn[u] >= 0 && (INMODE == TIN_BN || INMODE == TIN_BN_SKIP)) {
+            const float4 m = *reinterpret_cast<const float4*>(a.in_mean + b * CIN + chn[u]);
+            const float4 r = *reinterpret_cast<const float4*>(a.in_rstd + b * CIN + chn[u]);
+            x.x = fmaxf((x.x - m.x) * r.x, 0.f); x.y = fmaxf((x.y - m.y) * r.y, 0.f);
+            x.z = fmaxf((x.z - m.z) * r.z, 0.f); x.w = fmaxf((x.w - m.w) * r.w, 0.f);
+            if (INMODE == TIN_BN_SKIP) {
+              // x1 + skip1(x), src/XFeat.cc:153; skip1 = AvgPool2d(4,4) + Conv2d(1,24,1) (:36-39)
+              const float4 sw = *reinterpret_cast<const float4*>(a.skip_w + chn[u]);
+              const float4 sb = *reinterpret_cast<const float4*>(a.skip_b + chn[u]);
+              x.x += av[u] * sw.x + sb.x; x.y += av[u] * sw.y + sb.y; x.z += av[u] * sw.z + sb.z; x.w += av[u] * sw.w + sb.w;
+            }
+          }
+          float4 hi, lo;
+          tf32_split(x.x, hi.x, lo.x); tf32_split(x.y, hi.y, lo.y); tf32_split(x.z, hi.z, lo.z); tf32_split(x.w, hi.w, lo.w);
+          *reinterpret_cast<float4*>(sInHi + off[u]) = hi;
+          *reinterpret_cast<float4*>(sInLo + off[u]) = lo;
+        }
       }
       fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async-proxy reads
       mbar_arrive(bar_in);
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ===== weight loader: one bulk copy per (phase, tap) unit through the stage ring =====
     if (lane == 0) {
       for (int u = 0; u < C::UNITS; ++u) {
@@ -210,33 +233,38 @@ __global__ void __launch_bounds__(CTC_THREADS, 1) conv_tc_kernel(const ConvTcArg
     }
   }
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ===== epilogue: TMEM -> registers -> smem staging -> coalesced NHWC store + channel statistics =====
     mbar_wait(bar_acc, 0);
     tc_fence_after();
-    const int p = warp * 32 + lane;                 // pixel of the tile = TMEM lane
+    const int quad = warp & 3, half = warp >> 2;     // two warps per TMEM lane quadrant, each takes half of the columns
+    const int p = quad * 32 + lane;                   // pixel of the tile = TMEM lane
+    constexpr int NCH = C::NP / 32;                   // 32-column chunks
 #pragma unroll
-    for (int c0 = 0; c0 < C::NP; c0 += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+    for (int ci = 0; ci < NCH; ++ci) {
+      if ((NCH == 1 && half == 0) || (NCH > 1 && (ci * 2) / NCH == half)) {
+        const int c0 = ci * 32;
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
 #pragma unroll
-      for (int q = 0; q < 32; q += 4) {
-        if (c0 + q < COUT) {
-          float4 o = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
-          if (OUTMODE == TOUT_BIAS) {
-            const float4 bv = *reinterpret_cast<const float4*>(a.bias + c0 + q);
-            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+        for (int q = 0; q < 32; q += 4) {
+          if (c0 + q < COUT) {
+            float4 o = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+            if (OUTMODE == TOUT_BIAS) {
+              const float4 bv = *reinterpret_cast<const float4*>(a.bias + c0 + q);
+              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+            }
+            *reinterpret_cast<float4*>(sOut + p * C::OUT_LD + c0 + q) = o;
           }
-          *reinterpret_cast<float4*>(sOut + p * C::OUT_LD + c0 + q) = o;
         }
       }
     }
     tc_fence_before();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     // coalesced store: the 8 pixels of an output row are 8 * COUT contiguous floats in NHWC
     float* out_b = a.out + (size_t)b * a.Hout * a.Wout * COUT;
     constexpr int V4_PER_PIX = COUT / 4;
-    for (int idx = t; idx < 128 * V4_PER_PIX; idx += 128) {
+    for (int idx = t; idx < 128 * V4_PER_PIX; idx += CTC_PROD) {
       const int pp = idx / V4_PER_PIX, c4 = idx % V4_PER_PIX;
       const int oy = oy0 + (pp >> 3), ox = ox0 + (pp & 7);
       if (oy < a.Hout && ox < a.Wout)
@@ -245,9 +273,10 @@ __global__ void __launch_bounds__(CTC_THREADS, 1) conv_tc_kernel(const ConvTcArg
     if (OUTMODE == TOUT_STATS) {
       // per-channel sums over the valid pixels of the tile: COUT channels x NSLICE pixel slices
       constexpr int NSLICE = C::NSLICE, PIX_PER = 128 / NSLICE;
-      for (int item = t; item < COUT * NSLICE; item += 128) {
+      for (int item = t; item < COUT * NSLICE; item += CTC_PROD) {
         const int c = item % COUT, sl = item / COUT;
         float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
         for (int pp = sl * PIX_PER; pp < (sl + 1) * PIX_PER; ++pp) {
           const int oy = oy0 + (pp >> 3), ox = ox0 + (pp & 7);
           if (oy < a.Hout && ox < a.Wout) {
@@ -259,27 +288,27 @@ __global__ void __launch_bounds__(CTC_THREADS, 1) conv_tc_kernel(const ConvTcArg
         sStat[(sl * COUT + c) * 2] = (double)s1;
         sStat[(sl * COUT + c) * 2 + 1] = (double)s2;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       const int tiles = gridDim.x * gridDim.y;
       const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
       double* part_b = a.part + (size_t)b * tiles * COUT * 2;
-      for (int c = t; c < COUT; c += 128) {
+      for (int c = t; c < COUT; c += CTC_PROD) {
         double d1 = 0.0, d2 = 0.0;
         for (int sl = 0; sl < NSLICE; ++sl) { d1 += sStat[(sl * COUT + c) * 2]; d2 += sStat[(sl * COUT + c) * 2 + 1]; }
         part_b[((size_t)tile_id * COUT + c) * 2] = d1;
         part_b[((size_t)tile_id * COUT + c) * 2 + 1] = d2;
       }
       __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (t == 0) {
         const unsigned int prev = atomicAdd(a.ticket + b, 1u);
         s_last = (prev == (unsigned int)(tiles - 1)) ? 1u : 0u;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (s_last) {
         __threadfence();
         // last CTA of the frame: fixed-order fold of all tile partials (slice-strided, then slice order)
-        for (int e = t; e < NSLICE * COUT; e += 128) {
+        for (int e = t; e < NSLICE * COUT; e += CTC_PROD) {
           const int c = e % COUT, sl = e / COUT;
           double d1 = 0.0, d2 = 0.0;
           for (int i = sl; i < tiles; i += NSLICE) {
@@ -289,9 +318,9 @@ __global__ void __launch_bounds__(CTC_THREADS, 1) conv_tc_kernel(const ConvTcArg
           sStat[(sl * COUT + c) * 2] = d1;
           sStat[(sl * COUT + c) * 2 + 1] = d2;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         const double n = (double)a.Hout * (double)a.Wout;
-        for (int c = t; c < COUT; c += 128) {
+        for (int c = t; c < COUT; c += CTC_PROD) {
           double d1 = 0.0, d2 = 0.0;
           for (int sl = 0; sl < NSLICE; ++sl) { d1 += sStat[(sl * COUT + c) * 2]; d2 += sStat[(sl * COUT + c) * 2 + 1]; }
           const double mean = d1 / n;
@@ -306,7 +335,7 @@ __global__ void __launch_bounds__(CTC_THREADS, 1) conv_tc_kernel(const ConvTcArg
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
   }

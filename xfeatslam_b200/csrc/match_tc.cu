@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(256) match_prep_kernel(const float* desc, size
 #pragma unroll
   for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off, 16);
   if (kq == 0) {
-    nrm[(size_t)set * rows_padded + row] = (float)s;
+    // padded rows get |b|^2 = +inf: as COLUMNS they then score u = dot - |b|^2/2 = -inf and can never be candidates
+    nrm[(size_t)set * rows_padded + row] = (row < n) ? (float)s : CUDART_INF_F;
     if (s > 0.0) atomicMax(reinterpret_cast<unsigned int*>(nrm_max + set), __float_as_uint((float)s));   // non-negative floats order as uints
   }
 }
@@ -436,18 +437,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) match_bound_kernel(const MatchT
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acce + acc);
       const int j0 = c * TC_ROWS + part * 32;
-      const bool tail = (j0 + 32 > nB);
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
-        const float4 nb = *reinterpret_cast<const float4*>(nrmB + j0 + 4 * g);
-        float u0 = fmaf(-0.5f, nb.x, v[4 * g + 0]), u1 = fmaf(-0.5f, nb.y, v[4 * g + 1]);
-        float u2 = fmaf(-0.5f, nb.z, v[4 * g + 2]), u3 = fmaf(-0.5f, nb.w, v[4 * g + 3]);
-        if (tail) {
-          if (j0 + 4 * g + 0 >= nB) u0 = -CUDART_INF_F;
-          if (j0 + 4 * g + 1 >= nB) u1 = -CUDART_INF_F;
-          if (j0 + 4 * g + 2 >= nB) u2 = -CUDART_INF_F;
-          if (j0 + 4 * g + 3 >= nB) u3 = -CUDART_INF_F;
-        }
+        const float4 nb = *reinterpret_cast<const float4*>(nrmB + j0 + 4 * g);   // +inf for padded columns -> u = -inf
+        const float u0 = fmaf(-0.5f, nb.x, v[4 * g + 0]), u1 = fmaf(-0.5f, nb.y, v[4 * g + 1]);
+        const float u2 = fmaf(-0.5f, nb.z, v[4 * g + 2]), u3 = fmaf(-0.5f, nb.w, v[4 * g + 3]);
         top2_max_push(m1a, m2a, u0); top2_max_push(m1b, m2b, u1);
         top2_max_push(m1a, m2a, u2); top2_max_push(m1b, m2b, u3);
       }

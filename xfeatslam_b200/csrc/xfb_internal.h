@@ -104,6 +104,17 @@ struct Ctx {
   float* o_score = nullptr;
   float* o_desc = nullptr;
 
+  // pipelined submissions (xfb_submit / xfb_wait)
+  struct Slot {
+    uint8_t* d_gray = nullptr;
+    int32_t* nvalid = nullptr; float* xy = nullptr; float* score = nullptr; float* desc = nullptr;
+    int32_t* m[5] = {};
+    int m_cap = 0;                 // pairs the match buffers hold
+    cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_d2h = nullptr;
+    bool pending = false;
+  } slots[2];
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+
   // last extract geometry for xfb_match_frames
   int last_topk = 0;
   const int32_t* last_nvalid = nullptr;   // device
