@@ -195,6 +195,7 @@ def run_reference(args):
 def run_b200(args):
     import torch
     import torch.distributed as dist
+    from xfeatslam_b200 import shard
     from xfeatslam_b200.capi import XFeatB200
     from xfeatslam_b200.frames import synthetic_frames
 
@@ -215,8 +216,11 @@ def run_b200(args):
     stream = torch.cuda.Stream(device=dev)
     ctx.set_stream(stream.cuda_stream)
 
-    # frame shard of this rank: frames are independent units, frame i -> rank (i mod world)
-    host_pool = [torch.from_numpy(synthetic_frames(10000 * rank + 100 * p, Bsz, H, W)).pin_memory() for p in range(POOL)]
+    # frame shard of this rank: frames are independent units, global frame i -> rank (i mod world)
+    # (shard.frame_indices); the pool holds this rank's frames of POOL consecutive global batches
+    from xfeatslam_b200.frames import synthetic_frame
+    host_pool = [torch.from_numpy(np.stack([synthetic_frame(7000 + g) for g in shard.frame_indices(rank, world, world * Bsz * POOL)[p * Bsz:(p + 1) * Bsz]])).pin_memory()
+                 for p in range(POOL)]
     dev_pool = [t.to(dev) for t in host_pool]
     d_nv = torch.zeros(Bsz, dtype=torch.int32, device=dev)
     d_xy = torch.zeros(Bsz, TOPK, 2, dtype=torch.float32, device=dev)
@@ -291,16 +295,10 @@ def run_b200(args):
 
     nv = d_nv.cpu().numpy()
     matched = int((d_m[0].cpu().numpy() >= 0).sum())
-    counters = torch.tensor([K * Bsz, int(nv.sum()), matched, int(ms_dev * 1e6)], dtype=torch.int64, device=dev)
-    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)                      # max over ranks
-        gathered = [torch.zeros_like(counters) for _ in range(world)]
-        dist.all_gather(gathered, counters)                           # NCCL: counts/timings only
-        counters_all = torch.stack(gathered).cpu().numpy()
-    else:
-        counters_all = counters.cpu().numpy()[None]
-    ms_dev_max, ms_e2e_max = float(t[0]), float(t[1])
+    # NCCL carries counts / timings only: all-gather of int64[4] per rank + max-reduce of the time
+    counters_t, ms_dev_max = shard.gather_counters(K * Bsz, int(nv.sum()), matched, ms_dev, device=dev)
+    _, ms_e2e_max = shard.gather_counters(K * Bsz, int(nv.sum()), matched, ms_e2e, device=dev)
+    counters_all = counters_t.numpy()
     total_frames = int(counters_all[:, 0].sum())
     value = total_frames / (ms_dev_max * 1e-3)
     e2e_value = total_frames / (ms_e2e_max * 1e-3)
