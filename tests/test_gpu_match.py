@@ -92,12 +92,12 @@ def test_full_size_4096_properties(ctx):
 
 
 def test_tensor_core_estimate_error_bound(ctx):
-    """The matcher filters on a 3xTF32 tensor-core estimate t of 512*d; the filter is sound while
-    |t - 512*float(S)| < MATCH_EPS = 0.02 (csrc/match_tc.cu).  Measure the actual maximum over all pairs."""
+    """The matcher filters on a tensor-core estimate t of 512*d (bf16 split a1.b1 + a1.b2 + a2.b1); the filter is
+    sound while |t - 512*float(S)| < MATCH_EPS = 0.04 (csrc/match_tc.cu).  Measure the actual maximum over all pairs."""
     rng = np.random.RandomState(13)
     A = unit(rng, 1024)
     B = np.concatenate([related(rng, A, 512, 0.02), related(rng, A, 256, 0.3), unit(rng, 256)]).astype(np.float32)
     B[3] = 0                                               # phantom row
     B[4] = A[0]                                            # exact duplicate -> distance 0
     err = ctx.match_error(A, B)
-    assert err < 0.005, err
+    assert err < 0.02, err

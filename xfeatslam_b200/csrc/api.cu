@@ -191,7 +191,7 @@ static int tc_ensure_generic(Ctx* c, int n1, int n2) {
   const int need = pad128(n1 > n2 ? n1 : n2);
   if (need > c->tc_cap) {
     for (int i = 0; i < 2; ++i) { if (c->tc_img[i]) cudaFree(c->tc_img[i]); if (c->tc_nrm[i]) cudaFree(c->tc_nrm[i]); c->tc_img[i] = nullptr; c->tc_nrm[i] = nullptr; }
-    for (int i = 0; i < 2; ++i) { XFB_ALLOC(c, c->tc_img[i], (size_t)need * 160 * 4); XFB_ALLOC(c, c->tc_nrm[i], (size_t)need * 4); }
+    for (int i = 0; i < 2; ++i) { XFB_ALLOC(c, c->tc_img[i], (size_t)need * 64 * 4); XFB_ALLOC(c, c->tc_nrm[i], (size_t)need * 4); }
     c->tc_cap = need;
   }
   for (int i = 0; i < 2; ++i) if (!c->tc_nmax[i]) XFB_ALLOC(c, c->tc_nmax[i], 16);
@@ -253,14 +253,14 @@ static int tc_matrix_generic(Ctx* c, const float* dA, int n1, const float* dB, i
 // frames of the last extract: pairs (host) -> outputs [n_pairs][K] (device pointers, nullable)
 static int tc_match_frames(Ctx* c, const int32_t* pairs, int n_pairs, int init, int32_t* o[5]) {
   const int K = c->last_topk, P = pad128(K);
-  const size_t img_stride = (size_t)P * 160;
+  const size_t img_stride = (size_t)P * 64;
   if (!c->tc_fimg || c->tc_frows < P) {
     if (c->tc_fimg) cudaFree(c->tc_fimg);
     if (c->tc_fnrm) cudaFree(c->tc_fnrm);
     if (c->tc_fnmax) cudaFree(c->tc_fnmax);
     c->tc_fimg = nullptr; c->tc_fnrm = nullptr; c->tc_fnmax = nullptr;
     const int PM = pad128(c->max_topk);
-    XFB_ALLOC(c, c->tc_fimg, (size_t)c->max_batch * PM * 160 * 4);
+    XFB_ALLOC(c, c->tc_fimg, (size_t)c->max_batch * PM * 64 * 4);
     XFB_ALLOC(c, c->tc_fnrm, (size_t)c->max_batch * PM * 4);
     XFB_ALLOC(c, c->tc_fnmax, (size_t)c->max_batch * 4);
     c->tc_frows = PM;

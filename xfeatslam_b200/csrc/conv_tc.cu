@@ -344,10 +344,10 @@ __global__ void __launch_bounds__(CTC_THREADS, 1) conv_tc_kernel(const ConvTcArg
 // ---------------------------------------------------------------------------------------------------
 //                       CIN COUT KS S CSTAGE
 using TcB2x = TcCfg<24, 24, 3, 1, 24>;      // block2.0/.1                        120x160
-using TcB30 = TcCfg<24, 64, 3, 2, 24>;      // block3.0                           -> 60x80
-using TcC33 = TcCfg<64, 64, 3, 1, 64>;      // block3.1, block4.1/.2, block_fusion.0/.1
+using TcB30 = TcCfg<24, 64, 3, 2, 8>;       // block3.0                           -> 60x80   (3 channel phases: 56 KB smem, 4 CTAs / SM)
+using TcC33 = TcCfg<64, 64, 3, 1, 32>;      // block3.1, block4.1/.2, block_fusion.0/.1      (2 channel phases: 98 KB smem, 2 CTAs / SM)
 using TcC11 = TcCfg<64, 64, 1, 1, 64>;      // block3.2, block_fusion.2, heatmap_head.0/.1, keypoint_head.0/.1/.2
-using TcB40 = TcCfg<64, 64, 3, 2, 32>;      // block4.0                           -> 30x40
+using TcB40 = TcCfg<64, 64, 3, 2, 16>;      // block4.0                           -> 30x40   (4 channel phases: 107 KB smem, 2 CTAs / SM)
 using TcB50 = TcCfg<64, 128, 3, 2, 32>;     // block5.0                           -> 15x20
 using TcB5x = TcCfg<128, 128, 3, 1, 64>;    // block5.1/.2
 using TcB53 = TcCfg<128, 64, 1, 1, 128>;    // block5.3
