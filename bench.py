@@ -160,9 +160,23 @@ def cpu_reference_run(n_extract, n_match, threads, topk=TOPK, h=H, w=W, warm=2):
     t0 = time.perf_counter()
     for _ in range(n_match):
         mo.bruteforce(A, B)
-    out["match_s_per_pair"] = (time.perf_counter() - t0) / max(n_match, 1)
+    out["match_s_per_pair"] = (time.perf_counter() - t0) / n_match if n_match else 0.0
     out["fps"] = 1.0 / (out["extract_s_per_frame"] + out["match_s_per_pair"])
     return out
+
+
+def best_reference_threads(ncpu):
+    """libtorch's intra-op pool scales badly past ~16-32 threads on this small CNN: probe a few settings on a
+    3-frame sample and give the reference its best one ("all the host threads it can use")."""
+    best, best_t = ncpu, None
+    for thr in sorted({ncpu, min(ncpu, 64), min(ncpu, 32), min(ncpu, 16), min(ncpu, 8)}, reverse=True):
+        try:
+            r = cpu_reference_run(n_extract=3, n_match=0, threads=thr, warm=1)
+        except Exception:
+            continue
+        if best_t is None or r["extract_s_per_frame"] < best_t:
+            best, best_t = thr, r["extract_s_per_frame"]
+    return best
 
 
 def run_reference(args):
@@ -173,7 +187,8 @@ def run_reference(args):
     n_frames = max(1, args.steps + args.warmup)
     n_match = max(1, min(args.steps, 8))
     t0 = time.perf_counter()
-    r = cpu_reference_run(n_extract=n_frames, n_match=n_match, threads=ncpu, warm=max(args.warmup, 1))
+    thr = best_reference_threads(ncpu)
+    r = cpu_reference_run(n_extract=n_frames, n_match=n_match, threads=thr, warm=max(args.warmup, 1))
     wall = time.perf_counter() - t0
     value = r["fps"]
     sample = ("%d VGA frames through the reference XFextractor::operator() (libtorch CPU, %d threads: %.1f ms/frame) + %d brute-force "
@@ -313,23 +328,31 @@ def run_b200(args):
             alg = layer_flops(name, H, W) * Bsz
             pipe = "fp32-simt"
         elif name == "match_tile":
-            alg = 2.0 * TOPK * TOPK * 64
+            alg = 2.0 * TOPK * TOPK * 64 * Bsz           # one launch = Bsz frame pairs, 2*N1*N2*64 each
             pipe = "tcgen05 kind::tf32 (3xTF32 split) + exact fp64 fix-up"
         else:
             alg = 0.0
             pipe = "n/a"
+        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/), per launch
+        traffic = None
+        tp = REPO / "profiles" / "r01_dram_traffic_per_launch.json"
+        if tp.exists():
+            tj = json.loads(tp.read_text())
+            key = {"match_tile": "match_tc_kernel<0, 0>(MatchTcArgs)", "match_bound": "match_bound_kernel(MatchTcArgs)"}.get(name)
+            if key in tj:
+                traffic = tj[key]
         achieved = alg / (avg_ms * 1e-3) / 1e12
         shares = {k: round(v[0] / tot, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:8]}
         all_ms = {k: round(v[0] / K, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
         roofline = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"] + " cuBLAS bf16 burst",
+                    "frac": achieved / peaks["bf16_tflops"], "traffic": traffic, "peak_source": peaks["source"] + " cuBLAS bf16 burst",
                     "pipe_used": pipe, "avg_launch_ms": avg_ms, "launches_timed": kcnt, "algorithmic_flops_per_launch": alg,
                     "share_of_step": round(kms / tot, 4), "top_shares": shares, "kernel_ms_per_step": all_ms,
                     "whole_path_conv_tflops": conv_flops_per_frame(H, W) * value / max(world, 1) / 1e12}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             ncpu = os.cpu_count() or 1
-            r = cpu_reference_run(n_extract=16, n_match=3, threads=ncpu)
+            r = cpu_reference_run(n_extract=16, n_match=3, threads=best_reference_threads(ncpu))
             cpu = {"value": r["fps"], "unit": UNIT, "cores": ncpu, "kind": r["kind"],
                    "sample": "16 VGA frames reference XFextractor (libtorch CPU, %d threads, %.1f ms/frame) + 3 brute-force 4096x4096 matches "
                              "(C port, 1 thread, %.2f s/pair)" % (r["extract_threads"], r["extract_s_per_frame"] * 1e3, r["match_s_per_pair"])}
