@@ -167,8 +167,7 @@ static int ensure_match_scratch(Ctx* c, int n1, int n2, bool want_matrix) {
   if (n > c->m_cap) {
     float** fp[2] = {&c->m_a, &c->m_b};
     for (auto p : fp) { if (*p) cudaFree(*p); *p = nullptr; }
-    int32_t** ip[] = {&c->m_ga, &c->m_gb, &c->m_out[0], &c->m_out[1], &c->m_out[2], &c->m_out[3], &c->m_out[4], &c->m_rowpart,
-                      &c->m_colpart, &c->m_matrix};
+    int32_t** ip[] = {&c->m_ga, &c->m_gb, &c->m_out[0], &c->m_out[1], &c->m_out[2], &c->m_out[3], &c->m_out[4], &c->m_matrix};
     for (auto p : ip) { if (*p) cudaFree(*p); *p = nullptr; }
     const size_t cap = (size_t)((n + 63) / 64) * 64;
     XFB_ALLOC(c, c->m_a, cap * 64 * 4);
@@ -176,8 +175,6 @@ static int ensure_match_scratch(Ctx* c, int n1, int n2, bool want_matrix) {
     XFB_ALLOC(c, c->m_ga, cap * 4);
     XFB_ALLOC(c, c->m_gb, cap * 4);
     for (int i = 0; i < 5; ++i) XFB_ALLOC(c, c->m_out[i], cap * 4);
-    XFB_ALLOC(c, c->m_rowpart, cap * (cap / 64) * 3 * 4);
-    XFB_ALLOC(c, c->m_colpart, cap * (cap / 64) * 2 * 4);
     c->m_cap = (int)cap;
   }
   if (want_matrix && !c->m_matrix) XFB_ALLOC(c, c->m_matrix, (size_t)c->m_cap * c->m_cap * 4);
@@ -395,7 +392,7 @@ void xfb_destroy(xfb_ctx* c) {
   for (int L = 0; L < L_NUM_BN; ++L) { fr(c->bn[L].mean); fr(c->bn[L].rstd); }
   fr(c->d_gray); fr(c->xraw); fr(c->xn); fr(c->avg4); fr(c->pyr); fr(c->k1h); fr(c->in_mean); fr(c->in_rstd); fr(c->part);
   fr(c->ticket); fr(c->cand); fr(c->cand_count); fr(c->cand_count_last); fr(c->o_nvalid); fr(c->o_xy); fr(c->o_score); fr(c->o_desc);
-  fr(c->m_a); fr(c->m_b); fr(c->m_ga); fr(c->m_gb); fr(c->m_rowpart); fr(c->m_colpart); fr(c->m_matrix);
+  fr(c->m_a); fr(c->m_b); fr(c->m_ga); fr(c->m_gb); fr(c->m_matrix);
   for (int i = 0; i < 5; ++i) { fr(c->m_out[i]); fr(c->m_pairs_out[i]); }
   for (int i = 0; i < 2; ++i) { fr(c->tc_img[i]); fr(c->tc_nrm[i]); }
   fr(c->tc_fimg); fr(c->tc_fnrm); fr(c->tc_pairs); fr(c->tc_dbg); fr(c->tc_fnmax); fr(c->tc_bound); fr(c->tc_nmax[0]); fr(c->tc_nmax[1]);

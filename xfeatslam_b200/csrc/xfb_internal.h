@@ -130,7 +130,6 @@ struct Ctx {
   float* m_a = nullptr; float* m_b = nullptr;
   int32_t* m_ga = nullptr; int32_t* m_gb = nullptr;
   int32_t* m_out[5] = {};
-  int32_t* m_rowpart = nullptr; int32_t* m_colpart = nullptr;
   int32_t* m_matrix = nullptr;
   int m_cap = 0;
   int32_t* m_pairs_out[5] = {};   // [n_pairs][topk] staging for xfb_match_frame_pairs
@@ -198,10 +197,6 @@ cudaError_t launch_pyramid(Ctx* c);
 cudaError_t launch_heatmap_out(Ctx* c);                  // heatmap_head.2 + sigmoid -> H1
 cudaError_t launch_keypoint_out(Ctx* c);                 // keypoint_head.3 + softmax + fold -> K1h
 cudaError_t launch_post(Ctx* c, int topk, float nms_thr, int32_t* d_nvalid, float* d_xy, float* d_score, float* d_desc);
-cudaError_t launch_distance_matrix(Ctx* c, const float* dA, int n1, const float* dB, int n2, int32_t* d_out);
-cudaError_t launch_match(Ctx* c, const float* dA, int n1, const float* dB, int n2, const int32_t* ga, const int32_t* gb, int init,
-                         int32_t* bi, int32_t* bd, int32_t* sd, int32_t* ri, int32_t* rd, const int32_t* n1p = nullptr,
-                         const int32_t* n2p = nullptr);
 cudaError_t launch_match_prep(Ctx* c, const float* desc, size_t set_stride, int n_sets, const int32_t* n_dev, int n_host, int rows_padded,
                               float* img, size_t img_set_stride, float* nrm, float* nrm_max);
 cudaError_t launch_match_bound(Ctx* c, const MatchTcArgs& a, int row_tiles, int n_pairs);
