@@ -143,6 +143,7 @@ static int alloc_buffers(Ctx* c) {
   XFB_ALLOC(c, c->in_rstd, B * 4);
   size_t pe = conv_part_elems((int)H, (int)W);
   if (conv_tc_part_elems((int)H, (int)W) > pe) pe = conv_tc_part_elems((int)H, (int)W);
+  if (conv_small_part_elems((int)H, (int)W) > pe) pe = conv_small_part_elems((int)H, (int)W);
   const size_t prep_pe = ((HW + 2047) / 2048) * 2;
   if (prep_pe > pe) pe = prep_pe;
   c->part_elems = pe;
@@ -304,7 +305,12 @@ static int run_dense(Ctx* c, const uint8_t* d_gray, size_t frame_stride, int str
   XFB_CUDA_OK(c, launch_prep(c, d_gray, frame_stride, stride));
   static const int order1[] = {L_B1_0, L_B1_1, L_B1_2, L_B1_3, L_B2_0, L_B2_1, L_B3_0, L_B3_1, L_B3_2,
                                L_B4_0, L_B4_1, L_B4_2, L_B5_0, L_B5_1, L_B5_2, L_B5_3};
-  auto conv = [&](int L) { return (conv_tc_handles(L) && !c->force_simt) ? launch_conv_tc_layer(c, L) : launch_conv_layer(c, L); };
+  auto conv = [&](int L) {
+    if (c->force_simt) return launch_conv_layer(c, L);                 // generic FP32 SIMT kernels (A/B reference)
+    if (conv_tc_handles(L)) return launch_conv_tc_layer(c, L);         // tcgen05 implicit GEMM (Cin >= 24)
+    if (conv_small_handles(L)) return launch_conv_small_layer(c, L);   // block1: bandwidth-shaped SIMT
+    return launch_conv_layer(c, L);
+  };
   for (int L : order1) XFB_CUDA_OK(c, conv(L));
   XFB_CUDA_OK(c, launch_pyramid(c));
   static const int order2[] = {L_F_0, L_F_1, L_F_2, L_HM_0, L_HM_1};
@@ -312,7 +318,8 @@ static int run_dense(Ctx* c, const uint8_t* d_gray, size_t frame_stride, int str
   XFB_CUDA_OK(c, launch_heatmap_out(c));
   static const int order3[] = {L_KP_0, L_KP_1, L_KP_2};
   for (int L : order3) XFB_CUDA_OK(c, conv(L));
-  XFB_CUDA_OK(c, launch_keypoint_out(c));
+  if (c->force_simt) XFB_CUDA_OK(c, launch_keypoint_out(c));
+  else XFB_CUDA_OK(c, launch_conv_tc_layer(c, L_KP_3));
   return XFB_OK;
 }
 

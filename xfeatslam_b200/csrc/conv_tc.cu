@@ -31,7 +31,7 @@
 namespace xfb {
 
 enum TcInMode { TIN_PLAIN = 0, TIN_BN = 1, TIN_BN_SKIP = 2, TIN_UNFOLD = 3 };
-enum TcOutMode { TOUT_STATS = 0, TOUT_BIAS = 1 };
+enum TcOutMode { TOUT_STATS = 0, TOUT_BIAS = 1, TOUT_KPSOFTMAX = 2 };
 
 template <int CIN_, int COUT_, int KS_, int S_, int CSTAGE_>
 struct TcCfg {
@@ -233,7 +233,37 @@ __global__ void __launch_bounds__(CTC_THREADS, 1) conv_tc_kernel(const ConvTcArg
     }
   }
 
-  if (warp < 8) {
+  if (OUTMODE == TOUT_KPSOFTMAX) {
+    // ===== keypoint_head.3 epilogue: + bias, softmax over the 65 logits, drop the dustbin, 8x8 fold =====
+    // (src/XFeat.cc:85-90, XFextractor::getKptsHeatmap src/XFextractor.cc:204-217); one thread per cell
+    if (warp < 4) {
+      mbar_wait(bar_acc, 0);
+      tc_fence_after();
+      const int p = warp * 32 + lane;
+      float v[96];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + 0u, v);
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + 32u, v + 32);
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + 64u, v + 64);
+      float mx = -3.4e38f;
+#pragma unroll
+      for (int c = 0; c < 65; ++c) { v[c] += a.bias[c]; mx = fmaxf(mx, v[c]); }
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 65; ++c) { v[c] = expf(v[c] - mx); sum += v[c]; }
+      const int Y = oy0 + (p >> 3), X = ox0 + (p & 7);
+      if (Y < a.Hout && X < a.Wout) {
+        float* dst = a.out + (size_t)b * (a.Hout * 8) * a.full_w + (size_t)(Y * 8) * a.full_w + X * 8;
+#pragma unroll
+        for (int ry = 0; ry < 8; ++ry) {
+          const float4 lo4 = make_float4(v[ry * 8 + 0] / sum, v[ry * 8 + 1] / sum, v[ry * 8 + 2] / sum, v[ry * 8 + 3] / sum);
+          const float4 hi4 = make_float4(v[ry * 8 + 4] / sum, v[ry * 8 + 5] / sum, v[ry * 8 + 6] / sum, v[ry * 8 + 7] / sum);
+          *reinterpret_cast<float4*>(dst + (size_t)ry * a.full_w) = lo4;
+          *reinterpret_cast<float4*>(dst + (size_t)ry * a.full_w + 4) = hi4;
+        }
+      }
+      tc_fence_before();
+    }
+  } else if (warp < 8) {
     // ===== epilogue: TMEM -> registers -> smem staging -> coalesced NHWC store + channel statistics =====
     mbar_wait(bar_acc, 0);
     tc_fence_after();
@@ -351,6 +381,7 @@ using TcB40 = TcCfg<64, 64, 3, 2, 16>;      // block4.0                         
 using TcB50 = TcCfg<64, 128, 3, 2, 32>;     // block5.0                           -> 15x20
 using TcB5x = TcCfg<128, 128, 3, 1, 64>;    // block5.1/.2
 using TcB53 = TcCfg<128, 64, 1, 1, 128>;    // block5.3
+using TcKP3 = TcCfg<64, 80, 1, 1, 64>;      // keypoint_head.3 (65 outputs, N padded to 80) + softmax / fold epilogue
 
 struct TcLayerInfo { int cstage, np; };
 static TcLayerInfo tc_info(int L) {
@@ -361,6 +392,7 @@ static TcLayerInfo tc_info(int L) {
     case L_B5_0: return {TcB50::CSTAGE, TcB50::NP};
     case L_B5_1: case L_B5_2: return {TcB5x::CSTAGE, TcB5x::NP};
     case L_B5_3: return {TcB53::CSTAGE, TcB53::NP};
+    case L_KP_3: return {TcKP3::CSTAGE, TcKP3::NP};
     case L_B3_1: case L_B4_1: case L_B4_2: case L_F_0: case L_F_1: return {TcC33::CSTAGE, TcC33::NP};
     default: return {TcC11::CSTAGE, TcC11::NP};
   }
@@ -398,6 +430,7 @@ bool conv_tc_handles(int L) {
   switch (L) {
     case L_B2_0: case L_B2_1: case L_B3_0: case L_B3_1: case L_B3_2: case L_B4_0: case L_B4_1: case L_B4_2: case L_B5_0: case L_B5_1:
     case L_B5_2: case L_B5_3: case L_F_0: case L_F_1: case L_F_2: case L_HM_0: case L_HM_1: case L_KP_0: case L_KP_1: case L_KP_2:
+    case L_KP_3:
       return true;
     default:
       return false;
@@ -464,6 +497,7 @@ cudaError_t launch_conv_tc_layer(Ctx* c, int L) {
     case L_KP_0: a.in = c->xn; a.Hin = c->H >> 3; a.Win = c->W >> 3; return run_tc<TcC11, TIN_UNFOLD, TOUT_STATS>(c, a, L);
     case L_KP_1: from(L_KP_0); return run_tc<TcC11, TIN_BN, TOUT_STATS>(c, a, L);
     case L_KP_2: from(L_KP_1); return run_tc<TcC11, TIN_BN, TOUT_STATS>(c, a, L);
+    case L_KP_3: from(L_KP_2); a.out = c->k1h; return run_tc<TcKP3, TIN_BN, TOUT_KPSOFTMAX>(c, a, L);   // -> K1h [B, H, W]
     default: return cudaErrorInvalidValue;
   }
 }

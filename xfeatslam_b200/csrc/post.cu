@@ -46,7 +46,7 @@ __device__ __forceinline__ float bilinear1(const float* map, int mh, int mw, flo
   return bilerp4(nw, ne, sw, se, __fmul_rn(s, e), __fmul_rn(s, w), __fmul_rn(n, e), __fmul_rn(n, w));
 }
 
-constexpr int NMS_T = 32;
+constexpr int NMS_T = 16;   // 16 x 16 pixel tiles: 256-thread CTAs, 8 per SM, hide the tile-load latency
 __global__ void __launch_bounds__(NMS_T * NMS_T) nms_score_kernel(const float* k1h, const float* h1, int H, int W, float thr,
                                                                   u64* cand, int* cand_count) {
   __shared__ float tile[NMS_T + 4][NMS_T + 4];
@@ -61,28 +61,39 @@ __global__ void __launch_bounds__(NMS_T * NMS_T) nms_score_kernel(const float* k
   }
   __syncthreads();
   const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-  if (x >= W || y >= H) return;
-  const float v = tile[threadIdx.y + 2][threadIdx.x + 2];
-  if (!(v > thr)) return;
-  float m = v;
+  u64 key = 0;   // 0 = not a candidate (a real key has score bits > 0)
+  if (x < W && y < H) {
+    const float v = tile[threadIdx.y + 2][threadIdx.x + 2];
+    if (v > thr) {
+      float m = v;
 #pragma unroll
-  for (int dy = 0; dy < 5; ++dy)
+      for (int dy = 0; dy < 5; ++dy)
 #pragma unroll
-    for (int dx = 0; dx < 5; ++dx) m = fmaxf(m, tile[threadIdx.y + dy][threadIdx.x + dx]);
-  if (v != m) return;
-  if (x == 0 && y == 0) return;  // masked to -1 by the reference, never valid
-  // nearest(K1h)(kp): grid_sample nearest at full resolution (drops the last row / column)
-  const float nx = nearbyintf(grid_src(x, W, W)), ny = nearbyintf(grid_src(y, H, H));
-  float sn = 0.f;
-  if (nx >= 0.f && nx < (float)W && ny >= 0.f && ny < (float)H) sn = img[(size_t)(int)ny * W + (int)nx];
-  const int mh = H >> 3, mw = W >> 3;
-  const float sb = bilinear1(h1 + (size_t)b * mh * mw, mh, mw, grid_src(x, W, mw), grid_src(y, H, mh));
-  const float score = __fmul_rn(sn, sb);
-  if (!(score > 0.f)) return;  // `valid = scores > 0`, src/XFextractor.cc:313
-  const unsigned int lin = (unsigned int)(y * W + x);
-  const u64 key = ((u64)__float_as_uint(score) << 32) | (u64)(0xFFFFFFFFu - lin);
-  const int pos = atomicAdd(cand_count + b, 1);
-  cand[(size_t)b * H * W + pos] = key;
+        for (int dx = 0; dx < 5; ++dx) m = fmaxf(m, tile[threadIdx.y + dy][threadIdx.x + dx]);
+      if (v == m && !(x == 0 && y == 0)) {   // (0,0) is masked to -1 by the reference, never valid
+        // nearest(K1h)(kp): grid_sample nearest at full resolution (drops the last row / column)
+        const float nx = nearbyintf(grid_src(x, W, W)), ny = nearbyintf(grid_src(y, H, H));
+        float sn = 0.f;
+        if (nx >= 0.f && nx < (float)W && ny >= 0.f && ny < (float)H) sn = img[(size_t)(int)ny * W + (int)nx];
+        const int mh = H >> 3, mw = W >> 3;
+        const float sb = bilinear1(h1 + (size_t)b * mh * mw, mh, mw, grid_src(x, W, mw), grid_src(y, H, mh));
+        const float score = __fmul_rn(sn, sb);
+        if (score > 0.f) {                   // `valid = scores > 0`, src/XFextractor.cc:313
+          const unsigned int lin = (unsigned int)(y * W + x);
+          key = ((u64)__float_as_uint(score) << 32) | (u64)(0xFFFFFFFFu - lin);
+        }
+      }
+    }
+  }
+  // warp-aggregated append: one atomic per warp instead of one per candidate (order is irrelevant: the key sorts)
+  const unsigned int ballot = __ballot_sync(0xffffffffu, key != 0);
+  if (ballot) {
+    const int lane = tid & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(cand_count + b, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (key != 0) cand[(size_t)b * H * W + base + __popc(ballot & ((1u << lane) - 1u))] = key;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

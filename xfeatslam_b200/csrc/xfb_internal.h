@@ -204,6 +204,9 @@ cudaError_t launch_match_tc(Ctx* c, const MatchTcArgs& a, int row_tiles, int n_p
 cudaError_t launch_matrix_tc(Ctx* c, const MatchTcArgs& a, int row_tiles);
 size_t conv_part_elems(int H, int W);
 size_t conv_tc_part_elems(int H, int W);
+size_t conv_small_part_elems(int H, int W);
+bool conv_small_handles(int layer);
+cudaError_t launch_conv_small_layer(Ctx* c, int layer);
 bool conv_tc_handles(int layer);
 void conv_tc_pack_weights(int layer, const float* oihw, int cout, int cin, int ks, std::vector<float>& img);
 cudaError_t launch_conv_tc_layer(Ctx* c, int layer);  // partial-sum scratch (doubles) needed per frame
