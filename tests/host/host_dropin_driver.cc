@@ -67,8 +67,8 @@ int main(int argc, char** argv) {
     for (int i = 0; i < nA; ++i) { ka[i] = cv::KeyPoint(kA[2 * i], kA[2 * i + 1], 1, -1, 1.f); prev[i] = ka[i].pt; }
     for (int i = 0; i < nB; ++i) kb[i] = cv::KeyPoint(kB[2 * i], kB[2 * i + 1], 1, -1, 1.f);
     ORB_SLAM3::XFextractor ex(64, 1.2f, 8, 20, 7);   // only to own a context
-    cv::Mat tiny(32, 32, CV_8UC1);
-    std::memset(tiny.data, 7, 32 * 32);
+    cv::Mat tiny(32, 64, CV_8UC1);
+    std::memset(tiny.data, 7, 32 * 64);
     std::vector<cv::KeyPoint> tk; cv::Mat td; std::vector<int> lap = {0, 0};
     ex(tiny, cv::Mat(), tk, td, lap);
     ORB_SLAM3::XFBmatcher m(ex.context(), ratio, true);

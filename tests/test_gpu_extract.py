@@ -157,9 +157,14 @@ def test_edge_cases(xfb_small):
     flat = np.full((64, 96), 77, np.uint8)
     o = xfb_small.extract(flat, 64)
     assert 0 <= int(o["n_valid"]) <= 64
-    # smallest legal frame
-    o = xfb_small.extract(synthetic_frame(5, 32, 32), 16)
+    # smallest legal frame: two pixels at 1/32 resolution (with one, the reference's train-mode BatchNorm throws
+    # "Expected more than 1 value per channel when training" -- mirrored as an error code)
+    o = xfb_small.extract(synthetic_frame(5, 32, 64), 16)
     assert 0 <= int(o["n_valid"]) <= 16
+    with pytest.raises(XFBError):
+        xfb_small.extract(synthetic_frame(5, 32, 32), 16)
+    with pytest.raises(XFBError):
+        xfb_small.extract(synthetic_frame(5, 40, 50), 16)
     # topk larger than the number of candidates -> padded with zeros
     o = xfb_small.extract(synthetic_frame(6, 64, 64), 1024)
     n = int(o["n_valid"])
@@ -226,3 +231,48 @@ def test_pipelined_submit_equals_synchronous_calls(xfb_vga):
             assert np.array_equal(wo[k], go[k]), k
         for a, b in zip(wm, gm):
             assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("shape", [(40, 70), (77, 131), (128, 160), (96, 160)])
+def test_odd_sizes_against_oracle(xfb_small, weights, shape):
+    """Sizes that are not multiples of 32 go through the bilinear pre-resize (src/XFextractor.cc:182-202);
+    keypoints stay in the resized frame (SURVEY finding 2)."""
+    H, W = shape
+    frame = synthetic_frame(31 + H, H, W)
+    kp, sc, ds = xo.detect_and_compute(frame, weights, 512)
+    out = xfb_small.extract(frame, 512)
+    n, gi, oi = match_sets(out, kp)
+    assert abs(n - len(kp)) <= max(2, len(kp) // 50)
+    assert len(gi) >= 0.95 * len(kp)
+    if len(gi):
+        np.testing.assert_allclose(out["scores"][gi], sc[oi], atol=SCORE_TOL, rtol=0)
+        np.testing.assert_allclose(out["desc"][gi], ds[oi], atol=DESC_TOL, rtol=0)
+        assert out["kpts"][:n, 0].max() < (W // 32) * 32 and out["kpts"][:n, 1].max() < (H // 32) * 32
+
+
+def test_topk_8192_returns_every_candidate():
+    from xfeatslam_b200.capi import XFeatB200
+    ctx = XFeatB200(max_h=480, max_w=640, max_batch=1, max_topk=8192)
+    f = synthetic_frame(91)
+    out = ctx.extract(f, 8192)
+    n = int(out["n_valid"])
+    assert n == ctx.candidates(0) and 4096 < n < 8192          # ~7000 NMS survivors with score > 0 at VGA
+    s = out["scores"][:n]
+    assert np.all(s[:-1] >= s[1:]) and s[-1] > 0
+    assert len({(int(x), int(y)) for x, y in out["kpts"][:n]}) == n
+    top = ctx.extract(f, 1000)
+    assert np.array_equal(top["kpts"], out["kpts"][:1000]) and np.array_equal(top["desc"], out["desc"][:1000])   # top-k is a prefix
+    ctx.close()
+
+
+def test_hd720_batch_equals_singles():
+    from xfeatslam_b200.capi import XFeatB200
+    ctx = XFeatB200(max_h=720, max_w=1280, max_batch=2, max_topk=2000)
+    frames = synthetic_frames(120, 2, 720, 1280)
+    ob = ctx.extract(frames, 2000)
+    for i in range(2):
+        o1 = ctx.extract(frames[i], 2000)
+        for k in ("kpts", "scores", "desc"):
+            assert np.array_equal(ob[k][i], o1[k])
+        assert o1["kpts"][:, 1].max() < 704                     # 720 -> 704 rows internally, never rescaled
+    ctx.close()

@@ -330,6 +330,12 @@ static int check_extract_args(Ctx* c, int batch, int h, int w, int stride, int t
     c->err = "extract: size/batch/topk outside the limits given to xfb_create (image must be >= 32x32)";
     return XFB_ERR_ARG;
   }
+  if ((h / 32) * (w / 32) < 2) {
+    // block5 would normalise ONE value per channel: libtorch's train-mode batch_norm throws here
+    // ("Expected more than 1 value per channel when training"), i.e. the reference cannot process such frames
+    c->err = "extract: image too small -- the 1/32-resolution map has a single pixel (the reference's train-mode BatchNorm throws)";
+    return XFB_ERR_ARG;
+  }
   return XFB_OK;
 }
 
@@ -409,9 +415,12 @@ void xfb_destroy(xfb_ctx* c) {
     if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
     if (s.ev_comp) cudaEventDestroy(s.ev_comp);
     if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
+    if (s.ev_ext) cudaEventDestroy(s.ev_ext);
   }
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
   if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+  if (c->s_match) cudaStreamDestroy(c->s_match);
+  if (c->ev_match_free) cudaEventDestroy(c->ev_match_free);
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -581,6 +590,7 @@ static int slot_ensure(xfb_ctx* c, Ctx::Slot& s, int n_pairs) {
     XFB_CUDA_OK(c, cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
     XFB_CUDA_OK(c, cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming));
     XFB_CUDA_OK(c, cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming));
+    XFB_CUDA_OK(c, cudaEventCreateWithFlags(&s.ev_ext, cudaEventDisableTiming));
   }
   if (n_pairs > s.m_cap) {
     for (int i = 0; i < 5; ++i) { if (s.m[i]) cudaFree(s.m[i]); s.m[i] = nullptr; }
@@ -589,6 +599,11 @@ static int slot_ensure(xfb_ctx* c, Ctx::Slot& s, int n_pairs) {
   }
   if (!c->s_h2d) XFB_CUDA_OK(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
   if (!c->s_d2h) XFB_CUDA_OK(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+  if (!c->s_match) {
+    XFB_CUDA_OK(c, cudaStreamCreateWithFlags(&c->s_match, cudaStreamNonBlocking));
+    XFB_CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_match_free, cudaEventDisableTiming));
+    XFB_CUDA_OK(c, cudaEventRecord(c->ev_match_free, c->s_match));
+  }
   return XFB_OK;
 }
 
@@ -628,11 +643,23 @@ int xfb_submit(xfb_ctx* c, int slot, const uint8_t* gray, int batch, size_t fram
   if (r != XFB_OK) return r;
   int32_t* host_m[5] = {bi, bd, sd, ri, rd};
   if (n_pairs) {
+    // the matches of this batch run on their own stream, so that the (latency-bound, low-occupancy) conv
+    // kernels of the NEXT batch can share the SMs with the (1 CTA / SM) matcher kernels of this one
+    XFB_CUDA_OK(c, cudaEventRecord(s.ev_ext, c->stream));
+    XFB_CUDA_OK(c, cudaStreamWaitEvent(c->s_match, s.ev_ext, 0));
+    XFB_CUDA_OK(c, cudaStreamWaitEvent(c->s_match, c->ev_match_free, 0));   // previous batch's matcher is done with the shared images
     int32_t* d[5];
     for (int i = 0; i < 5; ++i) d[i] = host_m[i] ? s.m[i] : nullptr;
-    if ((r = tc_match_frames(c, pairs, n_pairs, init_dist, d)) != XFB_OK) return r;
+    cudaStream_t keep = c->stream;
+    c->stream = c->s_match;
+    r = tc_match_frames(c, pairs, n_pairs, init_dist, d);
+    c->stream = keep;
+    if (r != XFB_OK) return r;
+    XFB_CUDA_OK(c, cudaEventRecord(s.ev_comp, c->s_match));
+    XFB_CUDA_OK(c, cudaEventRecord(c->ev_match_free, c->s_match));
+  } else {
+    XFB_CUDA_OK(c, cudaEventRecord(s.ev_comp, c->stream));
   }
-  XFB_CUDA_OK(c, cudaEventRecord(s.ev_comp, c->stream));
   // copy-out stream
   XFB_CUDA_OK(c, cudaStreamWaitEvent(c->s_d2h, s.ev_comp, 0));
   const size_t K = topk;

@@ -110,10 +110,11 @@ struct Ctx {
     int32_t* nvalid = nullptr; float* xy = nullptr; float* score = nullptr; float* desc = nullptr;
     int32_t* m[5] = {};
     int m_cap = 0;                 // pairs the match buffers hold
-    cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_d2h = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_d2h = nullptr, ev_ext = nullptr;
     bool pending = false;
   } slots[2];
-  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_match = nullptr;
+  cudaEvent_t ev_match_free = nullptr;
 
   // last extract geometry for xfb_match_frames
   int last_topk = 0;
