@@ -194,10 +194,17 @@ __global__ void __launch_bounds__(CTC_THREADS, 1) conv_tc_kernel(const ConvTcArg
       }
     }
   } else {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp runs the (warp-uniform) loop and ONE elected lane issues, so that every tcgen05
+    // instruction compiles to a single UTCHMMA / UTCBAR; descriptors are a constant plus 16-byte-unit offsets =====
+    {
       constexpr uint32_t IDESC = umma_idesc_tf32(128, C::NP);
-      const uint32_t a_hi = smem_u32(sInHi), a_lo = smem_u32(sInLo);
+      const uint64_t da_hi0 = umma_desc_kmajor(smem_u32(sInHi), C::LBO_A, C::SBO_A);
+      const uint64_t da_lo0 = umma_desc_kmajor(smem_u32(sInLo), C::LBO_A, C::SBO_A);
+      const uint64_t db0 = umma_desc_kmajor(smem_u32(sW), C::LBO_B, C::SBO_B);
+      constexpr uint64_t KA = (2u * C::LBO_A) >> 4, KB = (2u * C::LBO_B) >> 4;      // one K = 8 step (two 16-byte chunks)
+      constexpr uint64_t W_LO = ((uint64_t)C::CSTAGE * C::NP * 4) >> 4;              // lo image behind the hi image
+      constexpr uint64_t W_STAGE = ((uint64_t)C::W_UNIT_FLOATS * 4) >> 4;
+      const bool leader = elect_one_sync();
       int u = 0;
       for (int ph = 0; ph < NPHASE; ++ph) {
         mbar_wait(bar_in, ph & 1);
@@ -214,22 +221,24 @@ __global__ void __launch_bounds__(CTC_THREADS, 1) conv_tc_kernel(const ConvTcArg
             const int py = (ky == 1) ? 0 : 1, dy = (ky == 0) ? 0 : 1, px = (kx == 1) ? 0 : 1, dx = (kx == 0) ? 0 : 1;
             tap_off = (uint32_t)((py * 2 + px) * C::SUB_FLOATS) * 4u + (uint32_t)(dy * WT + dx) * 16u;
           }
-          const uint32_t w_hi = smem_u32(sW + (size_t)s * C::W_UNIT_FLOATS), w_lo = w_hi + C::CSTAGE * C::NP * 4;
-#pragma unroll 4
-          for (int k8 = 0; k8 < C::CSTAGE / 8; ++k8) {
-            const uint64_t dah = umma_desc_kmajor(a_hi + tap_off + (uint32_t)k8 * 2u * C::LBO_A, C::LBO_A, C::SBO_A);
-            const uint64_t dal = umma_desc_kmajor(a_lo + tap_off + (uint32_t)k8 * 2u * C::LBO_A, C::LBO_A, C::SBO_A);
-            const uint64_t dbh = umma_desc_kmajor(w_hi + (uint32_t)k8 * 2u * C::LBO_B, C::LBO_B, C::SBO_B);
-            const uint64_t dbl = umma_desc_kmajor(w_lo + (uint32_t)k8 * 2u * C::LBO_B, C::LBO_B, C::SBO_B);
-            umma_tf32(tmem_base, dah, dbh, IDESC, (u > 0 || k8 > 0) ? 1u : 0u);
-            umma_tf32(tmem_base, dah, dbl, IDESC, 1u);
-            umma_tf32(tmem_base, dal, dbh, IDESC, 1u);
+          if (leader) {
+            const uint64_t dah0 = da_hi0 + (tap_off >> 4), dal0 = da_lo0 + (tap_off >> 4);
+            const uint64_t dbh0 = db0 + (uint64_t)s * W_STAGE, dbl0 = dbh0 + W_LO;
+#pragma unroll
+            for (int k8 = 0; k8 < C::CSTAGE / 8; ++k8) {
+              umma_tf32(tmem_base, dah0 + k8 * KA, dbh0 + k8 * KB, IDESC, (u > 0 || k8 > 0) ? 1u : 0u);
+              umma_tf32(tmem_base, dah0 + k8 * KA, dbl0 + k8 * KB, IDESC, 1u);
+              umma_tf32(tmem_base, dal0 + k8 * KA, dbh0 + k8 * KB, IDESC, 1u);
+            }
+            umma_commit(bar_wempty + s);
           }
-          umma_commit(bar_wempty + s);
+          __syncwarp();
         }
-        umma_commit(bar_free);            // staged tile may be overwritten by the next channel phase
+        if (leader) umma_commit(bar_free);            // staged tile may be overwritten by the next channel phase
+        __syncwarp();
       }
-      umma_commit(bar_acc);
+      if (leader) umma_commit(bar_acc);
+      __syncwarp();
     }
   }
 

@@ -17,8 +17,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done = 0;
+  uint32_t done = 0, spins = 0;
   while (!done) {
+    if (++spins == (1u << 26)) __trap();   // a protocol bug becomes a launch failure instead of a hung GPU
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -54,6 +55,19 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// one lane of a converged warp (the same lane on every call); tcgen05.mma / commit issued under this predicate compile to
+// single instructions, whereas under `if (lane == 0)` the compiler wraps each of them in a serialisation loop
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 // generic-proxy shared-memory writes -> visible to the async proxy (tensor core / bulk copies)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

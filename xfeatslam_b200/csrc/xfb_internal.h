@@ -150,6 +150,14 @@ struct Ctx {
   float* tc_fnmax = nullptr;      // [max_batch] same per frame
   float* tc_bound = nullptr;      // [64 pairs][rows] bound-pass output
   int tc_bound_rows = 0;
+  // streaming matcher (match_stream.cu): fp16 operand images, 20 KB per 128-row block
+  int match_impl = 2;             // 0 = match_tc.cu (bound + 3-piece filter), 1 / 2 = match_stream.cu with 128 / 256 rows per CTA
+  void* ms_img[2] = {};           // generic A / B sets
+  int ms_cap = 0;                 // rows (multiple of 256) the generic images hold
+  void* ms_fimg = nullptr;        // per-frame images of the last extract
+  int ms_frows = 0;
+  unsigned long long* ms_counters = nullptr;   // debug (XFB_MS_DEBUG): device counters, see MatchTcArgs
+  int ms_mode = 0;
 };
 
 // error helpers -------------------------------------------------------------------------------
@@ -182,6 +190,8 @@ struct MatchTcArgs {
   float* dbg_maxerr;                      // MATRIX mode + debug: max |t - 512*float(S)|
   float* bound;                           // [pair][rows_padded_A] upper bound of each row's second-best (bound pass), or nullptr
   const float* nrm_max_B;                 // [set] largest |b|^2 of each B set (bf16 error scale)
+  unsigned long long* ms_counters;        // debug: [0] queue pushes, [1] verified survivors, [2] queue overflows (or nullptr)
+  int ms_mode;                            // debug timing experiments (bit flags): 1 no candidate path, 2 no epilogue arithmetic, 4 no MMAs, 8 no tcgen05.ld, 16 no bulk copies
 };
 
 // profiling tags: 0..L_NUM-1 = layers, then the stages below
@@ -203,6 +213,10 @@ cudaError_t launch_match_prep(Ctx* c, const float* desc, size_t set_stride, int 
 cudaError_t launch_match_bound(Ctx* c, const MatchTcArgs& a, int row_tiles, int n_pairs);
 cudaError_t launch_match_tc(Ctx* c, const MatchTcArgs& a, int row_tiles, int n_pairs, bool grouped);
 cudaError_t launch_matrix_tc(Ctx* c, const MatchTcArgs& a, int row_tiles);
+size_t ms_image_bytes(int rows_padded);
+cudaError_t launch_ms_prep(Ctx* c, const float* desc, size_t set_stride, int n_sets, const int32_t* n_dev, int n_host, int rows_padded,
+                           void* img, size_t img_set_bytes, float* nrm, float* nrm_max);
+cudaError_t launch_match_stream(Ctx* c, const MatchTcArgs& a, int n_pairs, bool grouped, int rb);   // a.img_stride_* in BYTES
 size_t conv_part_elems(int H, int W);
 size_t conv_tc_part_elems(int H, int W);
 size_t conv_small_part_elems(int H, int W);
