@@ -80,6 +80,18 @@ int xfb_extract_batch_device(xfb_ctx* ctx, const uint8_t* d_gray, int batch, siz
 int xfb_distance_matrix(xfb_ctx* ctx, const float* A, int n1, const float* B, int n2, int32_t* out);
 int xfb_distance_matrix_device(xfb_ctx* ctx, const float* d_A, int n1, const float* d_B, int n2, int32_t* d_out);
 
+/* The same distance for an explicit list of pairs: out[p] = DescriptorDistance(A[idx_a[p]], B[idx_b[p]]).  This serves the
+ * DescriptorDistance call sites whose candidate set is not "all pairs": the vocabulary-node gated scans of SearchByBoW
+ * (src/ORBmatcher.cc:468,:489,:1019) and SearchForTriangulation (:1200), the projected-window searches (:100,:174,:699,:812,
+ * :1487,:1612,:1745,:1825,:1946,:2012,:2142), Frame.cc:1079 and MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:377).
+ * The caller lists the pairs in the reference's visiting order and replays the accept / reject logic over `out`
+ * (xfeatslam_b200/host/XFBmatcher.cc).  Indices out of range -> XFB_ERR_ARG.  Bit-exact w.r.t. oracle/matcher_oracle.c. */
+int xfb_distance_pairs(xfb_ctx* ctx, const float* A, int n1, const float* B, int n2, const int32_t* idx_a, const int32_t* idx_b, int n_pairs,
+                       int32_t* out);
+/* Device pointers, asynchronous on the ctx stream (out-of-range pairs produce -1). */
+int xfb_distance_pairs_device(xfb_ctx* ctx, const float* d_A, int n1, const float* d_B, int n2, const int32_t* d_idx_a, const int32_t* d_idx_b,
+                              int n_pairs, int32_t* d_out);
+
 /* Brute-force nearest / second-nearest search with the reference's update rule
  * (src/ORBmatcher.cc:476-486, :884-894; lowest index wins ties), fused with the distance.
  *   group_a/group_b : nullable; when given only pairs with equal ids compete (the vocabulary-node

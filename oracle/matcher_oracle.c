@@ -165,3 +165,262 @@ int mo_search_for_initialization(const float* D1, const float* k1xy, int n1, con
   grid_free(&g);
   return nmatches;
 }
+
+/* ---- DBoW2::FeatureVector (thirdparty/DBoW2/DBoW2/FeatureVector.h: std::map<NodeId, std::vector<unsigned int>>) ----
+ * node[i] = vocabulary node of feature i at `levelsup` (Frame::ComputeBoW, src/Frame.cc:931-938: levelsup = 4), or -1 when
+ * the feature's word has zero weight and is therefore absent (TemplatedVocabulary::transform, TemplatedVocabulary.h:1183-1190:
+ * `if(w > 0) { v.addWeight(id, w); fv.addFeature(nid, i_feature); }`).  Features of a node are stored in ascending feature
+ * index (addFeature appends, i_feature ascends).  The matchers walk two maps in ascending NodeId and only act on equal keys
+ * (src/ORBmatcher.cc:429-436, :579-586): a merge join. */
+typedef struct { int n_nodes; int* node_id; int* start; int* feat; } mo_featvec;
+
+static int cmp_int(const void* a, const void* b) { int x = *(const int*)a, y = *(const int*)b; return (x > y) - (x < y); }
+
+static void featvec_build(mo_featvec* fv, const int32_t* node, int n) {
+  int* ids = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  int m = 0;
+  for (int i = 0; i < n; ++i) if (node[i] >= 0) ids[m++] = node[i];
+  qsort(ids, (size_t)m, sizeof(int), cmp_int);
+  int u = 0;
+  for (int i = 0; i < m; ++i) if (i == 0 || ids[i] != ids[i - 1]) ids[u++] = ids[i];
+  fv->n_nodes = u; fv->node_id = ids;
+  fv->start = (int*)calloc((size_t)u + 1, sizeof(int));
+  fv->feat = (int*)malloc(sizeof(int) * (size_t)(m > 0 ? m : 1));
+  for (int i = 0; i < n; ++i) {
+    if (node[i] < 0) continue;
+    int* p = (int*)bsearch(&node[i], ids, (size_t)u, sizeof(int), cmp_int);
+    fv->start[(p - ids) + 1]++;
+  }
+  for (int k = 0; k < u; ++k) fv->start[k + 1] += fv->start[k];
+  int* fill = (int*)calloc((size_t)(u > 0 ? u : 1), sizeof(int));
+  for (int i = 0; i < n; ++i) {   /* ascending feature index inside a node */
+    if (node[i] < 0) continue;
+    int k = (int)((int*)bsearch(&node[i], ids, (size_t)u, sizeof(int), cmp_int) - ids);
+    fv->feat[fv->start[k] + fill[k]++] = i;
+  }
+  free(fill);
+}
+static void featvec_free(mo_featvec* fv) { free(fv->node_id); free(fv->start); free(fv->feat); }
+
+/* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&), src/ORBmatcher.cc:408-610, F.Nleft == -1 branch.
+ *   good_kf[i]   : vpMapPointsKF[i] != NULL && !isBad()   (:440-446)
+ *   matches_f[j] : out, index of the KF feature whose MapPoint frame feature j received (vpMapPointMatches[j] = pMP), -1 = NULL
+ * th_low = TH_LOW, ratio = mfNNratio (0.7 Tracking.cc:2754, 0.75 :3676).  XFeat keypoints all have angle -1, so every match
+ * lands in rotation bin 0 and ComputeThreeMaxima removes nothing (:589-607). */
+int mo_search_by_bow_kf_f(const float* Dkf, const int32_t* node_kf, const uint8_t* good_kf, int n_kf, const float* Df, const int32_t* node_f, int n_f,
+                          float ratio, int th_low, int32_t* matches_f) {
+  mo_featvec a, b;
+  featvec_build(&a, node_kf, n_kf);
+  featvec_build(&b, node_f, n_f);
+  for (int j = 0; j < n_f; ++j) matches_f[j] = -1;
+  int nmatches = 0, ia = 0, ib = 0;
+  while (ia < a.n_nodes && ib < b.n_nodes) {
+    if (a.node_id[ia] == b.node_id[ib]) {
+      for (int p = a.start[ia]; p < a.start[ia + 1]; ++p) {
+        const int realIdxKF = a.feat[p];
+        if (!good_kf[realIdxKF]) continue;
+        int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+        for (int q = b.start[ib]; q < b.start[ib + 1]; ++q) {
+          const int realIdxF = b.feat[q];
+          if (matches_f[realIdxF] >= 0) continue;   /* :463 already claimed */
+          const int dist = mo_descriptor_distance(Dkf + (size_t)realIdxKF * XF_DIM, Df + (size_t)realIdxF * XF_DIM);
+          if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = realIdxF; }
+          else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist1 <= th_low) {
+          if ((float)bestDist1 < ratio * (float)bestDist2) { matches_f[bestIdxF] = realIdxKF; nmatches++; }
+        }
+      }
+      ia++; ib++;
+    } else if (a.node_id[ia] < b.node_id[ib]) ia++;   /* lower_bound(Fit->first): first key >= ; stepping is equivalent in a merge */
+    else ib++;
+  }
+  featvec_free(&a); featvec_free(&b);
+  return nmatches;
+}
+
+/* ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&), src/ORBmatcher.cc:950-1090 (NLeft == -1).
+ *   good1 / good2 : MapPoint present and not bad;  matches12[i1] : out, index of the KF2 feature (vpMatches12[idx1] = vpMapPoints2[bestIdx2])
+ * Accept rule: bestDist1 < TH_LOW (strict, :1033) and ratio (0.9 at LoopClosing.cc:591). */
+int mo_search_by_bow_kf_kf(const float* D1, const int32_t* node1, const uint8_t* good1, int n1, const float* D2, const int32_t* node2,
+                           const uint8_t* good2, int n2, float ratio, int th_low, int32_t* matches12) {
+  mo_featvec a, b;
+  featvec_build(&a, node1, n1);
+  featvec_build(&b, node2, n2);
+  uint8_t* matched2 = (uint8_t*)calloc((size_t)(n2 > 0 ? n2 : 1), 1);
+  for (int i = 0; i < n1; ++i) matches12[i] = -1;
+  int nmatches = 0, ia = 0, ib = 0;
+  while (ia < a.n_nodes && ib < b.n_nodes) {
+    if (a.node_id[ia] == b.node_id[ib]) {
+      for (int p = a.start[ia]; p < a.start[ia + 1]; ++p) {
+        const int idx1 = a.feat[p];
+        if (!good1[idx1]) continue;
+        int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+        for (int q = b.start[ib]; q < b.start[ib + 1]; ++q) {
+          const int idx2 = b.feat[q];
+          if (matched2[idx2] || !good2[idx2]) continue;
+          const int dist = mo_descriptor_distance(D1 + (size_t)idx1 * XF_DIM, D2 + (size_t)idx2 * XF_DIM);
+          if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+          else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist1 < th_low) {
+          if ((float)bestDist1 < ratio * (float)bestDist2) { matches12[idx1] = bestIdx2; matched2[bestIdx2] = 1; nmatches++; }
+        }
+      }
+      ia++; ib++;
+    } else if (a.node_id[ia] < b.node_id[ib]) ia++;
+    else ib++;
+  }
+  free(matched2);
+  featvec_free(&a); featvec_free(&b);
+  return nmatches;
+}
+
+/* ORBmatcher::SearchForTriangulation, src/ORBmatcher.cc:1092-1331, single pinhole camera (mpCamera2 == NULL, NLeft == -1).
+ *   hasmp1 / hasmp2 : GetMapPoint(idx) != NULL (such features are skipped, :1159, :1189)
+ *   stereo1 / stereo2 : mvuRight[idx] >= 0
+ *   k1xy / k2xy : mvKeysUn positions;  ep : epipole of camera 1 in image 2 (:1105);  F12 : row-major fundamental matrix the
+ *   reference builds inside Pinhole::epipolarConstrain (src/CameraModels/Pinhole.cpp:107-129: K1^-T [t12]x R12 K2^-1, Eigen
+ *   float arithmetic -- supplied by the caller, Eigen is not in this image);  unc = mvLevelSigma2[kp2.octave] (octave 0: 1.0),
+ *   scale0 = mvScaleFactors[0] = 1.
+ * vbMatched2 is never set by the reference, so one KF2 feature may be taken by several KF1 features. */
+int mo_search_for_triangulation(const float* D1, const int32_t* node1, const uint8_t* hasmp1, const uint8_t* stereo1, const float* k1xy, int n1,
+                                const float* D2, const int32_t* node2, const uint8_t* hasmp2, const uint8_t* stereo2, const float* k2xy, int n2,
+                                const float* F12, const float* ep, int only_stereo, int coarse, int th_low, float unc, float scale0,
+                                int32_t* matches12) {
+  mo_featvec a, b;
+  featvec_build(&a, node1, n1);
+  featvec_build(&b, node2, n2);
+  for (int i = 0; i < n1; ++i) matches12[i] = -1;
+  int nmatches = 0, ia = 0, ib = 0;
+  while (ia < a.n_nodes && ib < b.n_nodes) {
+    if (a.node_id[ia] == b.node_id[ib]) {
+      for (int p = a.start[ia]; p < a.start[ia + 1]; ++p) {
+        const int idx1 = a.feat[p];
+        if (hasmp1[idx1]) continue;
+        const int bStereo1 = stereo1[idx1];
+        if (only_stereo && !bStereo1) continue;
+        const float x1 = k1xy[2 * idx1], y1 = k1xy[2 * idx1 + 1];
+        int bestDist = th_low, bestIdx2 = -1;
+        for (int q = b.start[ib]; q < b.start[ib + 1]; ++q) {
+          const int idx2 = b.feat[q];
+          if (hasmp2[idx2]) continue;
+          const int bStereo2 = stereo2[idx2];
+          if (only_stereo && !bStereo2) continue;
+          const int dist = mo_descriptor_distance(D1 + (size_t)idx1 * XF_DIM, D2 + (size_t)idx2 * XF_DIM);
+          if (dist > th_low || dist > bestDist) continue;
+          const float x2 = k2xy[2 * idx2], y2 = k2xy[2 * idx2 + 1];
+          if (!bStereo1 && !bStereo2) {
+            const float distex = ep[0] - x2, distey = ep[1] - y2;
+            if (distex * distex + distey * distey < 100 * scale0) continue;
+          }
+          int ok = coarse;
+          if (!ok) {   /* Pinhole::epipolarConstrain, src/CameraModels/Pinhole.cpp:114-128 */
+            const float la = x1 * F12[0] + y1 * F12[3] + F12[6];
+            const float lb = x1 * F12[1] + y1 * F12[4] + F12[7];
+            const float lc = x1 * F12[2] + y1 * F12[5] + F12[8];
+            const float num = la * x2 + lb * y2 + lc;
+            const float den = la * la + lb * lb;
+            if (den == 0) ok = 0;
+            else { const float dsqr = num * num / den; ok = (double)dsqr < 3.84 * (double)unc; }
+          }
+          if (ok) { bestIdx2 = idx2; bestDist = dist; }
+        }
+        if (bestIdx2 >= 0) { matches12[idx1] = bestIdx2; nmatches++; }
+      }
+      ia++; ib++;
+    } else if (a.node_id[ia] < b.node_id[ib]) ia++;
+    else ib++;
+  }
+  featvec_free(&a); featvec_free(&b);
+  return nmatches;
+}
+
+/* Frame::GetFeaturesInArea with level limits (src/Frame.cc:850-916) for keypoints that are all at octave 0. */
+static int grid_area_levels(const mo_grid* g, const float* kxy, float x, float y, float r, int minLevel, int maxLevel, int* out) {
+  const int bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+  if (bCheckLevels && 0 < minLevel) return 0;               /* kpUn.octave (0) < minLevel */
+  (void)maxLevel;                                            /* octave 0 > maxLevel is impossible for maxLevel >= 0 */
+  return grid_area(g, kxy, x, y, r, out);
+}
+
+/* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints), src/ORBmatcher.cc:42-212,
+ * monocular / RGB-D frames (F.Nleft == -1), the TrackLocalMap search.
+ * Per map point m: in_view = mbTrackInView && !(bFarPoints && mTrackDepth > thFarPoints) && !isBad();  proj = (mTrackProjX,
+ * mTrackProjY);  projxr = mTrackProjXR;  level = mnTrackScaleLevel;  viewcos = mTrackViewCos;  mp_obs = Observations() > 0.
+ * Per frame feature: kxy = mvKeysUn, occupied = (F.mvpMapPoints[idx] && Observations() > 0), uright = mvuRight.
+ * assign[idx] (out) = index of the map point written to F.mvpMapPoints[idx], -1 = untouched. */
+int mo_search_by_projection(const float* Dmp, const uint8_t* in_view, const float* proj, const float* projxr, const int32_t* level,
+                            const float* viewcos, const uint8_t* mp_obs, int n_mp, const float* Df, const float* kxy, const uint8_t* occupied_in,
+                            const float* uright, int n_f, int img_w, int img_h, float th, float scale_factor, float ratio, int th_high,
+                            int32_t* assign) {
+  mo_grid g;
+  grid_build(&g, kxy, n_f, img_w, img_h);
+  int* cand = (int*)malloc(sizeof(int) * (size_t)(n_f > 0 ? n_f : 1));
+  uint8_t* occupied = (uint8_t*)malloc((size_t)(n_f > 0 ? n_f : 1));
+  for (int j = 0; j < n_f; ++j) { assign[j] = -1; occupied[j] = occupied_in[j]; }
+  const int bFactor = th != 1.0f;
+  int nmatches = 0;
+  for (int m = 0; m < n_mp; ++m) {
+    if (!in_view[m]) continue;
+    const int lvl = level[m];
+    float r = (viewcos[m] > 0.998f) ? 2.5f : 4.0f;          /* RadiusByViewingCos, :214-220 */
+    if (bFactor) r *= th;
+    float sf = 1.0f;                                         /* F.mvScaleFactors[lvl] = scaleFactor^lvl (XFextractor.cc:75-95) */
+    for (int l = 0; l < lvl; ++l) sf *= scale_factor;
+    const int nc = grid_area_levels(&g, kxy, proj[2 * m], proj[2 * m + 1], r * sf, lvl - 1, lvl, cand);
+    if (nc == 0) continue;
+    int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+    for (int c = 0; c < nc; ++c) {
+      const int idx = cand[c];
+      if (occupied[idx]) continue;
+      if (uright[idx] > 0) {
+        const float er = fabsf(projxr[m] - uright[idx]);
+        if (er > r * sf) continue;
+      }
+      const int dist = mo_descriptor_distance(Dmp + (size_t)m * XF_DIM, Df + (size_t)idx * XF_DIM);
+      if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = 0; bestIdx = idx; }
+      else if (dist < bestDist2) { bestLevel2 = 0; bestDist2 = dist; }
+    }
+    if (bestDist <= th_high) {
+      if (bestLevel == bestLevel2 && (float)bestDist > ratio * (float)bestDist2) continue;
+      if (bestLevel != bestLevel2 || (float)bestDist <= ratio * (float)bestDist2) {
+        assign[bestIdx] = m;
+        occupied[bestIdx] = mp_obs[m];
+        nmatches++;
+      }
+    }
+  }
+  free(cand); free(occupied);
+  grid_free(&g);
+  return nmatches;
+}
+
+/* MapPoint::ComputeDistinctiveDescriptors, src/MapPoint.cc:329-403, for `n_sets` map points at once: the observations of
+ * set s are the rows offsets[s] .. offsets[s+1]-1 of D.  best[s] = the row (relative to the set) with the least median
+ * distance to the others: Distances[i][i] = 0, median = sorted[0.5 * (N - 1)] (truncated), first minimum wins (:388-393). */
+void mo_distinctive_descriptors(const float* D, const int32_t* offsets, int n_sets, int32_t* best) {
+  for (int s = 0; s < n_sets; ++s) {
+    const int o = offsets[s], N = offsets[s + 1] - offsets[s];
+    best[s] = 0;
+    if (N <= 0) { best[s] = -1; continue; }
+    int* dist = (int*)malloc(sizeof(int) * (size_t)N * N);
+    for (int i = 0; i < N; ++i) {
+      dist[i * N + i] = 0;
+      for (int j = i + 1; j < N; ++j) {
+        const int d = mo_descriptor_distance(D + (size_t)(o + i) * XF_DIM, D + (size_t)(o + j) * XF_DIM);
+        dist[i * N + j] = d; dist[j * N + i] = d;
+      }
+    }
+    int BestMedian = INT_MAX, BestIdx = 0;
+    int* row = (int*)malloc(sizeof(int) * (size_t)N);
+    for (int i = 0; i < N; ++i) {
+      memcpy(row, dist + (size_t)i * N, sizeof(int) * (size_t)N);
+      qsort(row, (size_t)N, sizeof(int), cmp_int);
+      const int median = row[(int)(0.5 * (N - 1))];
+      if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+    }
+    best[s] = BestIdx;
+    free(row); free(dist);
+  }
+}

@@ -72,3 +72,62 @@ def search_for_initialization(D1, k1xy, D2, k2xy, img_w, img_h, prev, window=100
                                            prev.ctypes.data_as(ctypes.c_void_p), int(window), ctypes.c_float(ratio), int(th_low),
                                            m.ctypes.data_as(ctypes.c_void_p))
     return n, m, prev
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a, a.ctypes.data_as(ctypes.c_void_p)
+
+
+def search_by_bow_kf_f(Dkf, node_kf, good_kf, Df, node_f, ratio=0.7, th_low=100):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...), src/ORBmatcher.cc:408-610 -> (nmatches, matches_f[n_f])."""
+    Dkf, p1 = _f(Dkf); Df, p2 = _f(Df)
+    nk, pnk = _i(node_kf); nf, pnf = _i(node_f); gk, pgk = _u8(good_kf)
+    m = np.empty(Df.shape[0], np.int32)
+    L = lib(); L.mo_search_by_bow_kf_f.restype = ctypes.c_int
+    n = L.mo_search_by_bow_kf_f(p1, pnk, pgk, Dkf.shape[0], p2, pnf, Df.shape[0], ctypes.c_float(ratio), int(th_low), m.ctypes.data_as(ctypes.c_void_p))
+    return n, m
+
+
+def search_by_bow_kf_kf(D1, node1, good1, D2, node2, good2, ratio=0.9, th_low=100):
+    """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...), src/ORBmatcher.cc:950-1090 -> (nmatches, matches12[n1])."""
+    D1, p1 = _f(D1); D2, p2 = _f(D2)
+    a1, pa1 = _i(node1); a2, pa2 = _i(node2); g1, pg1 = _u8(good1); g2, pg2 = _u8(good2)
+    m = np.empty(D1.shape[0], np.int32)
+    L = lib(); L.mo_search_by_bow_kf_kf.restype = ctypes.c_int
+    n = L.mo_search_by_bow_kf_kf(p1, pa1, pg1, D1.shape[0], p2, pa2, pg2, D2.shape[0], ctypes.c_float(ratio), int(th_low), m.ctypes.data_as(ctypes.c_void_p))
+    return n, m
+
+
+def search_for_triangulation(D1, node1, hasmp1, stereo1, k1xy, D2, node2, hasmp2, stereo2, k2xy, F12, ep, only_stereo=False, coarse=False,
+                             th_low=100, unc=1.0, scale0=1.0):
+    """ORBmatcher::SearchForTriangulation, src/ORBmatcher.cc:1092-1331 (one pinhole camera) -> (nmatches, matches12[n1])."""
+    D1, p1 = _f(D1); D2, p2 = _f(D2); k1, pk1 = _f(k1xy); k2, pk2 = _f(k2xy); Fm, pF = _f(np.asarray(F12).reshape(9)); e, pe = _f(ep)
+    a1, pa1 = _i(node1); a2, pa2 = _i(node2)
+    h1, ph1 = _u8(hasmp1); h2, ph2 = _u8(hasmp2); s1, ps1 = _u8(stereo1); s2, ps2 = _u8(stereo2)
+    m = np.empty(D1.shape[0], np.int32)
+    L = lib(); L.mo_search_for_triangulation.restype = ctypes.c_int
+    n = L.mo_search_for_triangulation(p1, pa1, ph1, ps1, pk1, D1.shape[0], p2, pa2, ph2, ps2, pk2, D2.shape[0], pF, pe, int(only_stereo), int(coarse),
+                                      int(th_low), ctypes.c_float(unc), ctypes.c_float(scale0), m.ctypes.data_as(ctypes.c_void_p))
+    return n, m
+
+
+def search_by_projection(Dmp, in_view, proj, projxr, level, viewcos, mp_obs, Df, kxy, occupied, uright, img_w, img_h, th=1.0, scale_factor=1.2,
+                         ratio=0.8, th_high=1000):
+    """ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th, ...), src/ORBmatcher.cc:42-212 (Nleft == -1) -> (nmatches, assign[n_f])."""
+    Dmp, p1 = _f(Dmp); Df, p2 = _f(Df); pr, ppr = _f(proj); px, ppx = _f(projxr); vc, pvc = _f(viewcos); kk, pkk = _f(kxy); ur, pur = _f(uright)
+    iv, piv = _u8(in_view); mo_, pmo = _u8(mp_obs); oc, poc = _u8(occupied); lv, plv = _i(level)
+    out = np.empty(Df.shape[0], np.int32)
+    L = lib(); L.mo_search_by_projection.restype = ctypes.c_int
+    n = L.mo_search_by_projection(p1, piv, ppr, ppx, plv, pvc, pmo, Dmp.shape[0], p2, pkk, poc, pur, Df.shape[0], int(img_w), int(img_h),
+                                  ctypes.c_float(th), ctypes.c_float(scale_factor), ctypes.c_float(ratio), int(th_high),
+                                  out.ctypes.data_as(ctypes.c_void_p))
+    return n, out
+
+
+def distinctive_descriptors(D, offsets):
+    """MapPoint::ComputeDistinctiveDescriptors, src/MapPoint.cc:329-403, batched -> best row (relative) per set."""
+    D, p = _f(D); off, po = _i(offsets)
+    best = np.empty(off.shape[0] - 1, np.int32)
+    lib().mo_distinctive_descriptors(p, po, off.shape[0] - 1, best.ctypes.data_as(ctypes.c_void_p))
+    return best

@@ -4,10 +4,13 @@
 // raw float files the Python test compares with the reference's golden output / the C oracle.
 //   extract <frame.u8> H W nfeatures lap0 lap1 <out_prefix>
 //   init    <descA.f32> nA <kpA.f32> <descB.f32> nB <kpB.f32> W H window ratio <out.i32>
+//   searches <bundle.bin> <out.bin>   (SearchByBoW x2, SearchForTriangulation, SearchByProjection, ComputeDistinctiveDescriptors)
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <cstring>
 #include <iostream>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -26,6 +29,41 @@ template <typename T>
 static void spit(const std::string& p, const std::vector<T>& v) {
   std::ofstream os(p, std::ios::binary);
   os.write(reinterpret_cast<const char*>(v.data()), static_cast<std::streamsize>(v.size() * sizeof(T)));
+}
+
+// ---- array bundle: [name 16 bytes][dtype 1 byte: f / i / b][pad 7][count int64][data] ... (written by the Python test) ----
+struct Bundle {
+  std::map<std::string, std::vector<char> > a;
+  explicit Bundle(const std::string& path) {
+    std::ifstream is(path, std::ios::binary);
+    char hdr[32];
+    while (is.read(hdr, 32)) {
+      const std::string name(hdr, strnlen(hdr, 16));
+      long long count; std::memcpy(&count, hdr + 24, 8);
+      const size_t bytes = static_cast<size_t>(count) * (hdr[16] == 'b' ? 1 : 4);
+      std::vector<char> v(bytes);
+      is.read(v.data(), static_cast<std::streamsize>(bytes));
+      a[name] = v;
+    }
+  }
+  template <typename T> std::vector<T> get(const std::string& n) const {
+    const std::vector<char>& v = a.at(n);
+    std::vector<T> o(v.size() / sizeof(T));
+    std::memcpy(o.data(), v.data(), v.size());
+    return o;
+  }
+  std::vector<bool> flags(const std::string& n) const { const std::vector<char>& v = a.at(n); return std::vector<bool>(v.begin(), v.end()); }
+  float scalar(const std::string& n) const { return get<float>(n)[0]; }
+};
+static ORB_SLAM3::XFBmatcher::FeatureVector featvec(const std::vector<int>& node) {
+  ORB_SLAM3::XFBmatcher::FeatureVector fv;   // FeatureVector::addFeature (thirdparty/DBoW2/DBoW2/FeatureVector.cpp): push_back in feature order
+  for (size_t i = 0; i < node.size(); ++i) if (node[i] >= 0) fv[static_cast<unsigned int>(node[i])].push_back(static_cast<unsigned int>(i));
+  return fv;
+}
+static std::vector<cv::KeyPoint> keypoints(const std::vector<float>& xy) {
+  std::vector<cv::KeyPoint> k(xy.size() / 2);
+  for (size_t i = 0; i < k.size(); ++i) k[i] = cv::KeyPoint(xy[2 * i], xy[2 * i + 1], 1, -1, 1.f);
+  return k;
 }
 
 int main(int argc, char** argv) {
@@ -87,6 +125,68 @@ int main(int argc, char** argv) {
     spit(argv[13], pv);
     return 0;
   }
-  std::cerr << "usage: extract ... | init ..." << std::endl;
+  if (mode == "searches" && argc >= 4) {
+    const Bundle b(argv[2]);
+    ORB_SLAM3::XFextractor ex(64, 1.2f, 8, 20, 7);   // only to own a context (created by the first extraction)
+    {
+      cv::Mat tiny(32, 64, CV_8UC1);
+      std::memset(tiny.data, 7, 32 * 64);
+      std::vector<cv::KeyPoint> tk; cv::Mat td; std::vector<int> lap = {0, 0};
+      ex(tiny, cv::Mat(), tk, td, lap);
+    }
+    std::vector<float> dA = b.get<float>("dA"), dB = b.get<float>("dB");
+    const int nA = static_cast<int>(dA.size() / 64), nB = static_cast<int>(dB.size() / 64);
+    cv::Mat A(nA, 64, CV_32F, dA.data()), B(nB, 64, CV_32F, dB.data());
+    const auto fvA = featvec(b.get<int>("nodeA")), fvB = featvec(b.get<int>("nodeB"));
+    std::vector<int> out;
+    auto put = [&](int n, const std::vector<int>& v) { out.push_back(n); out.push_back(static_cast<int>(v.size())); out.insert(out.end(), v.begin(), v.end()); };
+    {  // SearchByBoW(KeyFrame*, Frame&)
+      ORB_SLAM3::XFBmatcher m(ex.context(), b.scalar("ratio_kf_f"), true);
+      std::vector<int> mf;
+      put(m.SearchByBoW(A, fvA, b.flags("goodA"), B, fvB, mf), mf);
+    }
+    {  // SearchByBoW(KeyFrame*, KeyFrame*)
+      ORB_SLAM3::XFBmatcher m(ex.context(), b.scalar("ratio_kf_kf"), true);
+      std::vector<int> m12;
+      put(m.SearchByBoW(A, fvA, b.flags("goodA"), B, fvB, b.flags("goodB"), m12), m12);
+    }
+    {  // SearchForTriangulation
+      ORB_SLAM3::XFBmatcher m(ex.context(), 0.6f, false);
+      const auto F = b.get<float>("F12"), ep = b.get<float>("ep");
+      for (int coarse = 0; coarse < 2; ++coarse) {
+        std::vector<std::pair<size_t, size_t> > pairs;
+        const int n = m.SearchForTriangulation(A, fvA, b.flags("hasmpA"), b.flags("stereoA"), keypoints(b.get<float>("kA")), B, fvB, b.flags("hasmpB"),
+                                               b.flags("stereoB"), keypoints(b.get<float>("kB")), F.data(), cv::Point2f(ep[0], ep[1]), pairs, false,
+                                               coarse != 0);
+        std::vector<int> m12(nA, -1);
+        for (auto& pr : pairs) m12[pr.first] = static_cast<int>(pr.second);
+        put(n, m12);
+      }
+    }
+    {  // SearchByProjection(Frame&, vpMapPoints)
+      ORB_SLAM3::XFBmatcher m(ex.context(), b.scalar("ratio_proj"), true);
+      std::vector<float> dM = b.get<float>("dM"), dF = b.get<float>("dF");
+      const int nM = static_cast<int>(dM.size() / 64), nF = static_cast<int>(dF.size() / 64);
+      cv::Mat M(nM, 64, CV_32F, dM.data()), Fd(nF, 64, CV_32F, dF.data());
+      const auto proj = b.get<float>("proj"), projxr = b.get<float>("projxr"), viewcos = b.get<float>("viewcos");
+      const auto level = b.get<int>("level");
+      const auto in_view = b.flags("in_view"), mp_obs = b.flags("mp_obs");
+      std::vector<ORB_SLAM3::XFBmatcher::ProjectedPoint> pts(nM);
+      for (int i = 0; i < nM; ++i) pts[i] = {in_view[i], proj[2 * i], proj[2 * i + 1], projxr[i], level[i], viewcos[i], mp_obs[i]};
+      std::vector<int> assigned;
+      const auto wh = b.get<float>("img_wh");
+      put(m.SearchByProjection(pts, M, keypoints(b.get<float>("kF")), Fd, b.flags("occupied"), b.get<float>("uright"), 0.f, 0.f, wh[0], wh[1], 1.2f,
+                               b.scalar("th_proj"), assigned), assigned);
+    }
+    {  // MapPoint::ComputeDistinctiveDescriptors (batched)
+      ORB_SLAM3::XFBmatcher m(ex.context(), 0.6f, true);
+      std::vector<float> dS = b.get<float>("dS");
+      cv::Mat S(static_cast<int>(dS.size() / 64), 64, CV_32F, dS.data());
+      put(0, m.ComputeDistinctiveDescriptors(S, b.get<int>("offsets")));
+    }
+    spit(argv[3], out);
+    return 0;
+  }
+  std::cerr << "usage: extract ... | init ... | searches ..." << std::endl;
   return 1;
 }

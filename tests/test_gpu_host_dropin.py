@@ -103,3 +103,94 @@ def test_search_for_initialization_and_match_mirror(driver, tmp_path):
     want = [(i, int(bi[i])) for i in range(na) if bi[i] >= 0 and ri[bi[i]] == i]
     assert [tuple(p) for p in pairs.tolist()] == want
     ctx.close()
+
+
+def _bundle(path, arrays):
+    """[name 16 bytes][dtype f / i / b][pad 7][count int64][data] per array (read by tests/host/host_dropin_driver.cc)."""
+    import struct
+    with open(path, "wb") as f:
+        for name, arr in arrays.items():
+            arr = np.asarray(arr)
+            if arr.dtype == np.float32:
+                code = b"f"
+            elif arr.dtype == np.int32:
+                code = b"i"
+            else:
+                arr = arr.astype(np.uint8); code = b"b"
+            f.write(name.encode().ljust(16, b"\0") + code + b"\0" * 7 + struct.pack("<q", arr.size))
+            f.write(np.ascontiguousarray(arr).tobytes())
+
+
+def test_node_gated_and_window_searches_replay_the_oracle(driver, tmp_path):
+    """XFBmatcher::SearchByBoW (both overloads), SearchForTriangulation, SearchByProjection and ComputeDistinctiveDescriptors
+    (host loops over ONE xfb_distance_pairs launch each) against the C restatements of src/ORBmatcher.cc:408-610, :950-1090,
+    :1092-1331, :42-212 and src/MapPoint.cc:329-403 -- bit-exact."""
+    from xfeatslam_b200.capi import XFeatB200
+    rng = np.random.RandomState(21)
+    fa, fb = synthetic_pair(5, 480, 640, shift=(7, -3))
+    ctx = XFeatB200(max_h=480, max_w=640, max_batch=2, max_topk=1000)
+    o = ctx.extract(np.stack([fa, fb]), 1000)
+    na, nb = int(o["n_valid"][0]), int(o["n_valid"][1])
+    dA, dB, kA, kB = o["desc"][0][:na].copy(), o["desc"][1][:nb].copy(), o["kpts"][0][:na].copy(), o["kpts"][1][:nb].copy()
+    # sparse pair list primitive itself
+    ia = rng.randint(0, na, 5000).astype(np.int32); ib = rng.randint(0, nb, 5000).astype(np.int32)
+    want = np.array([mo.descriptor_distance(dA[i], dB[j]) for i, j in zip(ia[:500], ib[:500])], np.int32)
+    got = ctx.distance_pairs(dA, dB, ia, ib)
+    assert np.array_equal(got[:500], want)
+    assert np.array_equal(got, mo.distance_matrix(dA, dB)[ia, ib])
+    ctx.close()
+    # the synthetic motion between the two frames, measured (its sign convention is synthetic_pair's business)
+    bi, bd, _, _, _ = mo.bruteforce(dA, dB)
+    ok = bd < 60
+    dx, dy = [float(v) for v in np.median(kB[bi[ok]] - kA[ok], axis=0)]
+    assert ok.sum() > 200 and abs(abs(dx) - 7) <= 1 and abs(abs(dy) - 3) <= 1
+    # vocabulary nodes: a 10 x 10 grid of "level-2 nodes" (k = 10, L = 6, levelsup = 4 -> 100 nodes) by image position
+    nodeA = ((kA[:, 0] // 64).astype(np.int32) * 10 + (kA[:, 1] // 48).astype(np.int32)).astype(np.int32)
+    nodeB = (((kB[:, 0] - dx) // 64).astype(np.int32) * 10 + ((kB[:, 1] - dy) // 48).astype(np.int32)).astype(np.int32)
+    nodeB = np.clip(nodeB, 0, 99).astype(np.int32)
+    nodeA[rng.rand(na) < 0.05] = -1; nodeB[rng.rand(nb) < 0.05] = -1
+    goodA = (rng.rand(na) < 0.8); goodB = (rng.rand(nb) < 0.8)
+    hasA = (rng.rand(na) < 0.3); hasB = (rng.rand(nb) < 0.3)
+    stA = (rng.rand(na) < 0.5); stB = (rng.rand(nb) < 0.5)
+    F12 = np.array([[0, 0, 0], [0, 0, -1], [0, 1, -dy]], np.float32)      # x-translation: y2 = y1 + dy on the epipolar line
+    ep = np.array([900.0, 240.0], np.float32)
+    # projection search: map points = frame-A descriptors projected near their frame-B positions
+    nM = 600
+    src = rng.randint(0, na, nM)
+    proj = (kA[src] + np.array([dx, dy], np.float32) + rng.randn(nM, 2).astype(np.float32)).astype(np.float32)
+    level = rng.choice([0, 0, 0, 1, 2], nM).astype(np.int32)
+    viewcos = rng.choice([0.9, 0.9995], nM).astype(np.float32)
+    in_view = rng.rand(nM) < 0.9; mp_obs = rng.rand(nM) < 0.9
+    occupied = rng.rand(nb) < 0.1
+    uright = np.where(rng.rand(nb) < 0.5, kB[:, 0] - 25.0, -1.0).astype(np.float32)
+    projxr = (proj[:, 0] - 25.0 + 2 * rng.randn(nM)).astype(np.float32)
+    sizes = [1, 2, 3, 5, 8, 13, 40]
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    dS = dA[rng.randint(0, na, offsets[-1])] + 0.05 * rng.randn(offsets[-1], 64).astype(np.float32)
+    dS = (dS / np.linalg.norm(dS, axis=1, keepdims=True)).astype(np.float32)
+    arrays = dict(dA=dA, dB=dB, kA=kA, kB=kB, nodeA=nodeA, nodeB=nodeB, goodA=goodA, goodB=goodB, hasmpA=hasA, hasmpB=hasB, stereoA=stA, stereoB=stB,
+                  F12=F12.reshape(-1), ep=ep, ratio_kf_f=np.float32([0.7]), ratio_kf_kf=np.float32([0.9]), ratio_proj=np.float32([0.8]),
+                  th_proj=np.float32([3.0]), dM=dA[src], dF=dB, kF=kB, proj=proj.reshape(-1), projxr=projxr, viewcos=viewcos, level=level,
+                  in_view=in_view, mp_obs=mp_obs, occupied=occupied, uright=uright, img_wh=np.float32([640, 480]), dS=dS, offsets=offsets)
+    _bundle(tmp_path / "in.bin", arrays)
+    subprocess.run([str(driver), "searches", str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], check=True)
+    res = np.fromfile(tmp_path / "out.bin", np.int32)
+    pos = 0
+
+    def take():
+        nonlocal pos
+        n, ln = int(res[pos]), int(res[pos + 1])
+        v = res[pos + 2:pos + 2 + ln].copy(); pos += 2 + ln
+        return n, v
+    n, m = take(); wn, wm = mo.search_by_bow_kf_f(dA, nodeA, goodA, dB, nodeB, ratio=0.7, th_low=100)
+    assert n == wn and np.array_equal(m, wm) and n > 50
+    n, m = take(); wn, wm = mo.search_by_bow_kf_kf(dA, nodeA, goodA, dB, nodeB, goodB, ratio=0.9, th_low=100)
+    assert n == wn and np.array_equal(m, wm) and n > 50
+    for coarse in (False, True):
+        n, m = take(); wn, wm = mo.search_for_triangulation(dA, nodeA, hasA, stA, kA, dB, nodeB, hasB, stB, kB, F12, ep, only_stereo=False, coarse=coarse)
+        assert n == wn and np.array_equal(m, wm) and n > 20
+    n, m = take(); wn, wm = mo.search_by_projection(dA[src], in_view, proj, projxr, level, viewcos, mp_obs, dB, kB, occupied, uright, 640, 480, th=3.0,
+                                                     scale_factor=1.2, ratio=0.8, th_high=1000)
+    assert n == wn and np.array_equal(m, wm) and n > 50
+    _, best = take()
+    assert np.array_equal(best, mo.distinctive_descriptors(dS, offsets))

@@ -17,7 +17,8 @@ INT_MAX = 2 ** 31 - 1
 # every symbol include/xfeat_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
     "xfb_create", "xfb_destroy", "xfb_last_error", "xfb_set_stream", "xfb_extract", "xfb_extract_batch",
-    "xfb_extract_batch_device", "xfb_distance_matrix", "xfb_distance_matrix_device", "xfb_match", "xfb_match_device",
+    "xfb_extract_batch_device", "xfb_distance_matrix", "xfb_distance_matrix_device", "xfb_distance_pairs", "xfb_distance_pairs_device",
+    "xfb_match", "xfb_match_device",
     "xfb_submit", "xfb_wait", "xfb_match_frames", "xfb_match_frame_pairs", "xfb_match_frame_pairs_device", "xfb_profile_enable", "xfb_profile_read", "xfb_profile_tag_name",
     "xfb_debug_match_error", "xfb_debug_force_simt", "xfb_debug_read", "xfb_debug_read_stats", "xfb_debug_post", "xfb_debug_candidates", "xfb_launch_count",
 ]
@@ -46,6 +47,8 @@ def load_library(path=LIB_PATH):
     lib.xfb_extract_batch_device.argtypes = lib.xfb_extract_batch.argtypes
     lib.xfb_distance_matrix.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]
     lib.xfb_distance_matrix_device.argtypes = lib.xfb_distance_matrix.argtypes
+    lib.xfb_distance_pairs.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]
+    lib.xfb_distance_pairs_device.argtypes = lib.xfb_distance_pairs.argtypes
     lib.xfb_match.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int] + [c_void_p] * 5
     lib.xfb_match_device.argtypes = lib.xfb_match.argtypes
     lib.xfb_submit.argtypes = [c_void_p, c_int, c_void_p, c_int, c_size_t, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
@@ -142,6 +145,15 @@ class XFeatB200:
         A = np.ascontiguousarray(A, np.float32); B = np.ascontiguousarray(B, np.float32)
         out = np.zeros((A.shape[0], B.shape[0]), np.int32)
         self._check(self.lib.xfb_distance_matrix(self.h, _ptr(A), A.shape[0], _ptr(B), B.shape[0], _ptr(out)), "xfb_distance_matrix")
+        return out
+
+    def distance_pairs(self, A, B, idx_a, idx_b):
+        """DescriptorDistance(A[idx_a[p]], B[idx_b[p]]) for a list of pairs (xfb_distance_pairs)."""
+        A = np.ascontiguousarray(A, np.float32).reshape(-1, 64); B = np.ascontiguousarray(B, np.float32).reshape(-1, 64)
+        ia = np.ascontiguousarray(idx_a, np.int32); ib = np.ascontiguousarray(idx_b, np.int32)
+        out = np.zeros(ia.shape[0], np.int32)
+        self._check(self.lib.xfb_distance_pairs(self.h, _ptr(A), A.shape[0], _ptr(B), B.shape[0], _ptr(ia), _ptr(ib), ia.shape[0], _ptr(out)),
+                    "xfb_distance_pairs")
         return out
 
     def match(self, A, B, group_a=None, group_b=None, init=INT_MAX):

@@ -39,7 +39,7 @@ void prof_end(Ctx* c) {
   c->prof_ev.push_back(e);
 }
 static const char* kStageNames[] = {"prep_stats", "prep_norm", "pyramid_sum", "heatmap_out", "keypoint_out_softmax_fold", "nms_score",
-                                    "topk_select_sort", "describe", "match_tile", "match_merge", "distance_matrix", "match_prep", "match_bound"};
+                                    "topk_select_sort", "describe", "match_tile", "distance_pairs", "distance_matrix", "match_prep", "match_bound"};
 
 // ---- weight blob (tools/convert_weights.py) --------------------------------------------------------
 #pragma pack(push, 1)
@@ -488,7 +488,7 @@ void xfb_destroy(xfb_ctx* c) {
             h[12] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n, h[7] / n, h[8] / n, h[9] / n, h[10] / n, h[11] / n);
     fprintf(stderr, "[xfb] CTA(0,0) mma thread: cycles in tcgen05.mma issue %.0f, in tcgen05.commit %.0f, in tcgen05.fence %.0f, loop tail %.0f\n", h[14] / n, h[15] / n, h[16] / n, h[17] / n);
   }
-  fr(c->ms_img[0]); fr(c->ms_img[1]); fr(c->ms_fimg); fr(c->ms_counters);
+  fr(c->ms_img[0]); fr(c->ms_img[1]); fr(c->ms_fimg); fr(c->ms_counters); fr(c->p_idx); fr(c->p_out);
   fr(c->tc_fimg); fr(c->tc_fnrm); fr(c->tc_pairs); fr(c->tc_dbg); fr(c->tc_fnmax); fr(c->tc_bound); fr(c->tc_nmax[0]); fr(c->tc_nmax[1]);
   for (auto& s : c->slots) {
     fr(s.d_gray); fr(s.nvalid); fr(s.xy); fr(s.score); fr(s.desc);
@@ -576,6 +576,43 @@ int xfb_distance_matrix(xfb_ctx* c, const float* A, int n1, const float* B, int 
   r = tc_matrix_generic(c, c->m_a, n1, c->m_b, n2, c->m_matrix, nullptr);
   if (r != XFB_OK) return r;
   XFB_CUDA_OK(c, cudaMemcpyAsync(out, c->m_matrix, (size_t)n1 * n2 * 4, cudaMemcpyDeviceToHost, c->stream));
+  XFB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return XFB_OK;
+}
+
+int xfb_distance_pairs_device(xfb_ctx* c, const float* d_A, int n1, const float* d_B, int n2, const int32_t* d_ia, const int32_t* d_ib, int n_pairs,
+                               int32_t* d_out) {
+  if (!c) return XFB_ERR_ARG;
+  if (n1 < 0 || n2 < 0 || n_pairs < 0 || (n_pairs && (!d_A || !d_B || !d_ia || !d_ib || !d_out))) { c->err = "distance_pairs: bad argument"; return XFB_ERR_ARG; }
+  XFB_CUDA_OK(c, cudaSetDevice(c->device));
+  XFB_CUDA_OK(c, launch_distance_pairs(c, d_A, n1, d_B, n2, d_ia, d_ib, n_pairs, d_out));
+  return XFB_OK;
+}
+
+int xfb_distance_pairs(xfb_ctx* c, const float* A, int n1, const float* B, int n2, const int32_t* idx_a, const int32_t* idx_b, int n_pairs, int32_t* out) {
+  if (!c) return XFB_ERR_ARG;
+  if (n1 < 0 || n2 < 0 || n_pairs < 0 || (n_pairs && (!A || !B || !idx_a || !idx_b || !out))) { c->err = "distance_pairs: bad argument"; return XFB_ERR_ARG; }
+  if (n_pairs == 0) return XFB_OK;
+  for (int p = 0; p < n_pairs; ++p)
+    if (idx_a[p] < 0 || idx_a[p] >= n1 || idx_b[p] < 0 || idx_b[p] >= n2) { c->err = "distance_pairs: index out of range"; return XFB_ERR_ARG; }
+  XFB_CUDA_OK(c, cudaSetDevice(c->device));
+  int r = ensure_match_scratch(c, n1, n2, false);
+  if (r != XFB_OK) return r;
+  if (n_pairs > c->p_cap) {
+    if (c->p_idx) cudaFree(c->p_idx);
+    if (c->p_out) cudaFree(c->p_out);
+    c->p_idx = nullptr; c->p_out = nullptr; c->p_cap = 0;
+    const size_t cap = (size_t)(n_pairs + 4095) / 4096 * 4096;
+    XFB_ALLOC(c, c->p_idx, cap * 2 * 4);
+    XFB_ALLOC(c, c->p_out, cap * 4);
+    c->p_cap = (int)cap;
+  }
+  XFB_CUDA_OK(c, cudaMemcpyAsync(c->m_a, A, (size_t)n1 * 64 * 4, cudaMemcpyHostToDevice, c->stream));
+  XFB_CUDA_OK(c, cudaMemcpyAsync(c->m_b, B, (size_t)n2 * 64 * 4, cudaMemcpyHostToDevice, c->stream));
+  XFB_CUDA_OK(c, cudaMemcpyAsync(c->p_idx, idx_a, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
+  XFB_CUDA_OK(c, cudaMemcpyAsync(c->p_idx + c->p_cap, idx_b, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
+  XFB_CUDA_OK(c, launch_distance_pairs(c, c->m_a, n1, c->m_b, n2, c->p_idx, c->p_idx + c->p_cap, n_pairs, c->p_out));
+  XFB_CUDA_OK(c, cudaMemcpyAsync(out, c->p_out, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, c->stream));
   XFB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return XFB_OK;
 }

@@ -10,10 +10,17 @@
 //                       mutual nearest neighbours, distance = sqrt(2 (1 - cos)) = ||a - b||
 //   * SearchForInitialization : src/ORBmatcher.cc:833-948 replayed over a DistanceTable, with
 //                       Frame::GetFeaturesInArea (src/Frame.cc:850-916) restated on plain arrays.
+//   * SearchByBoW (both overloads), SearchForTriangulation, SearchByProjection, ComputeDistinctiveDescriptors:
+//                       the candidate pairs are listed in the reference's visiting order, all their distances come from ONE
+//                       xfb_distance_pairs launch, and the reference's sequential accept / reject logic is replayed over them.
+//                       MapPoint* / KeyFrame* / Frame& arguments become plain containers (those classes need Eigen / Sophus /
+//                       DBoW2); DBoW2::FeatureVector is kept as the std::map it is.
 // See INTEGRATION.md for the 3-line patch that routes ORBmatcher::DescriptorDistance through a table.
 #ifndef XFBMATCHER_H
 #define XFBMATCHER_H
 
+#include <map>
+#include <utility>
 #include <vector>
 
 #include <opencv2/opencv.hpp>
@@ -52,7 +59,51 @@ class XFBmatcher {
                               const cv::Mat& desc2, float minX, float minY, float maxX, float maxY,
                               std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10) const;
 
+  // DBoW2::FeatureVector (thirdparty/DBoW2/DBoW2/FeatureVector.h): node id -> feature indices, ascending
+  typedef std::map<unsigned int, std::vector<unsigned int> > FeatureVector;
+
+  // ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches), src/ORBmatcher.cc:408-610
+  // (F.Nleft == -1).  vbGoodMapPointKF[i] = (vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad()).
+  // vnMatchesF[j] = index of the KF feature whose MapPoint frame feature j receives, -1 = NULL.
+  int SearchByBoW(const cv::Mat& descKF, const FeatureVector& vFeatVecKF, const std::vector<bool>& vbGoodMapPointKF, const cv::Mat& descF,
+                  const FeatureVector& vFeatVecF, std::vector<int>& vnMatchesF) const;
+  // ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12), src/ORBmatcher.cc:950-1090.
+  // vnMatches12[i1] = index of the KF2 feature whose MapPoint is matched to feature i1 of KF1, -1 = NULL.
+  int SearchByBoW(const cv::Mat& desc1, const FeatureVector& vFeatVec1, const std::vector<bool>& vbGoodMapPoint1, const cv::Mat& desc2,
+                  const FeatureVector& vFeatVec2, const std::vector<bool>& vbGoodMapPoint2, std::vector<int>& vnMatches12) const;
+  // ORBmatcher::SearchForTriangulation, src/ORBmatcher.cc:1092-1331, one pinhole camera per keyframe.
+  // vbHasMapPoint = (GetMapPoint(idx) != NULL); vbStereo = (mvuRight[idx] >= 0); F12 = the row-major fundamental matrix of
+  // Pinhole::epipolarConstrain (src/CameraModels/Pinhole.cpp:109-112); ep = epipole of camera 1 in image 2 (:1105);
+  // sigma2Level0 = mvLevelSigma2[0], scaleFactor0 = mvScaleFactors[0].
+  int SearchForTriangulation(const cv::Mat& desc1, const FeatureVector& vFeatVec1, const std::vector<bool>& vbHasMapPoint1,
+                             const std::vector<bool>& vbStereo1, const std::vector<cv::KeyPoint>& vKeysUn1, const cv::Mat& desc2,
+                             const FeatureVector& vFeatVec2, const std::vector<bool>& vbHasMapPoint2, const std::vector<bool>& vbStereo2,
+                             const std::vector<cv::KeyPoint>& vKeysUn2, const float F12[9], const cv::Point2f& ep,
+                             std::vector<std::pair<size_t, size_t> >& vMatchedPairs, bool bOnlyStereo, bool bCoarse = false,
+                             float sigma2Level0 = 1.0f, float scaleFactor0 = 1.0f) const;
+
+  // One map point of ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints)
+  struct ProjectedPoint {
+    bool inView;            // mbTrackInView && !(bFarPoints && mTrackDepth > thFarPoints) && !isBad()
+    float projX, projY;     // mTrackProjX, mTrackProjY
+    float projXR;           // mTrackProjXR
+    int scaleLevel;         // mnTrackScaleLevel
+    float viewCos;          // mTrackViewCos
+    bool hasObservations;   // Observations() > 0
+  };
+  // src/ORBmatcher.cc:42-212 for monocular / RGB-D frames (F.Nleft == -1).  descMP row m = pMP->GetDescriptor();
+  // vbOccupiedF[idx] = (F.mvpMapPoints[idx] && F.mvpMapPoints[idx]->Observations() > 0); vuRightF = F.mvuRight.
+  // vnAssignedF[idx] = index of the map point written to F.mvpMapPoints[idx], -1 = untouched.
+  int SearchByProjection(const std::vector<ProjectedPoint>& vPoints, const cv::Mat& descMP, const std::vector<cv::KeyPoint>& vKeysUnF,
+                         const cv::Mat& descF, const std::vector<bool>& vbOccupiedF, const std::vector<float>& vuRightF, float minX, float minY,
+                         float maxX, float maxY, float scaleFactor, float th, std::vector<int>& vnAssignedF) const;
+
+  // MapPoint::ComputeDistinctiveDescriptors, src/MapPoint.cc:329-403, for many map points in one GPU launch: the observed
+  // descriptors of map point s are the rows offsets[s] .. offsets[s+1]-1 of `desc`; returns the chosen row (relative to the set).
+  std::vector<int> ComputeDistinctiveDescriptors(const cv::Mat& desc, const std::vector<int>& offsets) const;
+
  private:
+  std::vector<int32_t> PairDistances(const cv::Mat& desc1, const cv::Mat& desc2, const std::vector<int32_t>& i1, const std::vector<int32_t>& i2) const;
   xfb_ctx* ctx_;
   float mfNNratio;
   bool mbCheckOrientation;
