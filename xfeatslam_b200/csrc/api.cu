@@ -148,8 +148,8 @@ static int alloc_buffers(Ctx* c) {
   if (prep_pe > pe) pe = prep_pe;
   c->part_elems = pe;
   XFB_ALLOC(c, c->part, B * pe * sizeof(double));
-  XFB_ALLOC(c, c->ticket, B * 4);
-  XFB_CUDA_OK(c, cudaMemset(c->ticket, 0, B * 4));
+  XFB_ALLOC(c, c->ticket, B * XFB_TICKET_STRIDE * 4);
+  XFB_CUDA_OK(c, cudaMemset(c->ticket, 0, B * XFB_TICKET_STRIDE * 4));
   XFB_ALLOC(c, c->cand, B * HW * 8);
   XFB_ALLOC(c, c->cand_count, B * 4);
   XFB_ALLOC(c, c->cand_count_last, B * 4);

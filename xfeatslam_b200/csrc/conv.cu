@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(C::NT) conv_bn_kernel(const ConvArgs a) {
   __threadfence();
   __syncthreads();
   if (t == 0) {
-    const unsigned int prev = atomicAdd(a.ticket + b, 1u);
+    const unsigned int prev = atomicAdd(a.ticket + b * XFB_TICKET_STRIDE, 1u);
     s_last = (prev == (unsigned int)(tiles - 1)) ? 1u : 0u;
   }
   __syncthreads();
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(C::NT) conv_bn_kernel(const ConvArgs a) {
     a.out_mean[b * COUT + c] = (float)mean;
     a.out_rstd[b * COUT + c] = (float)(1.0 / sqrt(var + 1e-5));
   }
-  if (t == 0) a.ticket[b] = 0u;  // re-arm for the next layer
+  if (t == 0) a.ticket[b * XFB_TICKET_STRIDE] = 0u;  // re-arm for the next layer
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(CTC_THREADS, 1) conv_tc_kernel(const ConvTcArg
       __threadfence();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (t == 0) {
-        const unsigned int prev = atomicAdd(a.ticket + b, 1u);
+        const unsigned int prev = atomicAdd(a.ticket + b * XFB_TICKET_STRIDE, 1u);
         s_last = (prev == (unsigned int)(tiles - 1)) ? 1u : 0u;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(CTC_THREADS, 1) conv_tc_kernel(const ConvTcArg
           a.out_mean[b * COUT + c] = (float)mean;
           a.out_rstd[b * COUT + c] = (float)(1.0 / sqrt(var + 1e-5));
         }
-        if (t == 0) a.ticket[b] = 0u;
+        if (t == 0) a.ticket[b * XFB_TICKET_STRIDE] = 0u;
       }
     }
   }

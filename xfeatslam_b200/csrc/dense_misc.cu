@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(PREP_NT) prep_stats_kernel(const uint8_t* gray
     part_b[blockIdx.x * 2] = d1;
     part_b[blockIdx.x * 2 + 1] = d2;
     __threadfence();
-    const unsigned int prev = atomicAdd(ticket + b, 1u);
+    const unsigned int prev = atomicAdd(ticket + b * XFB_TICKET_STRIDE, 1u);
     s_last = (prev == (unsigned int)(tiles - 1)) ? 1u : 0u;
   }
   __syncthreads();
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(PREP_NT) prep_stats_kernel(const uint8_t* gray
     if (var < 0.0) var = 0.0;
     mean_out[b] = (float)mean;
     rstd_out[b] = (float)(1.0 / sqrt(var + 1e-5));
-    ticket[b] = 0u;
+    ticket[b * XFB_TICKET_STRIDE] = 0u;
   }
 }
 

@@ -46,54 +46,72 @@ __device__ __forceinline__ float bilinear1(const float* map, int mh, int mw, flo
   return bilerp4(nw, ne, sw, se, __fmul_rn(s, e), __fmul_rn(s, w), __fmul_rn(n, e), __fmul_rn(n, w));
 }
 
-constexpr int NMS_T = 16;   // 16 x 16 pixel tiles: 256-thread CTAs, 8 per SM, hide the tile-load latency
+constexpr int NMS_T = 16;    // 256-thread CTAs (16 x 16) ...
+constexpr int NMS_NX = 4;    // ... that each sweep a 64 x 16 pixel strip: 4x fewer, 4x longer CTAs than one 16 x 16 tile each
+                             // (the kernel is launch- / tile-load-latency bound, not bandwidth bound)
 __global__ void __launch_bounds__(NMS_T * NMS_T) nms_score_kernel(const float* k1h, const float* h1, int H, int W, float thr,
                                                                   u64* cand, int* cand_count) {
-  __shared__ float tile[NMS_T + 4][NMS_T + 4];
+  constexpr int TW = NMS_T * NMS_NX;
+  __shared__ float tile[NMS_T + 4][TW + 4];
   const int b = blockIdx.z;
   const float* img = k1h + (size_t)b * H * W;
-  const int x0 = blockIdx.x * NMS_T, y0 = blockIdx.y * NMS_T;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * NMS_T;
   const int tid = threadIdx.y * NMS_T + threadIdx.x;
-  for (int i = tid; i < (NMS_T + 4) * (NMS_T + 4); i += NMS_T * NMS_T) {
-    const int ty = i / (NMS_T + 4), tx = i - ty * (NMS_T + 4);
+  for (int i = tid; i < (NMS_T + 4) * (TW + 4); i += NMS_T * NMS_T) {
+    const int ty = i / (TW + 4), tx = i - ty * (TW + 4);
     const int gy = y0 + ty - 2, gx = x0 + tx - 2;
     tile[ty][tx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? img[(size_t)gy * W + gx] : -CUDART_INF_F;
   }
   __syncthreads();
-  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-  u64 key = 0;   // 0 = not a candidate (a real key has score bits > 0)
-  if (x < W && y < H) {
-    const float v = tile[threadIdx.y + 2][threadIdx.x + 2];
-    if (v > thr) {
-      float m = v;
+  __shared__ int s_cnt[NMS_NX * 8];   // candidates per (sub-tile, warp), then their exclusive prefix
+  __shared__ int s_base;
+  const int lane = tid & 31, wrp = tid >> 5;
+  u64 keys[NMS_NX];
+  unsigned int ballots[NMS_NX];
 #pragma unroll
-      for (int dy = 0; dy < 5; ++dy)
+  for (int sx = 0; sx < NMS_NX; ++sx) {
+    const int lx = sx * NMS_T + threadIdx.x;   // column inside the strip
+    const int x = x0 + lx, y = y0 + threadIdx.y;
+    u64 key = 0;   // 0 = not a candidate (a real key has score bits > 0)
+    if (x < W && y < H) {
+      const float v = tile[threadIdx.y + 2][lx + 2];
+      if (v > thr) {
+        float m = v;
 #pragma unroll
-        for (int dx = 0; dx < 5; ++dx) m = fmaxf(m, tile[threadIdx.y + dy][threadIdx.x + dx]);
-      if (v == m && !(x == 0 && y == 0)) {   // (0,0) is masked to -1 by the reference, never valid
-        // nearest(K1h)(kp): grid_sample nearest at full resolution (drops the last row / column)
-        const float nx = nearbyintf(grid_src(x, W, W)), ny = nearbyintf(grid_src(y, H, H));
-        float sn = 0.f;
-        if (nx >= 0.f && nx < (float)W && ny >= 0.f && ny < (float)H) sn = img[(size_t)(int)ny * W + (int)nx];
-        const int mh = H >> 3, mw = W >> 3;
-        const float sb = bilinear1(h1 + (size_t)b * mh * mw, mh, mw, grid_src(x, W, mw), grid_src(y, H, mh));
-        const float score = __fmul_rn(sn, sb);
-        if (score > 0.f) {                   // `valid = scores > 0`, src/XFextractor.cc:313
-          const unsigned int lin = (unsigned int)(y * W + x);
-          key = ((u64)__float_as_uint(score) << 32) | (u64)(0xFFFFFFFFu - lin);
+        for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 5; ++dx) m = fmaxf(m, tile[threadIdx.y + dy][lx + dx]);
+        if (v == m && !(x == 0 && y == 0)) {   // (0,0) is masked to -1 by the reference, never valid
+          // nearest(K1h)(kp): grid_sample nearest at full resolution (drops the last row / column)
+          const float nx = nearbyintf(grid_src(x, W, W)), ny = nearbyintf(grid_src(y, H, H));
+          float sn = 0.f;
+          if (nx >= 0.f && nx < (float)W && ny >= 0.f && ny < (float)H) sn = img[(size_t)(int)ny * W + (int)nx];
+          const int mh = H >> 3, mw = W >> 3;
+          const float sb = bilinear1(h1 + (size_t)b * mh * mw, mh, mw, grid_src(x, W, mw), grid_src(y, H, mh));
+          const float score = __fmul_rn(sn, sb);
+          if (score > 0.f) {                   // `valid = scores > 0`, src/XFextractor.cc:313
+            const unsigned int lin = (unsigned int)(y * W + x);
+            key = ((u64)__float_as_uint(score) << 32) | (u64)(0xFFFFFFFFu - lin);
+          }
         }
       }
     }
+    keys[sx] = key;
+    ballots[sx] = __ballot_sync(0xffffffffu, key != 0);
+    if (lane == 0) s_cnt[sx * 8 + wrp] = __popc(ballots[sx]);
   }
-  // warp-aggregated append: one atomic per warp instead of one per candidate (order is irrelevant: the key sorts)
-  const unsigned int ballot = __ballot_sync(0xffffffffu, key != 0);
-  if (ballot) {
-    const int lane = tid & 31;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(cand_count + b, __popc(ballot));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (key != 0) cand[(size_t)b * H * W + base + __popc(ballot & ((1u << lane) - 1u))] = key;
+  __syncthreads();
+  // CTA-aggregated append: ONE atomic per CTA on the frame's counter (the 32 per-frame counters share a cache line, so
+  // per-warp atomics of the whole batch serialise on it); the order inside the list is irrelevant, the key sorts
+  if (tid == 0) {
+    int total = 0;
+    for (int i = 0; i < NMS_NX * 8; ++i) { const int n = s_cnt[i]; s_cnt[i] = total; total += n; }
+    s_base = total ? atomicAdd(cand_count + b, total) : 0;
   }
+  __syncthreads();
+#pragma unroll
+  for (int sx = 0; sx < NMS_NX; ++sx)
+    if (keys[sx] != 0) cand[(size_t)b * H * W + s_base + s_cnt[sx * 8 + wrp] + __popc(ballots[sx] & ((1u << lane) - 1u))] = keys[sx];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -234,7 +252,7 @@ static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 cudaError_t launch_post(Ctx* c, int topk, float nms_thr, int32_t* d_nvalid, float* d_xy, float* d_score, float* d_desc) {
   const int H = c->H, W = c->W;
-  dim3 g1((W + NMS_T - 1) / NMS_T, (H + NMS_T - 1) / NMS_T, c->B);
+  dim3 g1((W + NMS_T * NMS_NX - 1) / (NMS_T * NMS_NX), (H + NMS_T - 1) / NMS_T, c->B);
   prof_begin(c, P_NMS);
   nms_score_kernel<<<g1, dim3(NMS_T, NMS_T), 0, c->stream>>>(c->k1h, c->act[L_HM_2], H, W, nms_thr, c->cand, c->cand_count);
   prof_end(c);

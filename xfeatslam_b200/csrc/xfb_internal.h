@@ -30,6 +30,9 @@ enum LayerId {
   L_NUM
 };
 
+// per-frame atomic counters are spaced one cache line apart: a batch's CTAs would otherwise serialise on ONE L2 line
+constexpr int XFB_TICKET_STRIDE = 32;
+
 struct LayerSpec {
   const char* ref_name;  // module path in the reference / weight blob
   int cin, cout, ks, stride;
@@ -92,7 +95,7 @@ struct Ctx {
   float* in_rstd = nullptr;
   double* part = nullptr;         // shared partial-sum scratch
   size_t part_elems = 0;
-  unsigned int* ticket = nullptr; // [B]
+  unsigned int* ticket = nullptr; // [B * XFB_TICKET_STRIDE]: one "CTAs done" counter per frame, each in its own 128-byte line
 
   // post-processing
   unsigned long long* cand = nullptr;  // [B][H*W] candidate keys
