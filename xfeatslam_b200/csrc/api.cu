@@ -39,7 +39,7 @@ void prof_end(Ctx* c) {
   c->prof_ev.push_back(e);
 }
 static const char* kStageNames[] = {"prep_stats", "prep_norm", "pyramid_sum", "heatmap_out", "keypoint_out_softmax_fold", "nms_score",
-                                    "topk_select_sort", "describe", "match_tile", "distance_pairs", "distance_matrix", "match_prep", "match_bound"};
+                                    "topk_select_sort", "describe", "match_tile", "distance_pairs", "distance_matrix", "match_prep"};
 
 // ---- weight blob (tools/convert_weights.py) --------------------------------------------------------
 #pragma pack(push, 1)
@@ -193,14 +193,8 @@ static int tc_ensure_generic(Ctx* c, int n1, int n2) {
     c->tc_cap = need;
   }
   for (int i = 0; i < 2; ++i) if (!c->tc_nmax[i]) XFB_ALLOC(c, c->tc_nmax[i], 16);
-  if (c->tc_bound_rows < need) {
-    if (c->tc_bound) cudaFree(c->tc_bound);
-    c->tc_bound = nullptr;
-    XFB_ALLOC(c, c->tc_bound, (size_t)64 * need * 4);
-    c->tc_bound_rows = need;
-  }
   if (!c->tc_dbg) XFB_ALLOC(c, c->tc_dbg, 16);
-  if (c->match_impl != 0 && c->ms_cap < need) {
+  if (c->ms_cap < need) {
     for (int i = 0; i < 2; ++i) { if (c->ms_img[i]) cudaFree(c->ms_img[i]); c->ms_img[i] = nullptr; }
     for (int i = 0; i < 2; ++i) XFB_ALLOC(c, c->ms_img[i], ms_image_bytes(need));
     c->ms_cap = need;
@@ -214,51 +208,25 @@ static int tc_match_generic(Ctx* c, const float* dA, int n1, const float* dB, in
   int r = tc_ensure_generic(c, n1, n2);
   if (r != XFB_OK) return r;
   const int p1 = pad128(n1), p2 = pad128(n2);
-  if (c->match_impl != 0) {
-    XFB_CUDA_OK(c, launch_ms_prep(c, dA, 0, 1, nullptr, n1, p1, c->ms_img[0], 0, c->tc_nrm[0], c->tc_nmax[0]));
-    XFB_CUDA_OK(c, launch_ms_prep(c, dB, 0, 1, nullptr, n2, p2, c->ms_img[1], 0, c->tc_nrm[1], c->tc_nmax[1]));
-    MatchTcArgs a = {};
-    a.init = init;
-    a.ms_counters = c->ms_counters; a.ms_mode = c->ms_mode;
-    const bool grouped = ga && gb;
-    if (n1 > 0 && (bi || bd || sd)) {
-      a.imgA = (const float*)c->ms_img[0]; a.imgB = (const float*)c->ms_img[1]; a.nrmA = c->tc_nrm[0]; a.nrmB = c->tc_nrm[1]; a.rawA = dA; a.rawB = dB;
-      a.gA = ga; a.gB = gb; a.nA_host = n1; a.nB_host = n2; a.rows_padded_A = p1; a.rows_padded_B = p2; a.out_stride = n1;
-      a.best_idx = bi; a.best_dist = bd; a.second_dist = sd;
-      a.nrm_max_B = c->tc_nmax[1];
-      XFB_CUDA_OK(c, launch_match_stream(c, a, 1, grouped, c->match_impl));
-    }
-    if (n2 > 0 && (ri || rd)) {   // column-wise best == row-wise best of the transposed problem (distances are symmetric, bit for bit)
-      a.imgA = (const float*)c->ms_img[1]; a.imgB = (const float*)c->ms_img[0]; a.nrmA = c->tc_nrm[1]; a.nrmB = c->tc_nrm[0]; a.rawA = dB; a.rawB = dA;
-      a.gA = gb; a.gB = ga; a.nA_host = n2; a.nB_host = n1; a.rows_padded_A = p2; a.rows_padded_B = p1; a.out_stride = n2;
-      a.best_idx = ri; a.best_dist = rd; a.second_dist = nullptr;
-      a.nrm_max_B = c->tc_nmax[0];
-      XFB_CUDA_OK(c, launch_match_stream(c, a, 1, grouped, c->match_impl));
-    }
-    return XFB_OK;
-  }
-  XFB_CUDA_OK(c, launch_match_prep(c, dA, 0, 1, nullptr, n1, p1, c->tc_img[0], 0, c->tc_nrm[0], c->tc_nmax[0]));
-  XFB_CUDA_OK(c, launch_match_prep(c, dB, 0, 1, nullptr, n2, p2, c->tc_img[1], 0, c->tc_nrm[1], c->tc_nmax[1]));
+  XFB_CUDA_OK(c, launch_ms_prep(c, dA, 0, 1, nullptr, n1, p1, c->ms_img[0], 0, c->tc_nrm[0], c->tc_nmax[0]));
+  XFB_CUDA_OK(c, launch_ms_prep(c, dB, 0, 1, nullptr, n2, p2, c->ms_img[1], 0, c->tc_nrm[1], c->tc_nmax[1]));
   MatchTcArgs a = {};
   a.init = init;
+  a.ms_counters = c->ms_counters; a.ms_mode = c->ms_mode;
   const bool grouped = ga && gb;
-  const bool use_bound = !grouped && n1 > 0 && n2 >= 256;   // the bound pass pays off for long scans only
   if (n1 > 0 && (bi || bd || sd)) {
-    a.imgA = c->tc_img[0]; a.imgB = c->tc_img[1]; a.nrmA = c->tc_nrm[0]; a.nrmB = c->tc_nrm[1]; a.rawA = dA; a.rawB = dB;
+    a.imgA = (const float*)c->ms_img[0]; a.imgB = (const float*)c->ms_img[1]; a.nrmA = c->tc_nrm[0]; a.nrmB = c->tc_nrm[1]; a.rawA = dA; a.rawB = dB;
     a.gA = ga; a.gB = gb; a.nA_host = n1; a.nB_host = n2; a.rows_padded_A = p1; a.rows_padded_B = p2; a.out_stride = n1;
     a.best_idx = bi; a.best_dist = bd; a.second_dist = sd;
     a.nrm_max_B = c->tc_nmax[1];
-    if (use_bound) { a.bound = c->tc_bound; XFB_CUDA_OK(c, launch_match_bound(c, a, p1 / 128, 1)); }
-    XFB_CUDA_OK(c, launch_match_tc(c, a, p1 / 128, 1, grouped));
+    XFB_CUDA_OK(c, launch_match_stream(c, a, 1, grouped));
   }
   if (n2 > 0 && (ri || rd)) {   // column-wise best == row-wise best of the transposed problem (distances are symmetric, bit for bit)
-    a.imgA = c->tc_img[1]; a.imgB = c->tc_img[0]; a.nrmA = c->tc_nrm[1]; a.nrmB = c->tc_nrm[0]; a.rawA = dB; a.rawB = dA;
+    a.imgA = (const float*)c->ms_img[1]; a.imgB = (const float*)c->ms_img[0]; a.nrmA = c->tc_nrm[1]; a.nrmB = c->tc_nrm[0]; a.rawA = dB; a.rawB = dA;
     a.gA = gb; a.gB = ga; a.nA_host = n2; a.nB_host = n1; a.rows_padded_A = p2; a.rows_padded_B = p1; a.out_stride = n2;
     a.best_idx = ri; a.best_dist = rd; a.second_dist = nullptr;
     a.nrm_max_B = c->tc_nmax[0];
-    a.bound = nullptr;
-    if (!grouped && n1 >= 256) { a.bound = c->tc_bound; XFB_CUDA_OK(c, launch_match_bound(c, a, p2 / 128, 1)); }
-    XFB_CUDA_OK(c, launch_match_tc(c, a, p2 / 128, 1, grouped));
+    XFB_CUDA_OK(c, launch_match_stream(c, a, 1, grouped));
   }
   return XFB_OK;
 }
@@ -279,87 +247,42 @@ static int tc_matrix_generic(Ctx* c, const float* dA, int n1, const float* dB, i
 // frames of the last extract: pairs (host) -> outputs [n_pairs][K] (device pointers, nullable)
 static int tc_match_frames(Ctx* c, const int32_t* pairs, int n_pairs, int init, int32_t* o[5]) {
   const int K = c->last_topk, P = pad128(K);
-  const size_t img_stride = (size_t)P * 64;
-  if (!c->tc_fimg || c->tc_frows < P) {
-    if (c->tc_fimg) cudaFree(c->tc_fimg);
+  if (!c->ms_fimg || c->ms_frows < P) {
+    if (c->ms_fimg) cudaFree(c->ms_fimg);
     if (c->tc_fnrm) cudaFree(c->tc_fnrm);
     if (c->tc_fnmax) cudaFree(c->tc_fnmax);
-    c->tc_fimg = nullptr; c->tc_fnrm = nullptr; c->tc_fnmax = nullptr;
+    c->ms_fimg = nullptr; c->tc_fnrm = nullptr; c->tc_fnmax = nullptr;
     const int PM = pad128(c->max_topk);
-    XFB_ALLOC(c, c->tc_fimg, (size_t)c->max_batch * PM * 64 * 4);
+    XFB_ALLOC(c, c->ms_fimg, (size_t)c->max_batch * ms_image_bytes(PM));
     XFB_ALLOC(c, c->tc_fnrm, (size_t)c->max_batch * PM * 4);
     XFB_ALLOC(c, c->tc_fnmax, (size_t)c->max_batch * 4);
-    c->tc_frows = PM;
+    c->ms_frows = PM;
     c->tc_fvalid = false;
   }
-  if (c->match_impl != 0) {
-    const int PM = pad128(c->max_topk);
-    if (!c->ms_fimg || c->ms_frows < P) {
-      if (c->ms_fimg) cudaFree(c->ms_fimg);
-      c->ms_fimg = nullptr;
-      XFB_ALLOC(c, c->ms_fimg, (size_t)c->max_batch * ms_image_bytes(PM));
-      c->ms_frows = PM;
-      c->tc_fvalid = false;
-    }
-    const size_t img_bytes = ms_image_bytes(P);
-    if (!c->tc_fvalid) {
-      XFB_CUDA_OK(c, launch_ms_prep(c, c->last_desc, (size_t)K * 64, c->B, c->last_nvalid, K, P, c->ms_fimg, img_bytes, c->tc_fnrm, c->tc_fnmax));
-      c->tc_fvalid = true;
-    }
-    for (int p0 = 0; p0 < n_pairs; p0 += 64) {
-      const int np = (n_pairs - p0) < 64 ? (n_pairs - p0) : 64;
-      MatchTcArgs a = {};
-      a.imgA = a.imgB = (const float*)c->ms_fimg; a.nrmA = a.nrmB = c->tc_fnrm; a.rawA = a.rawB = c->last_desc;
-      a.nA_dev = a.nB_dev = c->last_nvalid; a.nA_host = a.nB_host = K; a.rows_padded_A = a.rows_padded_B = P;
-      a.img_stride_A = a.img_stride_B = img_bytes; a.raw_stride_A = a.raw_stride_B = (size_t)K * 64;
-      a.init = init; a.out_stride = K;
-      a.nrm_max_B = c->tc_fnmax;
-      a.ms_counters = c->ms_counters; a.ms_mode = c->ms_mode;
-      if (o[0] || o[1] || o[2]) {
-        for (int p = 0; p < np; ++p) { a.pairs[2 * p] = pairs[2 * (p0 + p)]; a.pairs[2 * p + 1] = pairs[2 * (p0 + p) + 1]; }
-        a.best_idx = o[0] ? o[0] + (size_t)p0 * K : nullptr; a.best_dist = o[1] ? o[1] + (size_t)p0 * K : nullptr;
-        a.second_dist = o[2] ? o[2] + (size_t)p0 * K : nullptr;
-        XFB_CUDA_OK(c, launch_match_stream(c, a, np, false, c->match_impl));
-      }
-      if (o[3] || o[4]) {
-        for (int p = 0; p < np; ++p) { a.pairs[2 * p] = pairs[2 * (p0 + p) + 1]; a.pairs[2 * p + 1] = pairs[2 * (p0 + p)]; }
-        a.best_idx = o[3] ? o[3] + (size_t)p0 * K : nullptr; a.best_dist = o[4] ? o[4] + (size_t)p0 * K : nullptr; a.second_dist = nullptr;
-        XFB_CUDA_OK(c, launch_match_stream(c, a, np, false, c->match_impl));
-      }
-    }
-    return XFB_OK;
-  }
-  if (c->tc_bound_rows < P) {
-    if (c->tc_bound) cudaFree(c->tc_bound);
-    c->tc_bound = nullptr;
-    XFB_ALLOC(c, c->tc_bound, (size_t)64 * pad128(c->max_topk) * 4);
-    c->tc_bound_rows = pad128(c->max_topk);
-  }
-  if (!c->tc_fvalid) {
-    XFB_CUDA_OK(c, launch_match_prep(c, c->last_desc, (size_t)K * 64, c->B, c->last_nvalid, K, P, c->tc_fimg, img_stride, c->tc_fnrm, c->tc_fnmax));
+  const size_t img_bytes = ms_image_bytes(P);
+  if (!c->tc_fvalid) {   // operand images of every frame of the batch, once per extract
+    XFB_CUDA_OK(c, launch_ms_prep(c, c->last_desc, (size_t)K * 64, c->B, c->last_nvalid, K, P, c->ms_fimg, img_bytes, c->tc_fnrm, c->tc_fnmax));
     c->tc_fvalid = true;
   }
-  const bool use_bound = K >= 256;
   for (int p0 = 0; p0 < n_pairs; p0 += 64) {
     const int np = (n_pairs - p0) < 64 ? (n_pairs - p0) : 64;
     MatchTcArgs a = {};
-    a.imgA = a.imgB = c->tc_fimg; a.nrmA = a.nrmB = c->tc_fnrm; a.rawA = a.rawB = c->last_desc;
+    a.imgA = a.imgB = (const float*)c->ms_fimg; a.nrmA = a.nrmB = c->tc_fnrm; a.rawA = a.rawB = c->last_desc;
     a.nA_dev = a.nB_dev = c->last_nvalid; a.nA_host = a.nB_host = K; a.rows_padded_A = a.rows_padded_B = P;
-    a.img_stride_A = a.img_stride_B = img_stride; a.raw_stride_A = a.raw_stride_B = (size_t)K * 64;
+    a.img_stride_A = a.img_stride_B = img_bytes; a.raw_stride_A = a.raw_stride_B = (size_t)K * 64;
     a.init = init; a.out_stride = K;
-    a.nrm_max_B = c->tc_fnmax; a.bound = use_bound ? c->tc_bound : nullptr;
+    a.nrm_max_B = c->tc_fnmax;
+    a.ms_counters = c->ms_counters; a.ms_mode = c->ms_mode;
     if (o[0] || o[1] || o[2]) {
       for (int p = 0; p < np; ++p) { a.pairs[2 * p] = pairs[2 * (p0 + p)]; a.pairs[2 * p + 1] = pairs[2 * (p0 + p) + 1]; }
       a.best_idx = o[0] ? o[0] + (size_t)p0 * K : nullptr; a.best_dist = o[1] ? o[1] + (size_t)p0 * K : nullptr;
       a.second_dist = o[2] ? o[2] + (size_t)p0 * K : nullptr;
-      if (use_bound) XFB_CUDA_OK(c, launch_match_bound(c, a, P / 128, np));
-      XFB_CUDA_OK(c, launch_match_tc(c, a, P / 128, np, false));
+      XFB_CUDA_OK(c, launch_match_stream(c, a, np, false));
     }
-    if (o[3] || o[4]) {
+    if (o[3] || o[4]) {   // column-wise best = row-wise best of the transposed problem
       for (int p = 0; p < np; ++p) { a.pairs[2 * p] = pairs[2 * (p0 + p) + 1]; a.pairs[2 * p + 1] = pairs[2 * (p0 + p)]; }
       a.best_idx = o[3] ? o[3] + (size_t)p0 * K : nullptr; a.best_dist = o[4] ? o[4] + (size_t)p0 * K : nullptr; a.second_dist = nullptr;
-      if (use_bound) XFB_CUDA_OK(c, launch_match_bound(c, a, P / 128, np));
-      XFB_CUDA_OK(c, launch_match_tc(c, a, P / 128, np, false));
+      XFB_CUDA_OK(c, launch_match_stream(c, a, np, false));
     }
   }
   return XFB_OK;
@@ -449,8 +372,7 @@ int xfb_create(xfb_ctx** out, const void* weights_blob, size_t n, int device, in
     }
     if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { c->err = cudaGetErrorString(e); r = XFB_ERR_CUDA; break; }
     c->stream = c->own_stream;
-    if (const char* mi = getenv("XFB_MATCH_IMPL")) c->match_impl = atoi(mi);
-    if (const char* md = getenv("XFB_MS_DEBUG")) {   // experiment switch: 0 = count pushes / verifications, 1 / 2 = timing modes (wrong results)
+    if (const char* md = getenv("XFB_MS_DEBUG")) {   // profiling aid (match_stream.cu): cycle counters of CTA (0,0); bit flags switch stages off (then results are WRONG)
       c->ms_mode = atoi(md);
       if ((e = cudaMalloc(&c->ms_counters, 256)) != cudaSuccess || (e = cudaMemset(c->ms_counters, 0, 256)) != cudaSuccess) { c->err = cudaGetErrorString(e); r = XFB_ERR_CUDA; break; }
     }   // experiment switch (0 = match_tc.cu, 1 / 2 = match_stream.cu)
@@ -489,7 +411,7 @@ void xfb_destroy(xfb_ctx* c) {
     fprintf(stderr, "[xfb] CTA(0,0) mma thread: cycles in tcgen05.mma issue %.0f, in tcgen05.commit %.0f, in tcgen05.fence %.0f, loop tail %.0f\n", h[14] / n, h[15] / n, h[16] / n, h[17] / n);
   }
   fr(c->ms_img[0]); fr(c->ms_img[1]); fr(c->ms_fimg); fr(c->ms_counters); fr(c->p_idx); fr(c->p_out);
-  fr(c->tc_fimg); fr(c->tc_fnrm); fr(c->tc_pairs); fr(c->tc_dbg); fr(c->tc_fnmax); fr(c->tc_bound); fr(c->tc_nmax[0]); fr(c->tc_nmax[1]);
+  fr(c->tc_fnrm); fr(c->tc_pairs); fr(c->tc_dbg); fr(c->tc_fnmax); fr(c->tc_nmax[0]); fr(c->tc_nmax[1]);
   for (auto& s : c->slots) {
     fr(s.d_gray); fr(s.nvalid); fr(s.xy); fr(s.score); fr(s.desc);
     for (int i = 0; i < 5; ++i) fr(s.m[i]);

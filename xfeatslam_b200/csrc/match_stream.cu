@@ -1,32 +1,42 @@
-// match_stream.cu -- brute-force 64-D descriptor matching as ONE streaming tcgen05 GEMM per direction.
+// match_stream.cu -- brute-force 64-D descriptor matching (best / second-best per row) as a streaming tcgen05 GEMM.
 //
-// Output contract (unchanged): the reference's INTEGER distance (ORBmatcher::DescriptorDistance,
-// src/ORBmatcher.cc:2242-2250: int(float(||a-b||^2) * 512), fp32 subtract + fp64 accumulate in index order) and its
-// best / second-best scan (src/ORBmatcher.cc:476-486: strict '<', ascending index), bit-exact w.r.t.
-// oracle/matcher_oracle.c.
+// Output contract: the reference's INTEGER distance (ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:2242-2250:
+// int(float(||a-b||^2) * 512), fp32 subtract + fp64 accumulate in index order) and its best / second-best scan
+// (src/ORBmatcher.cc:476-486: strict '<', ascending index), bit-exact w.r.t. oracle/matcher_oracle.c.  ||a-b||^2 has no GEMM
+// form that rounds like that, so the tensor cores FILTER and the few survivors are VERIFIED exactly.
 //
-// Design: FILTER on the tensor cores, VERIFY exactly on the few survivors.
 //   * ms_prep_kernel: every descriptor becomes ONE fp16 operand row with the norm folded into the contraction:
-//       as a ROW   : [ a_0 .. a_63 | 1 1 1 0 ... ]            (the constant tail is built in shared memory)
+//       as a ROW   : [ a_0 .. a_63 | 1 1 1 0 ... ]            (the constant tail is written straight into tensor memory)
 //       as a COLUMN: [ b_0 .. b_63 | p1 p2 p3 0 ... ],  p1 + p2 + p3 = -|b|^2 / 2  (three fp16 pieces, residual 2^-33)
 //     so the K = 80 GEMM yields  u_ij = a_i.b_j - |b_j|^2 / 2  directly and  t_ij = 512 |a_i|^2 - 1024 u_ij  ~  512 d_ij
-//     with  |t - 512 float(d)| <= e_i = 1.05 sqrt(|a_i|^2 max|b|^2) + small  (fp16 rounding of both operands, rigorous).
-//     Images are in the canonical K-major no-swizzle UMMA layout (16-byte K chunks 2048 B apart, 8-row groups 128 B
-//     apart): one 128-row block = one contiguous 20 KB bulk copy.
-//   * ms_kernel: RB x 128 rows per CTA stay in shared memory; the column blocks stream through a ring of bulk copies;
-//     5 UTCHMMA (kind::f16, M = N = 128, K = 16) per (row block, column block) into fp32 TMEM accumulators.
-//     Epilogue (16 warps, one thread per row and 32-column slice): ONE fmax per element and one compare per 32
-//     columns against the row's running threshold.  Elements that pass (a handful per row per match) update the
-//     row's shared APPROXIMATE top-2 (two shared-memory atomicMin) and are appended to a per-warp queue.
-//     Soundness: let T2 be the second-smallest approximate t of a row.  Two columns have exact D <= T2 + e, so every
-//     member of the exact top-2 has t_approx < T2 + 2e + 1 -- the push threshold (T2 only decreases).  With a finite
-//     init_dist (256 in SearchByBoW) the threshold is also capped at init + e.
-//   * verification: the queues are drained warp-wide (32 survivors at a time, one lane each, so the 64-step fp64
-//     chain of the exact distance is paid once per 32 candidates instead of once per candidate): entries still under
-//     the final threshold get the exact distance and enter the row's exact top-2 -- two 64-bit shared-memory
-//     atomicMin on keys (D << 32 | column), i.e. the total order (distance, index) = the reference's scan order.
+//     with  |t - 512 float(d)| <= e_i = 1.05 sqrt(|a_i|^2 max|b|^2) + small  (fp16 rounding of both operands, rigorous;
+//     descriptors must fit fp16: |x| < 6e4 -- XFeat descriptors are unit vectors).  Images are in the canonical K-major
+//     no-swizzle UMMA layout (16-byte K chunks 2048 B apart, 8-row groups 128 B apart): a 128-row block = one 20 KB bulk copy.
+//   * ms_kernel, one CTA per (128 rows, frame pair): the row block is copied ONCE into tensor memory (tcgen05.st, columns
+//     384..423) and used as the A operand from there (tcgen05.mma with A in TMEM), so each 128 x 128 x 16 MMA reads only its
+//     4 KB column slice from shared memory.  The column blocks stream through a 7-stage ring of bulk copies into three
+//     128-column fp32 accumulators; 5 UTCHMMA (kind::f16) per accumulator.  The columns are streamed TWICE:
+//       pass 1  epilogue = one 3-input fmax per element: the maximum of every 32-column slice (kept in shared memory, fp16
+//               rounded up) and the row's two largest slice maxima.  The second-largest slice maximum is attained by a column
+//               other than the one of the largest, so T2 = 512|a|^2 - 1024 * (it) bounds the row's second-smallest t.
+//               Two columns have exact D <= T2 + e, hence every member of the exact top-2 has t < T2 + 2e + 1: the
+//               threshold is FINAL after pass 1 (with a finite init_dist -- 256 in SearchByBoW -- it is also capped at init + e).
+//       pass 2  only slices whose recorded maximum passes the threshold are read back from tensor memory (43 % at
+//               4096 x 4096); a branch-free compare builds a 32-bit survivor mask per row and slice, survivors (3.6 per row on
+//               XFeat descriptors) go to a per-warp queue.
+//     Verification: a warp drains its queue 32 survivors at a time, one per lane, so the 64-step fp64 chain of the exact
+//     distance is paid once per 32 survivors; results enter the row's exact top-2 with two 64-bit shared-memory atomicMin on
+//     keys (D << 32 | column), i.e. the total order (distance, index) = the reference's scan order.
+//     With vocabulary-node gating (group ids) pass 1 is skipped: the threshold is init + e alone.
+//   * Column-wise best (mutual-NN checks) = the same kernel on the transposed problem (distances are symmetric bit for bit).
 //
-// Warp roles (576 threads): warp 0 = loader, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2..17 = epilogue.
+// Warp roles (448 threads): warp 0 = loader, warp 1 = TMEM allocator + MMA issuer (ONE lane elected with elect.sync runs the
+// whole issue loop: barrier polls, UTCHMMA, UTCBAR), warps 2..13 = epilogue, three groups of four warps (one per TMEM lane
+// quadrant); group g owns accumulator g, i.e. the tiles g, g + 3, ...  -- every accumulator barrier is followed phase by phase
+// by ONE group (mbarrier parity waits alias when a waiter skips phases).
+// Measured (tools/tmem_bench.cu, B200): tcgen05.ld 32x32b.x32 + wait = 48 clk for one warp, >= 900 B/clk/SM with 16 warps;
+// kind::f16 M128 N128 K16 = 64 clk per MMA from shared or tensor memory: neither is what bounds this kernel -- the
+// per-tile barrier handshakes of the issuing lane are (profiles/).
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -40,9 +50,7 @@ constexpr int MS_ROWS = 128;                       // rows (or columns) per oper
 constexpr int MS_ACC = 3;                          // accumulator stages (3 x 128 TMEM columns; the row operand lives in columns 384..423)
 constexpr uint32_t MS_A_COL = 384;
 constexpr uint32_t MS_LBO = 2048, MS_SBO = 128;    // bytes between 16-byte K chunks / between 8-row groups
-constexpr int MS_DATA_BYTES = 8 * 2048;            // 64 fp16 of 128 rows
 constexpr int MS_BLK_BYTES = 10 * 2048;            // + the two K chunks of the column tail
-constexpr int MS_ONES_BYTES = 2 * 2048;            // the constant row tail
 constexpr int MS_STAGES = 7;                       // column blocks in flight
 constexpr int MS_REC_SLICES = 128;                 // pass-1 slice maxima kept for up to 128 slices (4096 columns)
 constexpr int MS_PARTS = 4;                        // 32-column slices per block = epilogue threads per row
@@ -429,7 +437,7 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ms_kernel(const MatchTcArgs a) 
     const float thr = fminf(__uint_as_float(need2 ? sT2[rs] : sT1[rs]) + margin, cap);
     const float tau = ok ? ((thr == CUDART_INF_F) ? -CUDART_INF_F : (base - thr - 1e-3f) * (1.0f / 1024.0f)) : CUDART_INF_F;
 
-    // ---- pass 2: collect the survivors (u > tau) into the ring ----
+    // ---- pass 2: collect the survivors (u > tau) ----
 #pragma unroll 1
     for (; k < total; k += GROUPS) {
       const int c = k - (passes - 1) * nblk;
@@ -535,7 +543,7 @@ cudaError_t launch_ms_prep(Ctx* c, const float* desc, size_t set_stride, int n_s
 }
 
 // img_stride_A / img_stride_B of `a` are in BYTES here.
-cudaError_t launch_match_stream(Ctx* c, const MatchTcArgs& a, int n_pairs, bool grouped, int) {
+cudaError_t launch_match_stream(Ctx* c, const MatchTcArgs& a, int n_pairs, bool grouped) {
   return grouped ? launch_ms<true>(c, a, n_pairs) : launch_ms<false>(c, a, n_pairs);
 }
 

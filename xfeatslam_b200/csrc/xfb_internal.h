@@ -138,23 +138,18 @@ struct Ctx {
   int m_cap = 0;
   int32_t* m_pairs_out[5] = {};   // [n_pairs][topk] staging for xfb_match_frame_pairs
   int m_pairs_cap = 0;
-  // tensor-core matcher operand images (match_tc.cu): [set][block][hi 32 KB | lo 32 KB], norms [set][rows_padded]
+  // distance-matrix operand images (match_tc.cu): [set][block][a1 16 KB | a2 16 KB] bf16, norms [set][rows_padded]
   float* tc_img[2] = {};          // generic A / B sets (xfb_match, xfb_distance_matrix)
   float* tc_nrm[2] = {};
   int tc_cap = 0;                 // rows (multiple of 128) the generic images hold
-  float* tc_fimg = nullptr;       // per-frame images of the last extract (xfb_match_frame*)
-  float* tc_fnrm = nullptr;
-  int tc_frows = 0;               // padded rows per frame of tc_fimg
-  bool tc_fvalid = false;         // images match the last extract result
+  float* tc_fnrm = nullptr;       // per-frame squared norms of the last extract (xfb_match_frame*), [frame][ms_frows]
+  bool tc_fvalid = false;         // the per-frame images (ms_fimg) match the last extract result
   int32_t* tc_pairs = nullptr;    // device copy of (pairs, swapped pairs)
   int tc_pairs_cap = 0;
   float* tc_dbg = nullptr;
   float* tc_nmax[2] = {};         // [1] largest squared norm of the generic A / B sets
   float* tc_fnmax = nullptr;      // [max_batch] same per frame
-  float* tc_bound = nullptr;      // [64 pairs][rows] bound-pass output
-  int tc_bound_rows = 0;
   // streaming matcher (match_stream.cu): fp16 operand images, 20 KB per 128-row block
-  int match_impl = 2;             // 0 = match_tc.cu (bound + 3-piece filter), 1 / 2 = match_stream.cu with 128 / 256 rows per CTA
   void* ms_img[2] = {};           // generic A / B sets
   int ms_cap = 0;                 // rows (multiple of 256) the generic images hold
   void* ms_fimg = nullptr;        // per-frame images of the last extract
@@ -193,7 +188,6 @@ struct MatchTcArgs {
   int32_t* best_idx; int32_t* best_dist; int32_t* second_dist;   // any may be null
   int32_t* matrix;                        // MATRIX mode: [nA][nB] exact distances
   float* dbg_maxerr;                      // MATRIX mode + debug: max |t - 512*float(S)|
-  float* bound;                           // [pair][rows_padded_A] upper bound of each row's second-best (bound pass), or nullptr
   const float* nrm_max_B;                 // [set] largest |b|^2 of each B set (bf16 error scale)
   unsigned long long* ms_counters;        // debug: [0] queue pushes, [1] verified survivors, [2] queue overflows (or nullptr)
   int ms_mode;                            // debug timing experiments (bit flags): 1 no candidate path, 2 no epilogue arithmetic, 4 no MMAs, 8 no tcgen05.ld, 16 no bulk copies
@@ -201,7 +195,7 @@ struct MatchTcArgs {
 
 // profiling tags: 0..L_NUM-1 = layers, then the stages below
 enum ProfTag { P_PREP_STATS = L_NUM, P_PREP_NORM, P_PYRAMID, P_HEATMAP_OUT, P_KEYPOINT_OUT, P_NMS, P_TOPK, P_DESCRIBE, P_MATCH_TILE,
-               P_DIST_PAIRS, P_DIST_MATRIX, P_MATCH_PREP, P_MATCH_BOUND, P_NUM };
+               P_DIST_PAIRS, P_DIST_MATRIX, P_MATCH_PREP, P_NUM };
 static_assert(P_NUM <= XFB_PROF_TAGS, "profile tag table");
 void prof_begin(Ctx* c, int tag);
 void prof_end(Ctx* c);
@@ -215,15 +209,13 @@ cudaError_t launch_keypoint_out(Ctx* c);                 // keypoint_head.3 + so
 cudaError_t launch_post(Ctx* c, int topk, float nms_thr, int32_t* d_nvalid, float* d_xy, float* d_score, float* d_desc);
 cudaError_t launch_match_prep(Ctx* c, const float* desc, size_t set_stride, int n_sets, const int32_t* n_dev, int n_host, int rows_padded,
                               float* img, size_t img_set_stride, float* nrm, float* nrm_max);
-cudaError_t launch_match_bound(Ctx* c, const MatchTcArgs& a, int row_tiles, int n_pairs);
-cudaError_t launch_match_tc(Ctx* c, const MatchTcArgs& a, int row_tiles, int n_pairs, bool grouped);
 cudaError_t launch_matrix_tc(Ctx* c, const MatchTcArgs& a, int row_tiles);
 cudaError_t launch_distance_pairs(Ctx* c, const float* dA, int n1, const float* dB, int n2, const int32_t* d_ia, const int32_t* d_ib, int n_pairs,
                                   int32_t* d_out);
 size_t ms_image_bytes(int rows_padded);
 cudaError_t launch_ms_prep(Ctx* c, const float* desc, size_t set_stride, int n_sets, const int32_t* n_dev, int n_host, int rows_padded,
                            void* img, size_t img_set_bytes, float* nrm, float* nrm_max);
-cudaError_t launch_match_stream(Ctx* c, const MatchTcArgs& a, int n_pairs, bool grouped, int rb);   // a.img_stride_* in BYTES
+cudaError_t launch_match_stream(Ctx* c, const MatchTcArgs& a, int n_pairs, bool grouped);   // a.img_stride_* in BYTES
 size_t conv_part_elems(int H, int W);
 size_t conv_tc_part_elems(int H, int W);
 size_t conv_small_part_elems(int H, int W);
