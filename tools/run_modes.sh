@@ -1,6 +1,4 @@
-timeout 150 python -m pytest tests -m gpu -q -x > gpurun_out/s19_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/s19_pytest.log
-for nc in 2; do
-timeout 100 python bench.py --steps 12 --warmup 3 --no-cpu-baseline --contexts $nc > gpurun_out/s19_bench_$nc.json 2> gpurun_out/s19_bench_$nc.err || { echo "bench $nc failed"; tail -3 gpurun_out/s19_bench_$nc.err; continue; }
+timeout 150 python -m pytest tests -m gpu -q -x > gpurun_out/s20_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/s20_pytest.log
+timeout 100 python bench.py --steps 12 --warmup 3 --no-cpu-baseline > gpurun_out/s20_bench.json 2> gpurun_out/s20_bench.err || { echo "bench failed"; tail -3 gpurun_out/s20_bench.err; }
 python -c "
-import json,sys;d=json.load(open(sys.argv[1]));print(sys.argv[2], round(d['value']), round(d['e2e']['value']), d['gpu_launches'], d['roofline']['kernel_ms_per_step'])" gpurun_out/s19_bench_$nc.json $nc
-done
+import json,sys;d=json.load(open(sys.argv[1]));print(round(d['value']), round(d['e2e']['value']), d['gpu_launches'], {k:v for k,v in d['roofline']['kernel_ms_per_step'].items() if k.startswith('match') or k.startswith('block3') or k.startswith('block2')})" gpurun_out/s20_bench.json

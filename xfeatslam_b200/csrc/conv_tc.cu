@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(CTC_THREADS, 1) conv_tc_kernel(const ConvTcArg
       mbar_arrive(bar_in);
     }
   } else if (warp == 8) {
-    // ===== weight loader: one bulk copy per (phase, tap) unit through the stage ring =====
-    if (lane == 0) {
+    // ===== weight loader (one elected lane): one bulk copy per (phase, tap) unit through the stage ring =====
+    if (elect_one_sync()) {
       for (int u = 0; u < C::UNITS; ++u) {
         const int s = u % NSTAGE;
         if (u >= NSTAGE) mbar_wait(bar_wempty + s, ((u / NSTAGE) - 1) & 1);

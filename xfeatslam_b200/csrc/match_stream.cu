@@ -306,9 +306,9 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ms_kernel(const MatchTcArgs a) 
 #pragma unroll 1
       for (int k = 0; k < total; ++k) {
         long long t0 = dbg ? clock64() : 0, t1;
-        mbar_wait(&sh->bar_full[s], sph);
+        if (k >= ACC) mbar_wait2(&sh->bar_full[s], sph, &sh->bar_acce[acc], aph ^ 1u);   // column block landed AND accumulator drained
+        else mbar_wait(&sh->bar_full[s], sph);
         if (dbg) { t1 = clock64(); c_full += t1 - t0; t0 = t1; }
-        if (k >= ACC) mbar_wait(&sh->bar_acce[acc], aph ^ 1u);
         tc_fence_after();
         if (dbg) { t1 = clock64(); c_acce += t1 - t0; t0 = t1; }
         const uint64_t db = db0 + (uint64_t)s * BSTAGE;

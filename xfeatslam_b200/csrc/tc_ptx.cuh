@@ -31,6 +31,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   }
 }
+// wait for two barriers at once: both polls are in flight together, so their latencies overlap (the MMA-issuing lane of
+// match_stream.cu needs a full smem stage AND a drained accumulator for every tile)
+__device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t parity_a, uint64_t* bar_b, uint32_t parity_b) {
+  uint32_t done = 0, spins = 0;
+  while (!done) {
+    if (++spins == (1u << 26)) __trap();
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4;\n\t"
+        "and.pred p, p, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar_a)), "r"(parity_a), "r"(smem_u32(bar_b)), "r"(parity_b)
+        : "memory");
+  }
+}
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
