@@ -185,7 +185,6 @@ __device__ __forceinline__ int ms_exact_distance(const float* arow, const float*
 struct MsShared {   // bookkeeping part of the dynamic shared memory (after the operand tiles)
   uint64_t bar_a, bar_full[MS_STAGES], bar_empty[MS_STAGES], bar_accf[MS_ACC], bar_acce[MS_ACC];
   uint32_t tmem;
-  uint32_t qcnt[MS_EPI_WARPS];
 };
 
 __device__ __forceinline__ void ms_top2_u32(unsigned int* k1, unsigned int* k2, unsigned int key) {
@@ -257,7 +256,6 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ms_kernel(const MatchTcArgs a) 
     sK1[r] = k0; sK2[r] = k0;
     sT1[r] = 0x7f800000u; sT2[r] = 0x7f800000u;
   }
-  if (threadIdx.x < MS_EPI_WARPS) sh->qcnt[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
     mbar_init(&sh->bar_a, 4);
     for (int s = 0; s < MS_STAGES; ++s) { mbar_init(&sh->bar_full[s], 1); mbar_init(&sh->bar_empty[s], 1); }
@@ -364,21 +362,19 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ms_kernel(const MatchTcArgs a) 
       if (lane == 0) mbar_arrive(&sh->bar_a);
     }
 
-    uint32_t* q = sQ + (size_t)ew * MS_QCAP;
-    uint32_t* qcnt = &sh->qcnt[ew];
+    uint32_t* q = sQ + (size_t)ew * MS_QCAP;         // this warp's survivor queue; its fill count `qn` is warp-uniform (a register)
+    int qn = 0;
     // survivors are verified warp-wide, 32 at a time (one per lane): the 64-step fp64 chain of the exact distance is paid
     // once per batch instead of once per survivor
     auto drain = [&]() {
       __syncwarp();
-      const int n = min((int)*qcnt, MS_QCAP);
-      for (int i = lane; i < n; i += 32) {
+      for (int i = lane; i < qn; i += 32) {
         const uint32_t ent = q[i];
         const int r = (int)(ent >> 24), j = (int)(ent & 0xffffffu);
         if (a.ms_counters && (a.ms_mode & 64)) atomicAdd(a.ms_counters + 1, 1ull);
         ms_verify(rawA + (size_t)(row0 + r) * 64, rawB + (size_t)j * 64, &sK1[r], &sK2[r], init_u, j);
       }
-      __syncwarp();
-      if (lane == 0) *qcnt = 0;
+      qn = 0;
       __syncwarp();
     };
 
@@ -465,24 +461,29 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ms_kernel(const MatchTcArgs a) 
         for (int e = 0; e < 32; ++e) mask |= (vv[e] > tau) ? (1u << e) : 0u;
         const int j0 = c * MS_ROWS + part * 32;
         if (j0 + 32 > nB) mask &= (nB > j0) ? (0xffffffffu >> (32 - (nB - j0))) : 0u;   // padded columns
-        while (mask) {
-          const int e = __ffs(mask) - 1;
-          mask &= mask - 1u;
-          const int j = j0 + e;
-          if (GROUPED && grp != a.gB[j]) continue;
-          if (a.ms_counters && (a.ms_mode & 64)) atomicAdd(a.ms_counters + 0, 1ull);
-          const uint32_t slot = atomicAdd(qcnt, 1u);
-          if (slot < (uint32_t)MS_QCAP) q[slot] = (uint32_t)j | ((uint32_t)rs << 24);
-          else {                                     // queue full (degenerate inputs): verify in place
-            if (a.ms_counters && (a.ms_mode & 64)) atomicAdd(a.ms_counters + 2, 1ull);
-            ms_verify(rawA + (size_t)(row0 + rs) * 64, rawB + (size_t)j * 64, &sK1[rs], &sK2[rs], init_u, j);
+        if (GROUPED) {   // vocabulary-node gating: drop the columns of other nodes
+          uint32_t keep = 0;
+          for (uint32_t mm = mask; mm; mm &= mm - 1u) { const int e = __ffs(mm) - 1; if (grp == a.gB[j0 + e]) keep |= 1u << e; }
+          mask = keep;
+        }
+        // warp-uniform append (no atomics): every round, each lane with survivors left contributes its lowest one
+        while (__any_sync(0xffffffffu, mask != 0u)) {
+          if (qn > MS_QCAP - 32) drain();           // (uniform) room for one round
+          const bool has = mask != 0u;
+          const uint32_t bal = __ballot_sync(0xffffffffu, has);
+          if (has) {
+            const int e = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            if (a.ms_counters && (a.ms_mode & 64)) atomicAdd(a.ms_counters + 0, 1ull);
+            q[qn + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)(j0 + e) | ((uint32_t)rs << 24);
           }
+          qn += __popc(bal);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh->bar_acce[acc]);
-      if (*qcnt >= (uint32_t)(MS_QCAP / 2)) drain();
+      if (qn >= MS_QCAP / 2) drain();
     }
     if (dbg && warp == 2 && lane == 0) atomicAdd(a.ms_counters + 10, (unsigned long long)(clock64() - t_start));   // end of pass 2
     drain();
