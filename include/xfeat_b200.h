@@ -123,6 +123,27 @@ int xfb_match_frame_pairs(xfb_ctx* ctx, const int32_t* pairs, int n_pairs, int i
 int xfb_match_frame_pairs_device(xfb_ctx* ctx, const int32_t* pairs, int n_pairs, int init_dist, int32_t* d_best_idx,
                                  int32_t* d_best_dist, int32_t* d_second_dist, int32_t* d_best_idx_rev, int32_t* d_best_dist_rev);
 
+/* ---- vocabulary tree walk ---------------------------------------------------
+ * Replaces the per-feature walk inside TemplatedVocabulary<FORB::TDescriptor, FORB>::transform
+ * (thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1218-1260, called from Frame::ComputeBoW src/Frame.cc:931-938 and
+ * KeyFrame::ComputeBoW) with FORB::distance (FORB.cpp:81-101) -- Hamming distance over the first 32 BYTES of the
+ * 64-float descriptor row, which is what the reference feeds DBoW2 for XFeat frames.
+ *
+ * xfb_vocab_load copies the tree: node 0 = root; the children of node i are child_index[child_start[i] .. child_start[i+1])
+ * in the order of m_nodes[i].children (loadFromTextFile, TemplatedVocabulary.h:1338-1420: the order of the file);
+ * node_desc[i] = the node's 32-byte ORB word; n_children == n_nodes - 1; L = m_L.
+ * xfb_bow_transform: leaf[i] = the node the walk ends in (word_id / weight are m_nodes[leaf].word_id / .weight on the
+ * host), nid[i] = the node passed at level L - levelsup (0 = root when L - levelsup <= 0; -1 if a leaf came first):
+ * BowVector / FeatureVector are then assembled on the host exactly like transform() (:1147-1190) does
+ * (xfeatslam_b200/host/XFBvocabulary.cc). */
+int xfb_vocab_load(xfb_ctx* ctx, const uint8_t* node_desc, const int32_t* child_start, const int32_t* child_index, int n_nodes, int n_children,
+                   int L);
+int xfb_bow_transform(xfb_ctx* ctx, const float* desc, int n, int levelsup, int32_t* leaf, int32_t* nid);
+int xfb_bow_transform_device(xfb_ctx* ctx, const float* d_desc, int n, int levelsup, int32_t* d_leaf, int32_t* d_nid);
+/* Every frame of the last xfb_extract_batch[_device] call in one launch (descriptors stay in HBM); outputs are DEVICE arrays
+ * [batch][topk], entries >= n_valid are -1; asynchronous on the ctx stream. */
+int xfb_bow_transform_frames_device(xfb_ctx* ctx, int levelsup, int32_t* d_leaf, int32_t* d_nid);
+
 /* ---- pipelined form for frame streams ------------------------------------------------------
  * xfb_submit enqueues one batch: host->device copy of the frames, extraction, (optionally) the frame-pair
  * matches of xfb_match_frame_pairs, and the device->host copies of every requested output -- on three CUDA

@@ -424,3 +424,49 @@ void mo_distinctive_descriptors(const float* D, const int32_t* offsets, int n_se
     free(row); free(dist);
   }
 }
+
+/* ---- DBoW2 vocabulary tree walk ----------------------------------------------------------------------------------
+ * FORB::distance, thirdparty/DBoW2/DBoW2/FORB.cpp:81-101: Hamming distance over 8 int32 words (the bit-count is the parallel
+ * bithack; the result equals popcount).  For XFeat frames `a` is a 1 x 64 CV_32F row, so the 8 words are the bit patterns of
+ * its first 8 floats; `b` is the node's 32-byte ORB word. */
+static int forb_distance(const uint32_t* pa, const uint32_t* pb) {
+  int dist = 0;
+  for (int i = 0; i < 8; i++) {
+    uint32_t v = pa[i] ^ pb[i];
+    v = v - ((v >> 1) & 0x55555555);
+    v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+    dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+  }
+  return dist;
+}
+
+/* TemplatedVocabulary::transform(feature, word_id, weight, nid, levelsup), TemplatedVocabulary.h:1218-1260, for n features.
+ * Tree as in xfb_vocab_load: node 0 = root, children of node i = child_index[child_start[i] .. child_start[i+1]) in
+ * m_nodes[i].children order.  leaf[i] = final_id (the caller maps it to word_id / weight), nid[i] = node at level L - levelsup
+ * (0 when L - levelsup <= 0; -1 where the reference would leave *nid unset because a leaf came first). */
+void mo_bow_transform(const float* desc, int n, const uint8_t* node_desc, const int32_t* child_start, const int32_t* child_index, int L,
+                      int levelsup, int32_t* leaf, int32_t* nid) {
+  const int nid_level = L - levelsup;
+  for (int i = 0; i < n; ++i) {
+    uint32_t f[8];
+    memcpy(f, desc + (size_t)i * XF_DIM, 32);
+    int final_id = 0, current_level = 0;
+    nid[i] = (nid_level <= 0) ? 0 : -1;
+    do {
+      ++current_level;
+      const int c0 = child_start[final_id], c1 = child_start[final_id + 1];
+      final_id = child_index[c0];
+      uint32_t w[8];
+      memcpy(w, node_desc + (size_t)final_id * 32, 32);
+      double best_d = forb_distance(f, w);
+      for (int c = c0 + 1; c < c1; ++c) {
+        const int id = child_index[c];
+        memcpy(w, node_desc + (size_t)id * 32, 32);
+        const double d = forb_distance(f, w);
+        if (d < best_d) { best_d = d; final_id = id; }
+      }
+      if (current_level == nid_level) nid[i] = final_id;
+    } while (child_start[final_id + 1] > child_start[final_id]);
+    leaf[i] = final_id;
+  }
+}

@@ -131,3 +131,12 @@ def distinctive_descriptors(D, offsets):
     best = np.empty(off.shape[0] - 1, np.int32)
     lib().mo_distinctive_descriptors(p, po, off.shape[0] - 1, best.ctypes.data_as(ctypes.c_void_p))
     return best
+
+
+def bow_transform(desc, node_desc, child_start, child_index, L, levelsup=4):
+    """TemplatedVocabulary::transform per feature (TemplatedVocabulary.h:1218-1260, FORB.cpp:81-101) -> (leaf node, node at L - levelsup)."""
+    D, p = _f(np.asarray(desc).reshape(-1, 64))
+    nd, pnd = _u8(np.asarray(node_desc).reshape(-1, 32)); cs, pcs = _i(child_start); ci, pci = _i(child_index)
+    leaf = np.empty(D.shape[0], np.int32); nid = np.empty(D.shape[0], np.int32)
+    lib().mo_bow_transform(p, D.shape[0], pnd, pcs, pci, int(L), int(levelsup), leaf.ctypes.data_as(ctypes.c_void_p), nid.ctypes.data_as(ctypes.c_void_p))
+    return leaf, nid

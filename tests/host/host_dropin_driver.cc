@@ -4,6 +4,7 @@
 // raw float files the Python test compares with the reference's golden output / the C oracle.
 //   extract <frame.u8> H W nfeatures lap0 lap1 <out_prefix>
 //   init    <descA.f32> nA <kpA.f32> <descB.f32> nB <kpB.f32> W H window ratio <out.i32>
+//   bow      <vocab.txt> <desc.f32> n levelsup <out_prefix>   (XFBvocabulary::loadFromTextFile + transform)
 //   searches <bundle.bin> <out.bin>   (SearchByBoW x2, SearchForTriangulation, SearchByProjection, ComputeDistinctiveDescriptors)
 #include <cstdio>
 #include <cstdlib>
@@ -15,6 +16,7 @@
 #include <vector>
 
 #include "XFBmatcher.h"
+#include "XFBvocabulary.h"
 #include "XFextractor.h"
 
 template <typename T>
@@ -125,6 +127,32 @@ int main(int argc, char** argv) {
     spit(argv[13], pv);
     return 0;
   }
+  if (mode == "bow" && argc >= 7) {
+    const int n = std::atoi(argv[4]), levelsup = std::atoi(argv[5]);
+    auto d = slurp<float>(argv[3], static_cast<size_t>(n) * 64);
+    cv::Mat D(n, 64, CV_32F, d.data());
+    ORB_SLAM3::XFextractor ex(64, 1.2f, 8, 20, 7);   // only to own a context (created by the first extraction)
+    {
+      cv::Mat tiny(32, 64, CV_8UC1);
+      std::memset(tiny.data, 7, 32 * 64);
+      std::vector<cv::KeyPoint> tk; cv::Mat td; std::vector<int> lap = {0, 0};
+      ex(tiny, cv::Mat(), tk, td, lap);
+    }
+    ORB_SLAM3::XFBvocabulary voc = ORB_SLAM3::XFBvocabulary::loadFromTextFile(ex.context(), argv[2]);
+    ORB_SLAM3::XFBvocabulary::BowVector v;
+    ORB_SLAM3::XFBvocabulary::FeatureVector fv;
+    voc.transform(D, v, fv, levelsup);
+    std::vector<double> bow;                       // (word id, value) pairs in map order
+    for (auto& kv : v) { bow.push_back(static_cast<double>(kv.first)); bow.push_back(kv.second); }
+    std::vector<int> feat;                         // node id, count, indices ... in map order
+    for (auto& kv : fv) { feat.push_back(static_cast<int>(kv.first)); feat.push_back(static_cast<int>(kv.second.size())); for (unsigned int i : kv.second) feat.push_back(static_cast<int>(i)); }
+    const std::string pre = argv[6];
+    spit(pre + ".bow", bow);
+    spit(pre + ".fv", feat);
+    std::vector<int> meta = {voc.getBranchingFactor(), voc.getDepthLevels(), static_cast<int>(voc.size())};
+    spit(pre + ".meta", meta);
+    return 0;
+  }
   if (mode == "searches" && argc >= 4) {
     const Bundle b(argv[2]);
     ORB_SLAM3::XFextractor ex(64, 1.2f, 8, 20, 7);   // only to own a context (created by the first extraction)
@@ -187,6 +215,6 @@ int main(int argc, char** argv) {
     spit(argv[3], out);
     return 0;
   }
-  std::cerr << "usage: extract ... | init ... | searches ..." << std::endl;
+  std::cerr << "usage: extract ... | init ... | bow ... | searches ..." << std::endl;
   return 1;
 }

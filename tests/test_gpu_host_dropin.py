@@ -22,7 +22,7 @@ def driver():
     exe = out / "host_dropin_driver"
     host = REPO / "xfeatslam_b200" / "host"
     cmd = ["g++", "-std=c++17", "-O2", "-I", str(REPO / "oracle" / "refbuild" / "shim"), "-I", str(REPO / "include"), "-I", str(host),
-           str(REPO / "tests" / "host" / "host_dropin_driver.cc"), str(host / "XFextractor.cc"), str(host / "XFBmatcher.cc"),
+           str(REPO / "tests" / "host" / "host_dropin_driver.cc"), str(host / "XFextractor.cc"), str(host / "XFBmatcher.cc"), str(host / "XFBvocabulary.cc"),
            "-L", str(REPO / "xfeatslam_b200" / "lib"), "-lxfeat_b200", "-Wl,-rpath," + str(REPO / "xfeatslam_b200" / "lib"), "-o", str(exe)]
     subprocess.run(cmd, check=True)
     return exe
@@ -194,3 +194,63 @@ def test_node_gated_and_window_searches_replay_the_oracle(driver, tmp_path):
     assert n == wn and np.array_equal(m, wm) and n > 50
     _, best = take()
     assert np.array_equal(best, mo.distinctive_descriptors(dS, offsets))
+
+
+def test_vocabulary_transform_on_device(driver, tmp_path):
+    """xfb_vocab_load + xfb_bow_transform (csrc/bow.cu) against the C restatement of TemplatedVocabulary::transform / FORB::distance,
+    and XFBvocabulary (text loader + BowVector / FeatureVector bookkeeping) against the same assembled in Python."""
+    from tools import orbvoc
+    from xfeatslam_b200.capi import XFeatB200
+    voc = orbvoc.synthetic(k=10, L=4, seed=3)                       # 11 111 nodes, 10 000 words
+    frame = synthetic_frame(11, 480, 640)
+    ctx = XFeatB200(max_h=480, max_w=640, max_batch=2, max_topk=2000)
+    o = ctx.extract(np.stack([frame, synthetic_frame(12, 480, 640)]), 2000)
+    n = int(o["n_valid"][0])
+    desc = np.ascontiguousarray(o["desc"][0][:n])
+    ctx.vocab_load(voc["node_desc"], voc["child_start"], voc["child_index"], voc["L"])
+    for levelsup in (4, 2, 0):
+        leaf, nid = ctx.bow_transform(desc, levelsup)
+        wl, wn = mo.bow_transform(desc, voc["node_desc"], voc["child_start"], voc["child_index"], voc["L"], levelsup)
+        assert np.array_equal(leaf, wl) and np.array_equal(nid, wn)
+    # every frame of the batch in one launch, descriptors resident on the device
+    import torch
+    d_leaf = torch.zeros(2, 2000, dtype=torch.int32, device="cuda"); d_nid = torch.zeros(2, 2000, dtype=torch.int32, device="cuda")
+    ctx.extract(np.stack([frame, synthetic_frame(12, 480, 640)]), 2000)
+    ctx.bow_transform_frames(2, d_leaf.data_ptr(), d_nid.data_ptr())
+    torch.cuda.synchronize()
+    for b in range(2):
+        nb = int(o["n_valid"][b])
+        wl, wn = mo.bow_transform(o["desc"][b][:nb], voc["node_desc"], voc["child_start"], voc["child_index"], voc["L"], 2)
+        assert np.array_equal(d_leaf[b, :nb].cpu().numpy(), wl) and np.array_equal(d_nid[b, :nb].cpu().numpy(), wn)
+        assert np.all(d_leaf[b, nb:].cpu().numpy() == -1)
+    ctx.close()
+    # the C++ class: text file in, maps out
+    lines = ["%d %d 0 0" % (voc["k"], voc["L"])]
+    parent = np.zeros(voc["node_desc"].shape[0], np.int32)
+    for p in range(voc["node_desc"].shape[0]):
+        parent[voc["child_index"][voc["child_start"][p]:voc["child_start"][p + 1]]] = p
+    for i in range(1, voc["node_desc"].shape[0]):
+        lines.append("%d %d %s %r" % (parent[i], voc["is_leaf"][i], " ".join(str(int(b)) for b in voc["node_desc"][i]), float(voc["weight"][i])))
+    (tmp_path / "voc.txt").write_text("\n".join(lines) + "\n")
+    desc.tofile(tmp_path / "d.f32")
+    subprocess.run([str(driver), "bow", str(tmp_path / "voc.txt"), str(tmp_path / "d.f32"), str(n), "2", str(tmp_path / "out")], check=True)
+    meta = np.fromfile(str(tmp_path / "out") + ".meta", np.int32)
+    assert list(meta) == [10, 4, 10000]
+    bow = np.fromfile(str(tmp_path / "out") + ".bow", np.float64).reshape(-1, 2)
+    fv = np.fromfile(str(tmp_path / "out") + ".fv", np.int32)
+    # TemplatedVocabulary::transform (TemplatedVocabulary.h:1147-1193) for TF_IDF weighting (0) + L1 scoring (0), from the oracle's walk
+    wl, wn = mo.bow_transform(desc, voc["node_desc"], voc["child_start"], voc["child_index"], voc["L"], 2)
+    want_v, want_fv = {}, {}
+    for i in range(n):
+        w = float(voc["weight"][wl[i]])
+        if w > 0:
+            wid = int(voc["word_id"][wl[i]])
+            want_v[wid] = want_v.get(wid, 0.0) + w
+            want_fv.setdefault(int(wn[i]), []).append(i)
+    norm = sum(abs(x) for x in (want_v[k] for k in sorted(want_v)))
+    assert [int(k) for k in bow[:, 0]] == sorted(want_v)
+    np.testing.assert_array_equal(bow[:, 1], np.array([want_v[k] / norm for k in sorted(want_v)]))   # same op order -> same doubles
+    flat = []
+    for k in sorted(want_fv):
+        flat += [k, len(want_fv[k])] + want_fv[k]
+    assert fv.tolist() == flat and len(want_fv) > 50

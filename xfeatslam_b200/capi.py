@@ -18,7 +18,7 @@ INT_MAX = 2 ** 31 - 1
 SYMBOLS = [
     "xfb_create", "xfb_destroy", "xfb_last_error", "xfb_set_stream", "xfb_extract", "xfb_extract_batch",
     "xfb_extract_batch_device", "xfb_distance_matrix", "xfb_distance_matrix_device", "xfb_distance_pairs", "xfb_distance_pairs_device",
-    "xfb_match", "xfb_match_device",
+    "xfb_match", "xfb_match_device", "xfb_vocab_load", "xfb_bow_transform", "xfb_bow_transform_device", "xfb_bow_transform_frames_device",
     "xfb_submit", "xfb_wait", "xfb_match_frames", "xfb_match_frame_pairs", "xfb_match_frame_pairs_device", "xfb_profile_enable", "xfb_profile_read", "xfb_profile_tag_name",
     "xfb_debug_match_error", "xfb_debug_force_simt", "xfb_debug_read", "xfb_debug_read_stats", "xfb_debug_post", "xfb_debug_candidates", "xfb_launch_count",
 ]
@@ -49,6 +49,10 @@ def load_library(path=LIB_PATH):
     lib.xfb_distance_matrix_device.argtypes = lib.xfb_distance_matrix.argtypes
     lib.xfb_distance_pairs.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]
     lib.xfb_distance_pairs_device.argtypes = lib.xfb_distance_pairs.argtypes
+    lib.xfb_vocab_load.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]
+    lib.xfb_bow_transform.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
+    lib.xfb_bow_transform_device.argtypes = lib.xfb_bow_transform.argtypes
+    lib.xfb_bow_transform_frames_device.argtypes = [c_void_p, c_int, c_void_p, c_void_p]
     lib.xfb_match.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int] + [c_void_p] * 5
     lib.xfb_match_device.argtypes = lib.xfb_match.argtypes
     lib.xfb_submit.argtypes = [c_void_p, c_int, c_void_p, c_int, c_size_t, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
@@ -155,6 +159,21 @@ class XFeatB200:
         self._check(self.lib.xfb_distance_pairs(self.h, _ptr(A), A.shape[0], _ptr(B), B.shape[0], _ptr(ia), _ptr(ib), ia.shape[0], _ptr(out)),
                     "xfb_distance_pairs")
         return out
+
+    def vocab_load(self, node_desc, child_start, child_index, L):
+        nd = np.ascontiguousarray(node_desc, np.uint8).reshape(-1, 32)
+        cs = np.ascontiguousarray(child_start, np.int32); ci = np.ascontiguousarray(child_index, np.int32)
+        self._check(self.lib.xfb_vocab_load(self.h, _ptr(nd), _ptr(cs), _ptr(ci), nd.shape[0], ci.shape[0], int(L)), "xfb_vocab_load")
+
+    def bow_transform(self, desc, levelsup):
+        """(leaf node, node at level L - levelsup) per descriptor row (xfb_bow_transform)."""
+        D = np.ascontiguousarray(desc, np.float32).reshape(-1, 64)
+        leaf = np.zeros(D.shape[0], np.int32); nid = np.zeros(D.shape[0], np.int32)
+        self._check(self.lib.xfb_bow_transform(self.h, _ptr(D), D.shape[0], int(levelsup), _ptr(leaf), _ptr(nid)), "xfb_bow_transform")
+        return leaf, nid
+
+    def bow_transform_frames(self, levelsup, leaf_ptr, nid_ptr):
+        self._check(self.lib.xfb_bow_transform_frames_device(self.h, int(levelsup), c_void_p(leaf_ptr), c_void_p(nid_ptr)), "xfb_bow_transform_frames_device")
 
     def match(self, A, B, group_a=None, group_b=None, init=INT_MAX):
         A = np.ascontiguousarray(A, np.float32).reshape(-1, 64); B = np.ascontiguousarray(B, np.float32).reshape(-1, 64)

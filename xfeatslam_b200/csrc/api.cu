@@ -39,7 +39,7 @@ void prof_end(Ctx* c) {
   c->prof_ev.push_back(e);
 }
 static const char* kStageNames[] = {"prep_stats", "prep_norm", "pyramid_sum", "heatmap_out", "keypoint_out_softmax_fold", "nms_score",
-                                    "topk_select_sort", "describe", "match_tile", "distance_pairs", "distance_matrix", "match_prep"};
+                                    "topk_select_sort", "describe", "match_tile", "distance_pairs", "distance_matrix", "match_prep", "bow_transform"};
 
 // ---- weight blob (tools/convert_weights.py) --------------------------------------------------------
 #pragma pack(push, 1)
@@ -410,7 +410,7 @@ void xfb_destroy(xfb_ctx* c) {
             h[12] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n, h[7] / n, h[8] / n, h[9] / n, h[10] / n, h[11] / n);
     fprintf(stderr, "[xfb] CTA(0,0) mma thread: cycles in tcgen05.mma issue %.0f, in tcgen05.commit %.0f, in tcgen05.fence %.0f, loop tail %.0f\n", h[14] / n, h[15] / n, h[16] / n, h[17] / n);
   }
-  fr(c->ms_img[0]); fr(c->ms_img[1]); fr(c->ms_fimg); fr(c->ms_counters); fr(c->p_idx); fr(c->p_out);
+  fr(c->ms_img[0]); fr(c->ms_img[1]); fr(c->ms_fimg); fr(c->ms_counters); fr(c->p_idx); fr(c->p_out); fr(c->v_desc); fr(c->v_start); fr(c->v_child); fr(c->v_out);
   fr(c->tc_fnrm); fr(c->tc_pairs); fr(c->tc_dbg); fr(c->tc_fnmax); fr(c->tc_nmax[0]); fr(c->tc_nmax[1]);
   for (auto& s : c->slots) {
     fr(s.d_gray); fr(s.nvalid); fr(s.xy); fr(s.score); fr(s.desc);
@@ -499,6 +499,69 @@ int xfb_distance_matrix(xfb_ctx* c, const float* A, int n1, const float* B, int 
   if (r != XFB_OK) return r;
   XFB_CUDA_OK(c, cudaMemcpyAsync(out, c->m_matrix, (size_t)n1 * n2 * 4, cudaMemcpyDeviceToHost, c->stream));
   XFB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return XFB_OK;
+}
+
+// ---- vocabulary tree walk (bow.cu) -----------------------------------------------------------------------------
+int xfb_vocab_load(xfb_ctx* c, const uint8_t* node_desc, const int32_t* child_start, const int32_t* child_index, int n_nodes, int n_children, int L) {
+  if (!c) return XFB_ERR_ARG;
+  if (!node_desc || !child_start || !child_index || n_nodes < 2 || n_children != n_nodes - 1 || L < 1 || child_start[0] != 0 ||
+      child_start[n_nodes] != n_children || child_start[1] <= 0) { c->err = "vocab_load: bad argument"; return XFB_ERR_ARG; }
+  for (int i = 0; i < n_nodes; ++i) if (child_start[i + 1] < child_start[i]) { c->err = "vocab_load: child_start is not monotone"; return XFB_ERR_ARG; }
+  for (int k = 0; k < n_children; ++k) if (child_index[k] <= 0 || child_index[k] >= n_nodes) { c->err = "vocab_load: child index out of range"; return XFB_ERR_ARG; }
+  XFB_CUDA_OK(c, cudaSetDevice(c->device));
+  XFB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  auto fr = [](void* p) { if (p) cudaFree(p); };
+  fr(c->v_desc); fr(c->v_start); fr(c->v_child);
+  c->v_desc = nullptr; c->v_start = nullptr; c->v_child = nullptr; c->v_nodes = 0;
+  XFB_ALLOC(c, c->v_desc, (size_t)n_nodes * 32);
+  XFB_ALLOC(c, c->v_start, (size_t)(n_nodes + 1) * 4);
+  XFB_ALLOC(c, c->v_child, (size_t)n_children * 4);
+  XFB_CUDA_OK(c, cudaMemcpy(c->v_desc, node_desc, (size_t)n_nodes * 32, cudaMemcpyHostToDevice));
+  XFB_CUDA_OK(c, cudaMemcpy(c->v_start, child_start, (size_t)(n_nodes + 1) * 4, cudaMemcpyHostToDevice));
+  XFB_CUDA_OK(c, cudaMemcpy(c->v_child, child_index, (size_t)n_children * 4, cudaMemcpyHostToDevice));
+  c->v_nodes = n_nodes; c->v_L = L;
+  return XFB_OK;
+}
+
+int xfb_bow_transform_device(xfb_ctx* c, const float* d_desc, int n, int levelsup, int32_t* d_leaf, int32_t* d_nid) {
+  if (!c) return XFB_ERR_ARG;
+  if (!c->v_nodes) { c->err = "bow_transform: no vocabulary loaded (xfb_vocab_load)"; return XFB_ERR_ARG; }
+  if (n < 0 || (n && (!d_desc || !d_leaf || !d_nid))) { c->err = "bow_transform: bad argument"; return XFB_ERR_ARG; }
+  XFB_CUDA_OK(c, cudaSetDevice(c->device));
+  XFB_CUDA_OK(c, launch_bow_transform(c, d_desc, 0, 1, nullptr, n, levelsup, d_leaf, d_nid, n));
+  return XFB_OK;
+}
+
+int xfb_bow_transform(xfb_ctx* c, const float* desc, int n, int levelsup, int32_t* leaf, int32_t* nid) {
+  if (!c) return XFB_ERR_ARG;
+  if (!c->v_nodes) { c->err = "bow_transform: no vocabulary loaded (xfb_vocab_load)"; return XFB_ERR_ARG; }
+  if (n < 0 || (n && (!desc || !leaf || !nid))) { c->err = "bow_transform: bad argument"; return XFB_ERR_ARG; }
+  if (n == 0) return XFB_OK;
+  XFB_CUDA_OK(c, cudaSetDevice(c->device));
+  int r = ensure_match_scratch(c, n, 0, false);
+  if (r != XFB_OK) return r;
+  if (n > c->v_out_cap) {
+    if (c->v_out) cudaFree(c->v_out);
+    c->v_out = nullptr; c->v_out_cap = 0;
+    XFB_ALLOC(c, c->v_out, (size_t)c->m_cap * 2 * 4);
+    c->v_out_cap = c->m_cap;
+  }
+  XFB_CUDA_OK(c, cudaMemcpyAsync(c->m_a, desc, (size_t)n * 64 * 4, cudaMemcpyHostToDevice, c->stream));
+  XFB_CUDA_OK(c, launch_bow_transform(c, c->m_a, 0, 1, nullptr, n, levelsup, c->v_out, c->v_out + c->v_out_cap, n));
+  XFB_CUDA_OK(c, cudaMemcpyAsync(leaf, c->v_out, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  XFB_CUDA_OK(c, cudaMemcpyAsync(nid, c->v_out + c->v_out_cap, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  XFB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return XFB_OK;
+}
+
+int xfb_bow_transform_frames_device(xfb_ctx* c, int levelsup, int32_t* d_leaf, int32_t* d_nid) {
+  if (!c) return XFB_ERR_ARG;
+  if (!c->v_nodes) { c->err = "bow_transform: no vocabulary loaded (xfb_vocab_load)"; return XFB_ERR_ARG; }
+  if (!c->last_desc || !d_leaf || !d_nid) { c->err = "bow_transform_frames: bad argument / no extract result"; return XFB_ERR_ARG; }
+  XFB_CUDA_OK(c, cudaSetDevice(c->device));
+  const int K = c->last_topk;
+  XFB_CUDA_OK(c, launch_bow_transform(c, c->last_desc, (size_t)K * 64, c->B, c->last_nvalid, K, levelsup, d_leaf, d_nid, K));
   return XFB_OK;
 }
 

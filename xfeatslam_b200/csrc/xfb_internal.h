@@ -154,6 +154,9 @@ struct Ctx {
   int ms_cap = 0;                 // rows (multiple of 256) the generic images hold
   void* ms_fimg = nullptr;        // per-frame images of the last extract
   int ms_frows = 0;
+  // vocabulary tree (bow.cu): node descriptors [n][32 B], CSR children; scratch for the host-pointer entry point
+  uint8_t* v_desc = nullptr; int32_t* v_start = nullptr; int32_t* v_child = nullptr; int v_nodes = 0, v_L = 0;
+  int32_t* v_out = nullptr; int v_out_cap = 0;
   // pair-list distances (pairs.cu): staging for the host-pointer entry point
   int32_t* p_idx = nullptr; int32_t* p_out = nullptr; int p_cap = 0;
   unsigned long long* ms_counters = nullptr;   // debug (XFB_MS_DEBUG): device counters, see MatchTcArgs
@@ -195,7 +198,7 @@ struct MatchTcArgs {
 
 // profiling tags: 0..L_NUM-1 = layers, then the stages below
 enum ProfTag { P_PREP_STATS = L_NUM, P_PREP_NORM, P_PYRAMID, P_HEATMAP_OUT, P_KEYPOINT_OUT, P_NMS, P_TOPK, P_DESCRIBE, P_MATCH_TILE,
-               P_DIST_PAIRS, P_DIST_MATRIX, P_MATCH_PREP, P_NUM };
+               P_DIST_PAIRS, P_DIST_MATRIX, P_MATCH_PREP, P_BOW, P_NUM };
 static_assert(P_NUM <= XFB_PROF_TAGS, "profile tag table");
 void prof_begin(Ctx* c, int tag);
 void prof_end(Ctx* c);
@@ -212,6 +215,8 @@ cudaError_t launch_match_prep(Ctx* c, const float* desc, size_t set_stride, int 
 cudaError_t launch_matrix_tc(Ctx* c, const MatchTcArgs& a, int row_tiles);
 cudaError_t launch_distance_pairs(Ctx* c, const float* dA, int n1, const float* dB, int n2, const int32_t* d_ia, const int32_t* d_ib, int n_pairs,
                                   int32_t* d_out);
+cudaError_t launch_bow_transform(Ctx* c, const float* d_desc, size_t set_stride, int n_sets, const int32_t* n_dev, int n_host, int levelsup,
+                                 int32_t* d_leaf, int32_t* d_nid, int out_stride);
 size_t ms_image_bytes(int rows_padded);
 cudaError_t launch_ms_prep(Ctx* c, const float* desc, size_t set_stride, int n_sets, const int32_t* n_dev, int n_host, int rows_padded,
                            void* img, size_t img_set_bytes, float* nrm, float* nrm_max);
