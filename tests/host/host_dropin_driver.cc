@@ -17,7 +17,9 @@
 
 #include "XFBmatcher.h"
 #include "XFBvocabulary.h"
+#ifndef XFB_CPU_STUB
 #include "XFextractor.h"
+#endif
 
 template <typename T>
 static std::vector<T> slurp(const std::string& p, size_t n) {
@@ -68,8 +70,26 @@ static std::vector<cv::KeyPoint> keypoints(const std::vector<float>& xy) {
   return k;
 }
 
+// The GPU build owns a real context through XFextractor; the CPU build of this driver (-DXFB_CPU_STUB, linked against
+// tests/host/cpu_stub.cc instead of libxfeat_b200.so) checks the HOST logic only and never dereferences the context.
+#ifdef XFB_CPU_STUB
+struct ContextOwner { xfb_ctx* context() { return reinterpret_cast<xfb_ctx*>(this); } };
+#else
+struct ContextOwner {
+  ORB_SLAM3::XFextractor ex;
+  ContextOwner() : ex(64, 1.2f, 8, 20, 7) {   // the context is created by the first extraction
+    cv::Mat tiny(32, 64, CV_8UC1);
+    std::memset(tiny.data, 7, 32 * 64);
+    std::vector<cv::KeyPoint> tk; cv::Mat td; std::vector<int> lap = {0, 0};
+    ex(tiny, cv::Mat(), tk, td, lap);
+  }
+  xfb_ctx* context() { return ex.context(); }
+};
+#endif
+
 int main(int argc, char** argv) {
   const std::string mode = argc > 1 ? argv[1] : "";
+#ifndef XFB_CPU_STUB
   if (mode == "extract" && argc >= 9) {
     const int H = std::atoi(argv[3]), W = std::atoi(argv[4]), nfeat = std::atoi(argv[5]);
     std::vector<int> lap = {std::atoi(argv[6]), std::atoi(argv[7])};
@@ -95,6 +115,7 @@ int main(int argc, char** argv) {
     spit(pre + ".meta", meta);
     return 0;
   }
+#endif
   if (mode == "init" && argc >= 14) {
     const int nA = std::atoi(argv[3]), nB = std::atoi(argv[6]);
     auto dA = slurp<float>(argv[2], static_cast<size_t>(nA) * 64), kA = slurp<float>(argv[4], static_cast<size_t>(nA) * 2);
@@ -106,11 +127,7 @@ int main(int argc, char** argv) {
     std::vector<cv::Point2f> prev(nA);
     for (int i = 0; i < nA; ++i) { ka[i] = cv::KeyPoint(kA[2 * i], kA[2 * i + 1], 1, -1, 1.f); prev[i] = ka[i].pt; }
     for (int i = 0; i < nB; ++i) kb[i] = cv::KeyPoint(kB[2 * i], kB[2 * i + 1], 1, -1, 1.f);
-    ORB_SLAM3::XFextractor ex(64, 1.2f, 8, 20, 7);   // only to own a context
-    cv::Mat tiny(32, 64, CV_8UC1);
-    std::memset(tiny.data, 7, 32 * 64);
-    std::vector<cv::KeyPoint> tk; cv::Mat td; std::vector<int> lap = {0, 0};
-    ex(tiny, cv::Mat(), tk, td, lap);
+    ContextOwner ex;
     ORB_SLAM3::XFBmatcher m(ex.context(), ratio, true);
     std::vector<int> m12;
     const int n = m.SearchForInitialization(ka, A, kb, B, 0.f, 0.f, static_cast<float>(W), static_cast<float>(H), prev, m12, window);
@@ -131,13 +148,7 @@ int main(int argc, char** argv) {
     const int n = std::atoi(argv[4]), levelsup = std::atoi(argv[5]);
     auto d = slurp<float>(argv[3], static_cast<size_t>(n) * 64);
     cv::Mat D(n, 64, CV_32F, d.data());
-    ORB_SLAM3::XFextractor ex(64, 1.2f, 8, 20, 7);   // only to own a context (created by the first extraction)
-    {
-      cv::Mat tiny(32, 64, CV_8UC1);
-      std::memset(tiny.data, 7, 32 * 64);
-      std::vector<cv::KeyPoint> tk; cv::Mat td; std::vector<int> lap = {0, 0};
-      ex(tiny, cv::Mat(), tk, td, lap);
-    }
+    ContextOwner ex;
     ORB_SLAM3::XFBvocabulary voc = ORB_SLAM3::XFBvocabulary::loadFromTextFile(ex.context(), argv[2]);
     ORB_SLAM3::XFBvocabulary::BowVector v;
     ORB_SLAM3::XFBvocabulary::FeatureVector fv;
@@ -155,13 +166,7 @@ int main(int argc, char** argv) {
   }
   if (mode == "searches" && argc >= 4) {
     const Bundle b(argv[2]);
-    ORB_SLAM3::XFextractor ex(64, 1.2f, 8, 20, 7);   // only to own a context (created by the first extraction)
-    {
-      cv::Mat tiny(32, 64, CV_8UC1);
-      std::memset(tiny.data, 7, 32 * 64);
-      std::vector<cv::KeyPoint> tk; cv::Mat td; std::vector<int> lap = {0, 0};
-      ex(tiny, cv::Mat(), tk, td, lap);
-    }
+    ContextOwner ex;
     std::vector<float> dA = b.get<float>("dA"), dB = b.get<float>("dB");
     const int nA = static_cast<int>(dA.size() / 64), nB = static_cast<int>(dB.size() / 64);
     cv::Mat A(nA, 64, CV_32F, dA.data()), B(nB, 64, CV_32F, dB.data());
