@@ -144,6 +144,28 @@ int xfb_bow_transform_device(xfb_ctx* ctx, const float* d_desc, int n, int level
  * [batch][topk], entries >= n_valid are -1; asynchronous on the ctx stream. */
 int xfb_bow_transform_frames_device(xfb_ctx* ctx, int levelsup, int32_t* d_leaf, int32_t* d_nid);
 
+/* ---- per-keypoint frame geometry -------------------------------------------
+ * What the reference's Frame constructor computes for every keypoint right after extraction (src/Frame.cc:289-345):
+ * Frame::UndistortKeyPoints (:940-973, cv::undistortPoints with K, mDistCoef, P = mK), Frame::ComputeStereoFromRGBD
+ * (:1177-1198) and the cell of Frame::AssignFeaturesToGrid / PosInGrid (:569-600, :918-928) -- one launch per frame. */
+typedef struct xfb_camera {
+  float fx, fy, cx, cy;               /* Pinhole::toK() == mK */
+  float k1, k2, p1, p2, k3;           /* mDistCoef (k3 = 0 for 4 coefficients); k1 == 0: keypoints are copied, as :942-946 */
+  float bf;                           /* mbf (stereo baseline times fx) */
+  float min_x, min_y, max_x, max_y;   /* mnMinX, mnMinY, mnMaxX, mnMaxY: filled by xfb_image_bounds */
+} xfb_camera;
+/* Frame::ComputeImageBounds (src/Frame.cc:975-1003): undistorted image corners -> cam->min_x .. max_y.  Host only, no ctx. */
+int xfb_image_bounds(xfb_camera* cam, int w, int h);
+/* xy [n,2]: keypoint positions as XFextractor packs them (mvKeys[i].pt, phantom (0,0) rows included); depth: the CV_32F depth
+ * image in metres (after mDepthMapFactor), `depth_stride` floats per row, NULL for monocular frames.  Outputs (any may be
+ * NULL): un_xy [n,2] = mvKeysUn[i].pt; kp_depth [n] = mvDepth; uright [n] = mvuRight (both -1 without a positive depth);
+ * cell [n] = posX * 48 + posY of mGrid[posX][posY], -1 when PosInGrid fails.  Host pointers, synchronous. */
+int xfb_keypoint_geometry(xfb_ctx* ctx, const float* xy, int n, const float* depth, int h, int w, int depth_stride, const xfb_camera* cam,
+                          float* un_xy, float* kp_depth, float* uright, int32_t* cell);
+/* Device pointers, asynchronous on the ctx stream. */
+int xfb_keypoint_geometry_device(xfb_ctx* ctx, const float* d_xy, int n, const float* d_depth, int h, int w, int depth_stride,
+                                 const xfb_camera* cam, float* d_un_xy, float* d_kp_depth, float* d_uright, int32_t* d_cell);
+
 /* ---- pipelined form for frame streams ------------------------------------------------------
  * xfb_submit enqueues one batch: host->device copy of the frames, extraction, (optionally) the frame-pair
  * matches of xfb_match_frame_pairs, and the device->host copies of every requested output -- on three CUDA

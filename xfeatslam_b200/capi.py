@@ -18,12 +18,21 @@ INT_MAX = 2 ** 31 - 1
 SYMBOLS = [
     "xfb_create", "xfb_destroy", "xfb_last_error", "xfb_set_stream", "xfb_extract", "xfb_extract_batch",
     "xfb_extract_batch_device", "xfb_distance_matrix", "xfb_distance_matrix_device", "xfb_distance_pairs", "xfb_distance_pairs_device",
-    "xfb_match", "xfb_match_device", "xfb_vocab_load", "xfb_bow_transform", "xfb_bow_transform_device", "xfb_bow_transform_frames_device",
+    "xfb_match", "xfb_match_device", "xfb_image_bounds", "xfb_keypoint_geometry", "xfb_keypoint_geometry_device", "xfb_vocab_load", "xfb_bow_transform", "xfb_bow_transform_device", "xfb_bow_transform_frames_device",
     "xfb_submit", "xfb_wait", "xfb_match_frames", "xfb_match_frame_pairs", "xfb_match_frame_pairs_device", "xfb_profile_enable", "xfb_profile_read", "xfb_profile_tag_name",
     "xfb_debug_match_error", "xfb_debug_force_simt", "xfb_debug_read", "xfb_debug_read_stats", "xfb_debug_post", "xfb_debug_candidates", "xfb_launch_count",
 ]
 
 _lib = None
+
+
+def image_bounds(cam, w, h):
+    """xfb_image_bounds: fills cam[10:14] (min_x, min_y, max_x, max_y) of a float32[14] camera array in place."""
+    cam = np.ascontiguousarray(cam, np.float32)
+    rc = load_library().xfb_image_bounds(_ptr(cam), int(w), int(h))
+    if rc != 0:
+        raise RuntimeError("xfb_image_bounds failed (%d)" % rc)
+    return cam
 
 
 def load_library(path=LIB_PATH):
@@ -49,6 +58,9 @@ def load_library(path=LIB_PATH):
     lib.xfb_distance_matrix_device.argtypes = lib.xfb_distance_matrix.argtypes
     lib.xfb_distance_pairs.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]
     lib.xfb_distance_pairs_device.argtypes = lib.xfb_distance_pairs.argtypes
+    lib.xfb_image_bounds.argtypes = [c_void_p, c_int, c_int]
+    lib.xfb_keypoint_geometry.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p] + [c_void_p] * 4
+    lib.xfb_keypoint_geometry_device.argtypes = lib.xfb_keypoint_geometry.argtypes
     lib.xfb_vocab_load.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]
     lib.xfb_bow_transform.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
     lib.xfb_bow_transform_device.argtypes = lib.xfb_bow_transform.argtypes
@@ -159,6 +171,19 @@ class XFeatB200:
         self._check(self.lib.xfb_distance_pairs(self.h, _ptr(A), A.shape[0], _ptr(B), B.shape[0], _ptr(ia), _ptr(ib), ia.shape[0], _ptr(out)),
                     "xfb_distance_pairs")
         return out
+
+    def keypoint_geometry(self, xy, depth, cam):
+        """(un_xy, depth, uright, cell) per keypoint (xfb_keypoint_geometry); cam: float32[14] = fx fy cx cy k1 k2 p1 p2 k3 bf minx miny maxx maxy."""
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2); n = xy.shape[0]
+        cam = np.ascontiguousarray(cam, np.float32)
+        un = np.zeros((n, 2), np.float32); kd = np.zeros(n, np.float32); ur = np.zeros(n, np.float32); cell = np.zeros(n, np.int32)
+        if depth is None:
+            dp, h, w, st = None, 0, 0, 0
+        else:
+            depth = np.ascontiguousarray(depth, np.float32); dp, (h, w), st = _ptr(depth), depth.shape, depth.shape[1]
+        self._check(self.lib.xfb_keypoint_geometry(self.h, _ptr(xy), n, dp, h, w, st, _ptr(cam), _ptr(un), _ptr(kd), _ptr(ur), _ptr(cell)),
+                    "xfb_keypoint_geometry")
+        return un, kd, ur, cell
 
     def vocab_load(self, node_desc, child_start, child_index, L):
         nd = np.ascontiguousarray(node_desc, np.uint8).reshape(-1, 32)

@@ -410,7 +410,7 @@ void xfb_destroy(xfb_ctx* c) {
             h[12] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n, h[7] / n, h[8] / n, h[9] / n, h[10] / n, h[11] / n);
     fprintf(stderr, "[xfb] CTA(0,0) mma thread: cycles in tcgen05.mma issue %.0f, in tcgen05.commit %.0f, in tcgen05.fence %.0f, loop tail %.0f\n", h[14] / n, h[15] / n, h[16] / n, h[17] / n);
   }
-  fr(c->ms_img[0]); fr(c->ms_img[1]); fr(c->ms_fimg); fr(c->ms_counters); fr(c->p_idx); fr(c->p_out); fr(c->v_desc); fr(c->v_start); fr(c->v_child); fr(c->v_out);
+  fr(c->ms_img[0]); fr(c->ms_img[1]); fr(c->ms_fimg); fr(c->ms_counters); fr(c->p_idx); fr(c->p_out); fr(c->g_buf); fr(c->v_desc); fr(c->v_start); fr(c->v_child); fr(c->v_out);
   fr(c->tc_fnrm); fr(c->tc_pairs); fr(c->tc_dbg); fr(c->tc_fnmax); fr(c->tc_nmax[0]); fr(c->tc_nmax[1]);
   for (auto& s : c->slots) {
     fr(s.d_gray); fr(s.nvalid); fr(s.xy); fr(s.score); fr(s.desc);
@@ -498,6 +498,53 @@ int xfb_distance_matrix(xfb_ctx* c, const float* A, int n1, const float* B, int 
   r = tc_matrix_generic(c, c->m_a, n1, c->m_b, n2, c->m_matrix, nullptr);
   if (r != XFB_OK) return r;
   XFB_CUDA_OK(c, cudaMemcpyAsync(out, c->m_matrix, (size_t)n1 * n2 * 4, cudaMemcpyDeviceToHost, c->stream));
+  XFB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return XFB_OK;
+}
+
+// ---- per-keypoint frame geometry (geom.cu) ---------------------------------------------------------------------
+int xfb_image_bounds(xfb_camera* cam, int w, int h) {
+  if (!cam || w <= 0 || h <= 0 || cam->fx == 0.f || cam->fy == 0.f) return XFB_ERR_ARG;
+  image_bounds_host(cam, w, h);
+  return XFB_OK;
+}
+
+int xfb_keypoint_geometry_device(xfb_ctx* c, const float* d_xy, int n, const float* d_depth, int h, int w, int depth_stride, const xfb_camera* cam,
+                                 float* d_un, float* d_kd, float* d_ur, int32_t* d_cell) {
+  if (!c) return XFB_ERR_ARG;
+  if (n < 0 || !cam || (n && !d_xy) || (d_depth && (h <= 0 || w <= 0 || depth_stride < w)) || cam->fx == 0.f || cam->fy == 0.f ||
+      (d_cell && (!(cam->max_x > cam->min_x) || !(cam->max_y > cam->min_y)))) { c->err = "keypoint_geometry: bad argument"; return XFB_ERR_ARG; }
+  XFB_CUDA_OK(c, cudaSetDevice(c->device));
+  XFB_CUDA_OK(c, launch_keypoint_geometry(c, d_xy, n, d_depth, h, w, depth_stride, *cam, d_un, d_kd, d_ur, d_cell));
+  return XFB_OK;
+}
+
+int xfb_keypoint_geometry(xfb_ctx* c, const float* xy, int n, const float* depth, int h, int w, int depth_stride, const xfb_camera* cam, float* un_xy,
+                          float* kp_depth, float* uright, int32_t* cell) {
+  if (!c) return XFB_ERR_ARG;
+  if (n < 0 || !cam || (n && !xy) || (depth && (h <= 0 || w <= 0 || depth_stride < w)) || cam->fx == 0.f || cam->fy == 0.f ||
+      (cell && (!(cam->max_x > cam->min_x) || !(cam->max_y > cam->min_y)))) { c->err = "keypoint_geometry: bad argument"; return XFB_ERR_ARG; }
+  if (n == 0) return XFB_OK;
+  XFB_CUDA_OK(c, cudaSetDevice(c->device));
+  const size_t img = depth ? (size_t)h * w * 4 : 0, pts = (size_t)n * 4;
+  const size_t need = img + pts * 7;   // depth | xy (2) | un (2) | depth out | uright | cell
+  if (need > c->g_cap) {
+    if (c->g_buf) cudaFree(c->g_buf);
+    c->g_buf = nullptr; c->g_cap = 0;
+    XFB_ALLOC(c, c->g_buf, need + (1 << 20));
+    c->g_cap = need + (1 << 20);
+  }
+  float* d_depth = depth ? c->g_buf : nullptr;
+  float* d_xy = reinterpret_cast<float*>(reinterpret_cast<char*>(c->g_buf) + img);
+  float* d_un = d_xy + 2 * (size_t)n; float* d_kd = d_un + 2 * (size_t)n; float* d_ur = d_kd + n;
+  int32_t* d_cell = reinterpret_cast<int32_t*>(d_ur + n);
+  if (depth) XFB_CUDA_OK(c, cudaMemcpy2DAsync(d_depth, (size_t)w * 4, depth, (size_t)depth_stride * 4, (size_t)w * 4, h, cudaMemcpyHostToDevice, c->stream));
+  XFB_CUDA_OK(c, cudaMemcpyAsync(d_xy, xy, pts * 2, cudaMemcpyHostToDevice, c->stream));
+  XFB_CUDA_OK(c, launch_keypoint_geometry(c, d_xy, n, d_depth, h, w, w, *cam, d_un, d_kd, d_ur, d_cell));
+  if (un_xy) XFB_CUDA_OK(c, cudaMemcpyAsync(un_xy, d_un, pts * 2, cudaMemcpyDeviceToHost, c->stream));
+  if (kp_depth) XFB_CUDA_OK(c, cudaMemcpyAsync(kp_depth, d_kd, pts, cudaMemcpyDeviceToHost, c->stream));
+  if (uright) XFB_CUDA_OK(c, cudaMemcpyAsync(uright, d_ur, pts, cudaMemcpyDeviceToHost, c->stream));
+  if (cell) XFB_CUDA_OK(c, cudaMemcpyAsync(cell, d_cell, pts, cudaMemcpyDeviceToHost, c->stream));
   XFB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return XFB_OK;
 }

@@ -157,6 +157,8 @@ struct Ctx {
   // vocabulary tree (bow.cu): node descriptors [n][32 B], CSR children; scratch for the host-pointer entry point
   uint8_t* v_desc = nullptr; int32_t* v_start = nullptr; int32_t* v_child = nullptr; int v_nodes = 0, v_L = 0;
   int32_t* v_out = nullptr; int v_out_cap = 0;
+  // keypoint geometry (geom.cu): staging for the host-pointer entry point
+  float* g_buf = nullptr; size_t g_cap = 0;      // bytes
   // pair-list distances (pairs.cu): staging for the host-pointer entry point
   int32_t* p_idx = nullptr; int32_t* p_out = nullptr; int p_cap = 0;
   unsigned long long* ms_counters = nullptr;   // debug (XFB_MS_DEBUG): device counters, see MatchTcArgs
@@ -217,6 +219,9 @@ cudaError_t launch_distance_pairs(Ctx* c, const float* dA, int n1, const float* 
                                   int32_t* d_out);
 cudaError_t launch_bow_transform(Ctx* c, const float* d_desc, size_t set_stride, int n_sets, const int32_t* n_dev, int n_host, int levelsup,
                                  int32_t* d_leaf, int32_t* d_nid, int out_stride);
+void image_bounds_host(xfb_camera* cam, int w, int h);
+cudaError_t launch_keypoint_geometry(Ctx* c, const float* d_xy, int n, const float* d_depth, int h, int w, int depth_stride, const xfb_camera& cam,
+                                     float* d_un, float* d_depth_out, float* d_uright, int32_t* d_cell);
 size_t ms_image_bytes(int rows_padded);
 cudaError_t launch_ms_prep(Ctx* c, const float* desc, size_t set_stride, int n_sets, const int32_t* n_dev, int n_host, int rows_padded,
                            void* img, size_t img_set_bytes, float* nrm, float* nrm_max);
