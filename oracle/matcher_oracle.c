@@ -470,3 +470,68 @@ void mo_bow_transform(const float* desc, int n, const uint8_t* node_desc, const 
     leaf[i] = final_id;
   }
 }
+
+/* Frame::GetFeaturesInArea with explicit level limits for keypoints that are all at octave 0 (src/Frame.cc:850-916). */
+static int grid_area_minmax(const mo_grid* g, const float* kxy, float x, float y, float r, int minLevel, int maxLevel, int* out) {
+  const int bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+  if (bCheckLevels) {
+    if (0 < minLevel) return 0;                      /* kpUn.octave < minLevel */
+    if (maxLevel >= 0 && 0 > maxLevel) return 0;     /* never true for octave 0 */
+  }
+  return grid_area(g, kxy, x, y, r, out);
+}
+
+/* ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono), src/ORBmatcher.cc:1861-2072, the
+ * TrackWithMotionModel search, CurrentFrame.Nleft == -1.  The caller projects the map points of LastFrame with the current pose
+ * (:1888-1903, Sophus / Eigen arithmetic, not restated): per last-frame feature i
+ *   valid[i]   : pMP && !mvbOutlier[i] && invzc >= 0 && the projection lies inside the image bounds
+ *   uv[i]      : projected position; invzc[i] : 1 / depth in the current camera; octave[i] : LastFrame.mvKeys[i].octave (0 for XFeat)
+ *   mp_obs[i]  : pMP->Observations() > 0
+ * forward / backward : bForward / bBackward (:1875-1876).  assign[i2] (out) = last-frame index whose MapPoint is written to
+ * CurrentFrame.mvpMapPoints[i2].  XFeat angles are all -1, so the rotation histogram removes nothing (:2047-2069). */
+int mo_search_by_projection_frames(const float* Dlast, const uint8_t* valid, const float* uv, const float* invzc, const int32_t* octave,
+                                   const uint8_t* mp_obs, int n_last, const float* Dcur, const float* kxy, const uint8_t* occupied_in,
+                                   const float* uright, int n_cur, int img_w, int img_h, float th, float scale_factor, float mbf, int forward,
+                                   int backward, int th_high, int32_t* assign) {
+  mo_grid g;
+  grid_build(&g, kxy, n_cur, img_w, img_h);
+  int* cand = (int*)malloc(sizeof(int) * (size_t)(n_cur > 0 ? n_cur : 1));
+  uint8_t* occupied = (uint8_t*)malloc((size_t)(n_cur > 0 ? n_cur : 1));
+  for (int j = 0; j < n_cur; ++j) { assign[j] = -1; occupied[j] = occupied_in[j]; }
+  int nmatches = 0;
+  for (int i = 0; i < n_last; ++i) {
+    if (!valid[i]) continue;
+    const int nLastOctave = octave[i];
+    float sf = 1.0f;
+    for (int l = 0; l < nLastOctave; ++l) sf *= scale_factor;
+    const float radius = th * sf;
+    int nc;
+    if (forward) nc = grid_area_minmax(&g, kxy, uv[2 * i], uv[2 * i + 1], radius, nLastOctave, -1, cand);
+    else if (backward) nc = grid_area_minmax(&g, kxy, uv[2 * i], uv[2 * i + 1], radius, 0, nLastOctave, cand);
+    else nc = grid_area_minmax(&g, kxy, uv[2 * i], uv[2 * i + 1], radius, nLastOctave - 1, nLastOctave + 1, cand);
+    if (nc == 0) continue;
+    int bestDist = 256, bestIdx2 = -1;
+    for (int c = 0; c < nc; ++c) {
+      const int i2 = cand[c];
+      if (occupied[i2]) continue;
+      if (uright[i2] > 0) {
+        const float ur = uv[2 * i] - mbf * invzc[i];
+        const float er = fabsf(ur - uright[i2]);
+        if (er > radius) continue;
+      }
+      const int dist = mo_descriptor_distance(Dlast + (size_t)i * XF_DIM, Dcur + (size_t)i2 * XF_DIM);
+      if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+    }
+    /* Reference: `if(bestDist<=TH_HIGH) CurrentFrame.mvpMapPoints[bestIdx2]=pMP;` (:1955-1958).  With XFeat TH_HIGH = 1000 > the
+     * initial bestDist 256, so when every candidate was skipped or is >= 256 away the reference writes mvpMapPoints[-1] (undefined
+     * behaviour, and counts a match).  Restated as "no match": bestIdx2 must be valid. */
+    if (bestDist <= th_high && bestIdx2 >= 0) {
+      assign[bestIdx2] = i;
+      occupied[bestIdx2] = mp_obs[i];
+      nmatches++;
+    }
+  }
+  free(cand); free(occupied);
+  grid_free(&g);
+  return nmatches;
+}

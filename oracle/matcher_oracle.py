@@ -140,3 +140,16 @@ def bow_transform(desc, node_desc, child_start, child_index, L, levelsup=4):
     leaf = np.empty(D.shape[0], np.int32); nid = np.empty(D.shape[0], np.int32)
     lib().mo_bow_transform(p, D.shape[0], pnd, pcs, pci, int(L), int(levelsup), leaf.ctypes.data_as(ctypes.c_void_p), nid.ctypes.data_as(ctypes.c_void_p))
     return leaf, nid
+
+
+def search_by_projection_frames(Dlast, valid, uv, invzc, octave, mp_obs, Dcur, kxy, occupied, uright, img_w, img_h, th=15.0, scale_factor=1.2,
+                                mbf=40.0, forward=False, backward=False, th_high=1000):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono), src/ORBmatcher.cc:1861-2072 -> (nmatches, assign[n_cur])."""
+    Dl, p1 = _f(Dlast); Dc, p2 = _f(Dcur); u, pu = _f(uv); iz, piz = _f(invzc); kk, pkk = _f(kxy); ur, pur = _f(uright)
+    va, pva = _u8(valid); ob, pob = _u8(mp_obs); oc, poc = _u8(occupied); ot, pot = _i(octave)
+    out = np.empty(Dc.shape[0], np.int32)
+    L = lib(); L.mo_search_by_projection_frames.restype = ctypes.c_int
+    n = L.mo_search_by_projection_frames(p1, pva, pu, piz, pot, pob, Dl.shape[0], p2, pkk, poc, pur, Dc.shape[0], int(img_w), int(img_h),
+                                         ctypes.c_float(th), ctypes.c_float(scale_factor), ctypes.c_float(mbf), int(forward), int(backward),
+                                         int(th_high), out.ctypes.data_as(ctypes.c_void_p))
+    return n, out

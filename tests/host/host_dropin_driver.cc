@@ -211,6 +211,21 @@ int main(int argc, char** argv) {
       put(m.SearchByProjection(pts, M, keypoints(b.get<float>("kF")), Fd, b.flags("occupied"), b.get<float>("uright"), 0.f, 0.f, wh[0], wh[1], 1.2f,
                                b.scalar("th_proj"), assigned), assigned);
     }
+    if (b.a.count("lf_uv")) {  // SearchByProjection(CurrentFrame, LastFrame): last frame = A, current frame = B
+      ORB_SLAM3::XFBmatcher m(ex.context(), 0.9f, true);
+      const auto uv = b.get<float>("lf_uv"), invzc = b.get<float>("lf_invzc");
+      const auto oct = b.get<int>("lf_octave");
+      const auto valid = b.flags("lf_valid"), obs = b.flags("lf_obs");
+      std::vector<ORB_SLAM3::XFBmatcher::LastFramePoint> pts(nA);
+      for (int i = 0; i < nA; ++i) pts[i] = {valid[i], uv[2 * i], uv[2 * i + 1], invzc[i], oct[i], obs[i]};
+      const auto wh = b.get<float>("img_wh");
+      const auto mode3 = b.get<int>("lf_modes");   // (forward, backward) pairs to run
+      for (size_t k = 0; k + 1 < mode3.size(); k += 2) {
+        std::vector<int> assigned;
+        put(m.SearchByProjection(pts, A, keypoints(b.get<float>("kB")), B, b.flags("occupied"), b.get<float>("uright"), 0.f, 0.f, wh[0], wh[1], 1.2f,
+                                 b.scalar("lf_th"), b.scalar("lf_mbf"), mode3[k] != 0, mode3[k + 1] != 0, assigned), assigned);
+      }
+    }
     {  // MapPoint::ComputeDistinctiveDescriptors (batched)
       ORB_SLAM3::XFBmatcher m(ex.context(), 0.6f, true);
       std::vector<float> dS = b.get<float>("dS");

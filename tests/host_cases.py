@@ -24,7 +24,7 @@ def bundle(path, arrays):
             f.write(np.ascontiguousarray(arr).tobytes())
 
 
-def run_searches_case(driver, tmp_path, dA, kA, dB, kB, seed=21):
+def run_searches_case(driver, tmp_path, dA, kA, dB, kB, seed=21, frame_to_frame=False):
     """XFBmatcher::SearchByBoW (both overloads), SearchForTriangulation, SearchByProjection and ComputeDistinctiveDescriptors
     against the C restatements of src/ORBmatcher.cc:408-610, :950-1090, :1092-1331, :42-212 and src/MapPoint.cc:329-403."""
     rng = np.random.RandomState(seed)
@@ -62,6 +62,16 @@ def run_searches_case(driver, tmp_path, dA, kA, dB, kB, seed=21):
                   F12=F12.reshape(-1), ep=ep, ratio_kf_f=np.float32([0.7]), ratio_kf_kf=np.float32([0.9]), ratio_proj=np.float32([0.8]),
                   th_proj=np.float32([3.0]), dM=dA[src], dF=dB, kF=kB, proj=proj.reshape(-1), projxr=projxr, viewcos=viewcos, level=level,
                   in_view=in_view, mp_obs=mp_obs, occupied=occupied, uright=uright, img_wh=np.float32([640, 480]), dS=dS, offsets=offsets)
+    if frame_to_frame:
+        # SearchByProjection(CurrentFrame, LastFrame): the map points of frame A projected into frame B with a slightly wrong pose
+        lf_uv = (kA + np.array([dx, dy], np.float32) + 2.0 * rng.randn(na, 2).astype(np.float32)).astype(np.float32)
+        lf_valid = (rng.rand(na) < 0.8) & (lf_uv[:, 0] >= 0) & (lf_uv[:, 0] <= 640) & (lf_uv[:, 1] >= 0) & (lf_uv[:, 1] <= 480)
+        lf_invzc = (1.0 / (0.5 + 4.0 * rng.rand(na))).astype(np.float32)
+        lf_octave = rng.choice([0, 0, 0, 0, 1], na).astype(np.int32)
+        lf_obs = rng.rand(na) < 0.9
+        lf_modes = np.array([0, 0, 1, 0, 0, 1], np.int32)
+        arrays.update(lf_uv=lf_uv.reshape(-1), lf_valid=lf_valid, lf_invzc=lf_invzc, lf_octave=lf_octave, lf_obs=lf_obs, lf_modes=lf_modes,
+                      lf_th=np.float32([15.0]), lf_mbf=np.float32([40.0]))
     bundle(tmp_path / "in.bin", arrays)
     subprocess.run([str(driver), "searches", str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], check=True)
     res = np.fromfile(tmp_path / "out.bin", np.int32)
@@ -82,6 +92,12 @@ def run_searches_case(driver, tmp_path, dA, kA, dB, kB, seed=21):
     n, m = take(); wn, wm = mo.search_by_projection(dA[src], in_view, proj, projxr, level, viewcos, mp_obs, dB, kB, occupied, uright, 640, 480, th=3.0,
                                                      scale_factor=1.2, ratio=0.8, th_high=1000)
     assert n == wn and np.array_equal(m, wm) and n > 50
+    if frame_to_frame:
+        for fwd, bwd in ((0, 0), (1, 0), (0, 1)):
+            n, m = take()
+            wn, wm = mo.search_by_projection_frames(dA, lf_valid, lf_uv, lf_invzc, lf_octave, lf_obs, dB, kB, occupied, uright, 640, 480, th=15.0,
+                                                    scale_factor=1.2, mbf=40.0, forward=bool(fwd), backward=bool(bwd), th_high=1000)
+            assert n == wn and np.array_equal(m, wm) and n > 100
     _, best = take()
     assert np.array_equal(best, mo.distinctive_descriptors(dS, offsets))
 

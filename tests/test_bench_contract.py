@@ -1,0 +1,32 @@
+"""bench.py's JSON contract, checked on the arm that runs without a GPU (`--impl reference`: the reference's own CPU implementation
+through oracle/_ref when it is built, else the C / torch port), plus the static shape of the B200 arm's line builder."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+REPO = Path(__file__).resolve().parents[1]
+
+
+@pytest.mark.skipif(not (REPO / "oracle" / "_ref" / "ref_xfeat").exists(), reason="oracle/_ref is built by __graft_entry__.build() where the reference tree is mounted")
+def test_reference_arm_prints_one_json_line():
+    out = subprocess.run([sys.executable, str(REPO / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+                         timeout=600, check=True).stdout.strip().splitlines()
+    line = json.loads(out[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["config"]["workload"].startswith("vga_640x480")
+
+
+def test_b200_arm_declares_every_contract_key():
+    src = (REPO / "bench.py").read_text()
+    for key in ('"metric"', '"value"', '"unit"', '"n_gpus"', '"steps"', '"warmup"', '"ms_per_step"', '"higher_is_better"', '"scaling"', '"vs_baseline"',
+                '"dtype"', '"data"', '"config"', '"e2e"', '"h2d_bytes_per_step"', '"d2h_bytes_per_step"', '"gpu_launches"', '"roofline"', '"bound"',
+                '"achieved"', '"peak"', '"frac"', '"traffic"', '"cpu_baseline"', '"cores"', '"kind"', '"sample"', '"clocks"', '"workload"'):
+        assert key in src, key

@@ -57,7 +57,7 @@ def test_search_for_initialization_and_match(driver_cpu, tmp_path, frame_pair):
 
 def test_node_gated_and_window_searches(driver_cpu, tmp_path, frame_pair):
     dA, kA, dB, kB = frame_pair
-    host_cases.run_searches_case(driver_cpu, tmp_path, dA, kA, dB, kB)
+    host_cases.run_searches_case(driver_cpu, tmp_path, dA, kA, dB, kB, frame_to_frame=True)
 
 
 def test_vocabulary_text_loader_and_transform(driver_cpu, tmp_path, frame_pair):

@@ -216,3 +216,67 @@ def test_distinctive_descriptors():
         np.fill_diagonal(d, 0)
         med = [sorted(d[i])[int(0.5 * (n - 1))] for i in range(n)]
         assert best[s] == int(np.argmin(med))           # first minimum wins (:388-393)
+
+
+def _naive_area(kxy, cells, W, H, x, y, rr, min_level, max_level):
+    """Frame::GetFeaturesInArea (src/Frame.cc:850-916) for octave-0 keypoints, brute force over the cell dictionary."""
+    f32 = np.float32
+    if (min_level > 0 or max_level >= 0) and 0 < min_level:
+        return []
+    wInv, hInv = f32(64) / f32(W), f32(48) / f32(H)
+    c0 = max(0, int(math.floor(float(f32(f32(x - rr) * wInv))))); c1 = min(63, int(math.ceil(float(f32(f32(x + rr) * wInv)))))
+    r0 = max(0, int(math.floor(float(f32(f32(y - rr) * hInv))))); r1 = min(47, int(math.ceil(float(f32(f32(y + rr) * hInv)))))
+    if c0 >= 64 or c1 < 0 or r0 >= 48 or r1 < 0:
+        return []
+    return [j for ix in range(c0, c1 + 1) for iy in range(r0, r1 + 1) for j in cells.get((ix, iy), [])
+            if abs(f32(kxy[j, 0] - x)) < rr and abs(f32(kxy[j, 1] - y)) < rr]
+
+
+@pytest.mark.parametrize("forward,backward", [(False, False), (True, False), (False, True)])
+def test_search_by_projection_frames(forward, backward):
+    rng = np.random.RandomState(17)
+    nL, nC, W, H = 300, 420, 640, 480
+    kxy = np.stack([rng.randint(0, W, nC), rng.randint(0, H, nC)], 1).astype(np.float32)
+    Dc = unit(rng, nC)
+    src = rng.randint(0, nC, nL)
+    Dl = related(rng, Dc, src, 0.03)
+    Dl[rng.rand(nL) < 0.2] = unit(rng, 1)[0]                      # map points that match nothing well (distance >= 256 everywhere)
+    uv = (kxy[src] + rng.randn(nL, 2) * 3).astype(np.float32)
+    valid = (rng.rand(nL) < 0.85).astype(np.uint8)
+    invzc = (1.0 / (0.5 + 4 * rng.rand(nL))).astype(np.float32)
+    octave = rng.choice([0, 0, 0, 1, 2], nL).astype(np.int32)
+    obs = (rng.rand(nL) < 0.9).astype(np.uint8)
+    occupied = (rng.rand(nC) < 0.1).astype(np.uint8)
+    uright = np.where(rng.rand(nC) < 0.5, kxy[:, 0] - 20.0, -1.0).astype(np.float32)
+    n, a = mo.search_by_projection_frames(Dl, valid, uv, invzc, octave, obs, Dc, kxy, occupied, uright, W, H, th=15.0, scale_factor=1.2, mbf=40.0,
+                                          forward=forward, backward=backward, th_high=1000)
+    f32 = np.float32
+    wInv, hInv = f32(64) / f32(W), f32(48) / f32(H)
+    cells = {}
+    for i in range(nC):
+        px, py = int(math.floor(float(f32(kxy[i, 0] * wInv)) + 0.5)), int(math.floor(float(f32(kxy[i, 1] * hInv)) + 0.5))
+        if 0 <= px < 64 and 0 <= py < 48:
+            cells.setdefault((px, py), []).append(i)
+    occ = occupied.copy(); want = np.full(nC, -1, np.int32); cnt = 0
+    for i in range(nL):
+        if not valid[i]:
+            continue
+        o = int(octave[i])
+        sf = f32(1.0)
+        for _ in range(o):
+            sf = f32(sf * f32(1.2))
+        radius = f32(f32(15.0) * sf)
+        lv = (o, -1) if forward else ((0, o) if backward else (o - 1, o + 1))
+        cand = _naive_area(kxy, cells, W, H, uv[i, 0], uv[i, 1], radius, *lv)
+        best, bi = 256, -1
+        for j in cand:
+            if occ[j]:
+                continue
+            if uright[j] > 0 and abs(f32(f32(uv[i, 0] - f32(f32(40.0) * invzc[i])) - uright[j])) > radius:
+                continue
+            d = mo.descriptor_distance(Dl[i], Dc[j])
+            if d < best:
+                best, bi = d, j
+        if best <= 1000 and bi >= 0:                                # (the reference omits `bi >= 0`: out-of-bounds write, see the oracle)
+            want[bi] = i; occ[bi] = obs[i]; cnt += 1
+    assert n == cnt and np.array_equal(a, want) and cnt > 30

@@ -330,6 +330,57 @@ int XFBmatcher::SearchByProjection(const std::vector<ProjectedPoint>& vPoints, c
   return nmatches;
 }
 
+int XFBmatcher::SearchByProjection(const std::vector<LastFramePoint>& vLast, const cv::Mat& descLast, const std::vector<cv::KeyPoint>& vKeysUnCur,
+                                   const cv::Mat& descCur, const std::vector<bool>& vbOccupiedCur, const std::vector<float>& vuRightCur, float minX,
+                                   float minY, float maxX, float maxY, float scaleFactor, float th, float mbf, bool bForward, bool bBackward,
+                                   std::vector<int>& vnAssignedCur) const {
+  const Grid grid(vKeysUnCur, minX, minY, maxX, maxY);
+  std::vector<std::vector<size_t> > cand(vLast.size());
+  std::vector<float> radius(vLast.size(), 0.f);
+  std::vector<int32_t> p1, p2;
+  for (size_t i = 0; i < vLast.size(); i++) {
+    const LastFramePoint& lp = vLast[i];
+    if (!lp.valid) continue;
+    const int nLastOctave = lp.octave;
+    float sf = 1.0f;                                 // CurrentFrame.mvScaleFactors[nLastOctave]
+    for (int l = 0; l < nLastOctave; ++l) sf *= scaleFactor;
+    radius[i] = th * sf;
+    if (bForward) cand[i] = grid.area(vKeysUnCur, lp.u, lp.v, radius[i], nLastOctave);
+    else if (bBackward) cand[i] = grid.area(vKeysUnCur, lp.u, lp.v, radius[i], 0, nLastOctave);
+    else cand[i] = grid.area(vKeysUnCur, lp.u, lp.v, radius[i], nLastOctave - 1, nLastOctave + 1);
+    for (size_t i2 : cand[i]) { p1.push_back(static_cast<int32_t>(i)); p2.push_back(static_cast<int32_t>(i2)); }
+  }
+  const std::vector<int32_t> dist = PairDistances(descLast, descCur, p1, p2);
+  vnAssignedCur = std::vector<int>(vKeysUnCur.size(), -1);
+  std::vector<bool> occupied = vbOccupiedCur;
+  int nmatches = 0;
+  size_t cur = 0;
+  for (size_t i = 0; i < vLast.size(); i++) {
+    const LastFramePoint& lp = vLast[i];
+    if (!lp.valid || cand[i].empty()) continue;
+    int bestDist = 256, bestIdx2 = -1;
+    for (size_t i2 : cand[i]) {
+      const int d = dist[cur++];
+      if (occupied[i2]) continue;
+      if (vuRightCur[i2] > 0) {
+        const float ur = lp.u - mbf * lp.invzc;
+        const float er = std::fabs(ur - vuRightCur[i2]);
+        if (er > radius[i]) continue;
+      }
+      if (d < bestDist) { bestDist = d; bestIdx2 = static_cast<int>(i2); }
+    }
+    // (reference :1955-1958 tests only bestDist <= TH_HIGH; with TH_HIGH = 1000 > the initial 256 it then writes mvpMapPoints[-1]
+    //  when no candidate was taken -- undefined behaviour there, "no match" here)
+    if (bestDist <= TH_HIGH && bestIdx2 >= 0) {
+      vnAssignedCur[bestIdx2] = static_cast<int>(i);
+      occupied[bestIdx2] = lp.hasObservations;
+      nmatches++;
+      // rotation histogram (:1967-1985, :2047-2069): every XFeat keypoint has angle -1 => one bin, nothing is removed
+    }
+  }
+  return nmatches;
+}
+
 std::vector<int> XFBmatcher::ComputeDistinctiveDescriptors(const cv::Mat& desc, const std::vector<int>& offsets) const {
   const size_t nsets = offsets.empty() ? 0 : offsets.size() - 1;
   std::vector<int32_t> p1, p2;

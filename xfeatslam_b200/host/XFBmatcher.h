@@ -98,6 +98,21 @@ class XFBmatcher {
                          const cv::Mat& descF, const std::vector<bool>& vbOccupiedF, const std::vector<float>& vuRightF, float minX, float minY,
                          float maxX, float maxY, float scaleFactor, float th, std::vector<int>& vnAssignedF) const;
 
+  // One feature of LastFrame for ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)
+  struct LastFramePoint {
+    bool valid;             // pMP && !mvbOutlier[i] && invzc >= 0 && projection inside the image bounds (:1881-1903)
+    float u, v;             // CurrentFrame.mpCamera->project(Tcw * pMP->GetWorldPos())
+    float invzc;            // 1 / depth in the current camera
+    int octave;             // LastFrame.mvKeys[i].octave
+    bool hasObservations;   // pMP->Observations() > 0
+  };
+  // src/ORBmatcher.cc:1861-2072 (TrackWithMotionModel), CurrentFrame.Nleft == -1.  descLast row i = pMP->GetDescriptor() of feature i.
+  // bForward / bBackward as computed at :1875-1876.  vnAssignedCur[i2] = last-frame index written to CurrentFrame.mvpMapPoints[i2].
+  int SearchByProjection(const std::vector<LastFramePoint>& vLast, const cv::Mat& descLast, const std::vector<cv::KeyPoint>& vKeysUnCur,
+                         const cv::Mat& descCur, const std::vector<bool>& vbOccupiedCur, const std::vector<float>& vuRightCur, float minX, float minY,
+                         float maxX, float maxY, float scaleFactor, float th, float mbf, bool bForward, bool bBackward,
+                         std::vector<int>& vnAssignedCur) const;
+
   // MapPoint::ComputeDistinctiveDescriptors, src/MapPoint.cc:329-403, for many map points in one GPU launch: the observed
   // descriptors of map point s are the rows offsets[s] .. offsets[s+1]-1 of `desc`; returns the chosen row (relative to the set).
   std::vector<int> ComputeDistinctiveDescriptors(const cv::Mat& desc, const std::vector<int>& offsets) const;
