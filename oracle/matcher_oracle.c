@@ -535,3 +535,79 @@ int mo_search_by_projection_frames(const float* Dlast, const uint8_t* valid, con
   grid_free(&g);
   return nmatches;
 }
+
+/* ORBmatcher::SearchByProjection(KeyFrame* pKF, Sophus::Sim3f& Scw, vpPoints, vpMatched, th, ratioHamming), src/ORBmatcher.cc:612-717
+ * (loop closing / merging; :719-831 is the same search with an extra vpMatchedKF bookkeeping array).  The geometric pre-checks
+ * (:633-662: bad / already found, positive depth, inside the image, distance range, viewing angle) and the projection are the
+ * caller's (Sophus / Eigen): valid[m], uv[m], radius[m] = th * mvScaleFactors[nPredictedLevel], level[m] = nPredictedLevel.
+ * matched_in[idx] = (vpMatched[idx] != NULL) on entry.  assign[idx] (out) = map point written to vpMatched[idx], -1 = untouched.
+ * All keypoints are at octave 0. */
+int mo_search_by_projection_sim3(const float* Dmp, const uint8_t* valid, const float* uv, const float* radius, const int32_t* level, int n_mp,
+                                 const float* Dkf, const float* kxy, const uint8_t* matched_in, int n_kf, int img_w, int img_h, int th_low,
+                                 float ratio_hamming, int32_t* assign) {
+  mo_grid g;
+  grid_build(&g, kxy, n_kf, img_w, img_h);
+  int* cand = (int*)malloc(sizeof(int) * (size_t)(n_kf > 0 ? n_kf : 1));
+  uint8_t* matched = (uint8_t*)malloc((size_t)(n_kf > 0 ? n_kf : 1));
+  for (int j = 0; j < n_kf; ++j) { assign[j] = -1; matched[j] = matched_in[j]; }
+  int nmatches = 0;
+  for (int m = 0; m < n_mp; ++m) {
+    if (!valid[m]) continue;
+    const int nPredictedLevel = level[m];
+    const int nc = grid_area(&g, kxy, uv[2 * m], uv[2 * m + 1], radius[m], cand);   /* GetFeaturesInArea(u, v, radius): no level limits */
+    if (nc == 0) continue;
+    int bestDist = 256, bestIdx = -1;
+    for (int c = 0; c < nc; ++c) {
+      const int idx = cand[c];
+      if (matched[idx]) continue;
+      const int kpLevel = 0;
+      if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+      const int dist = mo_descriptor_distance(Dmp + (size_t)m * XF_DIM, Dkf + (size_t)idx * XF_DIM);
+      if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+    }
+    if ((float)bestDist <= (float)th_low * ratio_hamming) { assign[bestIdx] = m; matched[bestIdx] = 1; nmatches++; }
+  }
+  free(cand); free(matched);
+  grid_free(&g);
+  return nmatches;
+}
+
+/* The candidate search of ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th, bRight = false), src/ORBmatcher.cc:1333-1523 (:1413-1479): per
+ * map point the closest keypoint in the window that passes the level filter and the chi-square reprojection test.  The pre-checks
+ * (:1363-1408) and the Replace / AddObservation decisions on the result (:1481-1503, `if(bestDist<=TH_LOW)`) stay with the caller.
+ *   valid, uv, ur (= u - bf * invz), radius, level : per map point;  uright = pKF->mvuRight;  inv_sigma2_0 = mvInvLevelSigma2[0]
+ * best_idx / best_dist (out): -1 / 256 where nothing qualified. */
+void mo_fuse_search(const float* Dmp, const uint8_t* valid, const float* uv, const float* ur, const float* radius, const int32_t* level, int n_mp,
+                    const float* Dkf, const float* kxy, const float* uright, int n_kf, int img_w, int img_h, float inv_sigma2_0, int32_t* best_idx,
+                    int32_t* best_dist) {
+  mo_grid g;
+  grid_build(&g, kxy, n_kf, img_w, img_h);
+  int* cand = (int*)malloc(sizeof(int) * (size_t)(n_kf > 0 ? n_kf : 1));
+  for (int m = 0; m < n_mp; ++m) {
+    best_idx[m] = -1; best_dist[m] = 256;
+    if (!valid[m]) continue;
+    const int nPredictedLevel = level[m];
+    const int nc = grid_area(&g, kxy, uv[2 * m], uv[2 * m + 1], radius[m], cand);
+    int bestDist = 256, bestIdx = -1;
+    for (int c = 0; c < nc; ++c) {
+      const int idx = cand[c];
+      const int kpLevel = 0;
+      if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+      const float kpx = kxy[2 * idx], kpy = kxy[2 * idx + 1];
+      if (uright[idx] >= 0) {
+        const float ex = uv[2 * m] - kpx, ey = uv[2 * m + 1] - kpy, er = ur[m] - uright[idx];
+        const float e2 = ex * ex + ey * ey + er * er;
+        if ((double)(e2 * inv_sigma2_0) > 7.8) continue;
+      } else {
+        const float ex = uv[2 * m] - kpx, ey = uv[2 * m + 1] - kpy;
+        const float e2 = ex * ex + ey * ey;
+        if ((double)(e2 * inv_sigma2_0) > 5.99) continue;
+      }
+      const int dist = mo_descriptor_distance(Dmp + (size_t)m * XF_DIM, Dkf + (size_t)idx * XF_DIM);
+      if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+    }
+    best_idx[m] = bestIdx; best_dist[m] = bestDist;
+  }
+  free(cand);
+  grid_free(&g);
+}

@@ -153,3 +153,24 @@ def search_by_projection_frames(Dlast, valid, uv, invzc, octave, mp_obs, Dcur, k
                                          ctypes.c_float(th), ctypes.c_float(scale_factor), ctypes.c_float(mbf), int(forward), int(backward),
                                          int(th_high), out.ctypes.data_as(ctypes.c_void_p))
     return n, out
+
+
+def search_by_projection_sim3(Dmp, valid, uv, radius, level, Dkf, kxy, matched, img_w, img_h, th_low=100, ratio_hamming=1.0):
+    """ORBmatcher::SearchByProjection(KeyFrame*, Sim3, vpPoints, vpMatched, th, ratioHamming), src/ORBmatcher.cc:612-717 -> (nmatches, assign[n_kf])."""
+    Dm, p1 = _f(Dmp); Dk, p2 = _f(Dkf); u, pu = _f(uv); r, pr = _f(radius); kk, pkk = _f(kxy)
+    va, pva = _u8(valid); ma, pma = _u8(matched); lv, plv = _i(level)
+    out = np.empty(Dk.shape[0], np.int32)
+    L = lib(); L.mo_search_by_projection_sim3.restype = ctypes.c_int
+    n = L.mo_search_by_projection_sim3(p1, pva, pu, pr, plv, Dm.shape[0], p2, pkk, pma, Dk.shape[0], int(img_w), int(img_h), int(th_low),
+                                       ctypes.c_float(ratio_hamming), out.ctypes.data_as(ctypes.c_void_p))
+    return n, out
+
+
+def fuse_search(Dmp, valid, uv, ur, radius, level, Dkf, kxy, uright, img_w, img_h, inv_sigma2_0=1.0):
+    """Candidate search of ORBmatcher::Fuse, src/ORBmatcher.cc:1413-1479 -> (best_idx[n_mp], best_dist[n_mp])."""
+    Dm, p1 = _f(Dmp); Dk, p2 = _f(Dkf); u, pu = _f(uv); urr, pur = _f(ur); r, pr = _f(radius); kk, pkk = _f(kxy); rr, prr = _f(uright)
+    va, pva = _u8(valid); lv, plv = _i(level)
+    bi = np.empty(Dm.shape[0], np.int32); bd = np.empty(Dm.shape[0], np.int32)
+    lib().mo_fuse_search(p1, pva, pu, pur, pr, plv, Dm.shape[0], p2, pkk, prr, Dk.shape[0], int(img_w), int(img_h), ctypes.c_float(inv_sigma2_0),
+                         bi.ctypes.data_as(ctypes.c_void_p), bd.ctypes.data_as(ctypes.c_void_p))
+    return bi, bd

@@ -226,6 +226,24 @@ int main(int argc, char** argv) {
                                  b.scalar("lf_th"), b.scalar("lf_mbf"), mode3[k] != 0, mode3[k + 1] != 0, assigned), assigned);
       }
     }
+    if (b.a.count("wq_uv")) {  // SearchByProjection(KeyFrame*, Sim3, ...) and Fuse: map points = rows of dM, keyframe = B
+      ORB_SLAM3::XFBmatcher m(ex.context(), 0.6f, true);
+      std::vector<float> dM = b.get<float>("dM");
+      const int nM = static_cast<int>(dM.size() / 64);
+      cv::Mat M(nM, 64, CV_32F, dM.data());
+      const auto uv = b.get<float>("wq_uv"), ur = b.get<float>("wq_ur"), rad = b.get<float>("wq_radius");
+      const auto lvl = b.get<int>("wq_level");
+      const auto valid = b.flags("wq_valid");
+      std::vector<ORB_SLAM3::XFBmatcher::WindowQuery> qs(nM);
+      for (int i = 0; i < nM; ++i) qs[i] = {valid[i], uv[2 * i], uv[2 * i + 1], ur[i], rad[i], lvl[i]};
+      const auto wh = b.get<float>("img_wh");
+      std::vector<int> assigned;
+      put(m.SearchByProjection(qs, M, keypoints(b.get<float>("kB")), B, b.flags("occupied"), 0.f, 0.f, wh[0], wh[1], b.scalar("wq_ratio"), assigned), assigned);
+      std::vector<int> bi, bd;
+      const std::vector<float> sig(8, b.scalar("wq_invsigma2"));
+      m.FuseSearch(qs, M, keypoints(b.get<float>("kB")), b.get<float>("uright"), sig, B, 0.f, 0.f, wh[0], wh[1], true, bi, bd);
+      put(0, bi); put(0, bd);
+    }
     {  // MapPoint::ComputeDistinctiveDescriptors (batched)
       ORB_SLAM3::XFBmatcher m(ex.context(), 0.6f, true);
       std::vector<float> dS = b.get<float>("dS");

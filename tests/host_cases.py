@@ -72,6 +72,14 @@ def run_searches_case(driver, tmp_path, dA, kA, dB, kB, seed=21, frame_to_frame=
         lf_modes = np.array([0, 0, 1, 0, 0, 1], np.int32)
         arrays.update(lf_uv=lf_uv.reshape(-1), lf_valid=lf_valid, lf_invzc=lf_invzc, lf_octave=lf_octave, lf_obs=lf_obs, lf_modes=lf_modes,
                       lf_th=np.float32([15.0]), lf_mbf=np.float32([40.0]))
+    if frame_to_frame:
+        # loop-closing SearchByProjection (Sim3) and Fuse: the same projected map points, windows of 4 / 7 px
+        wq_valid = rng.rand(nM) < 0.85
+        wq_level = rng.choice([0, 0, 1, 2], nM).astype(np.int32)
+        wq_radius = (np.float32(5.0) * np.float32(1.2) ** wq_level).astype(np.float32)
+        wq_ur = projxr
+        arrays.update(wq_uv=proj.reshape(-1), wq_ur=wq_ur, wq_radius=wq_radius, wq_level=wq_level, wq_valid=wq_valid, wq_ratio=np.float32([1.0]),
+                      wq_invsigma2=np.float32([1.0]))
     bundle(tmp_path / "in.bin", arrays)
     subprocess.run([str(driver), "searches", str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], check=True)
     res = np.fromfile(tmp_path / "out.bin", np.int32)
@@ -98,6 +106,12 @@ def run_searches_case(driver, tmp_path, dA, kA, dB, kB, seed=21, frame_to_frame=
             wn, wm = mo.search_by_projection_frames(dA, lf_valid, lf_uv, lf_invzc, lf_octave, lf_obs, dB, kB, occupied, uright, 640, 480, th=15.0,
                                                     scale_factor=1.2, mbf=40.0, forward=bool(fwd), backward=bool(bwd), th_high=1000)
             assert n == wn and np.array_equal(m, wm) and n > 100
+        n, m = take()
+        wn, wm = mo.search_by_projection_sim3(dA[src], wq_valid, proj, wq_radius, wq_level, dB, kB, occupied, 640, 480, th_low=100, ratio_hamming=1.0)
+        assert n == wn and np.array_equal(m, wm) and n > 50
+        _, bi_ = take(); _, bd_ = take()
+        wbi, wbd = mo.fuse_search(dA[src], wq_valid, proj, wq_ur, wq_radius, wq_level, dB, kB, uright, 640, 480, inv_sigma2_0=1.0)
+        assert np.array_equal(bi_, wbi) and np.array_equal(bd_, wbd) and (wbd <= 100).sum() > 50
     _, best = take()
     assert np.array_equal(best, mo.distinctive_descriptors(dS, offsets))
 

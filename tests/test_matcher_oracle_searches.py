@@ -280,3 +280,70 @@ def test_search_by_projection_frames(forward, backward):
         if best <= 1000 and bi >= 0:                                # (the reference omits `bi >= 0`: out-of-bounds write, see the oracle)
             want[bi] = i; occ[bi] = obs[i]; cnt += 1
     assert n == cnt and np.array_equal(a, want) and cnt > 30
+
+
+def _window_problem(seed):
+    rng = np.random.RandomState(seed)
+    nM, nK, W, H = 350, 450, 640, 480
+    kxy = np.stack([rng.randint(0, W, nK), rng.randint(0, H, nK)], 1).astype(np.float32)
+    Dk = unit(rng, nK)
+    src = rng.randint(0, nK, nM)
+    Dm = related(rng, Dk, src, 0.04)
+    uv = (kxy[src] + rng.randn(nM, 2) * 1.5).astype(np.float32)
+    valid = (rng.rand(nM) < 0.85).astype(np.uint8)
+    level = rng.choice([0, 0, 1, 2], nM).astype(np.int32)
+    radius = (np.float32(5.0) * np.float32(1.2) ** level).astype(np.float32)
+    cells = {}
+    f32 = np.float32
+    wInv, hInv = f32(64) / f32(W), f32(48) / f32(H)
+    for i in range(nK):
+        px, py = int(math.floor(float(f32(kxy[i, 0] * wInv)) + 0.5)), int(math.floor(float(f32(kxy[i, 1] * hInv)) + 0.5))
+        if 0 <= px < 64 and 0 <= py < 48:
+            cells.setdefault((px, py), []).append(i)
+    return rng, Dm, Dk, kxy, uv, valid, level, radius, cells, W, H
+
+
+def test_search_by_projection_sim3():
+    rng, Dm, Dk, kxy, uv, valid, level, radius, cells, W, H = _window_problem(23)
+    matched = (rng.rand(len(Dk)) < 0.1).astype(np.uint8)
+    n, a = mo.search_by_projection_sim3(Dm, valid, uv, radius, level, Dk, kxy, matched, W, H, th_low=100, ratio_hamming=0.9)
+    occ = matched.copy(); want = np.full(len(Dk), -1, np.int32); cnt = 0
+    for m in range(len(Dm)):
+        if not valid[m]:
+            continue
+        best, bi = 256, -1
+        for j in _naive_area(kxy, cells, W, H, uv[m, 0], uv[m, 1], radius[m], -1, -1):
+            if occ[j] or 0 < level[m] - 1 or 0 > level[m]:
+                continue
+            d = mo.descriptor_distance(Dm[m], Dk[j])
+            if d < best:
+                best, bi = d, j
+        if np.float32(best) <= np.float32(100) * np.float32(0.9):
+            want[bi] = m; occ[bi] = 1; cnt += 1
+    assert n == cnt and np.array_equal(a, want) and cnt > 30
+
+
+def test_fuse_search():
+    rng, Dm, Dk, kxy, uv, valid, level, radius, cells, W, H = _window_problem(29)
+    uright = np.where(rng.rand(len(Dk)) < 0.5, kxy[:, 0] - 20.0, -1.0).astype(np.float32)
+    ur = (uv[:, 0] - 20.0 + rng.randn(len(Dm))).astype(np.float32)
+    bi, bd = mo.fuse_search(Dm, valid, uv, ur, radius, level, Dk, kxy, uright, W, H, inv_sigma2_0=1.0)
+    f32 = np.float32
+    wbi = np.full(len(Dm), -1, np.int32); wbd = np.full(len(Dm), 256, np.int32)
+    for m in range(len(Dm)):
+        if not valid[m]:
+            continue
+        for j in _naive_area(kxy, cells, W, H, uv[m, 0], uv[m, 1], radius[m], -1, -1):
+            if 0 < level[m] - 1 or 0 > level[m]:
+                continue
+            ex, ey = f32(uv[m, 0] - kxy[j, 0]), f32(uv[m, 1] - kxy[j, 1])
+            if uright[j] >= 0:
+                er = f32(ur[m] - uright[j])
+                if float(f32(f32(f32(ex * ex) + f32(ey * ey)) + f32(er * er)) * f32(1.0)) > 7.8:
+                    continue
+            elif float(f32(f32(ex * ex) + f32(ey * ey)) * f32(1.0)) > 5.99:
+                continue
+            d = mo.descriptor_distance(Dm[m], Dk[j])
+            if d < wbd[m]:
+                wbd[m], wbi[m] = d, j
+    assert np.array_equal(bi, wbi) and np.array_equal(bd, wbd) and (bd <= 100).sum() > 30

@@ -381,6 +381,86 @@ int XFBmatcher::SearchByProjection(const std::vector<LastFramePoint>& vLast, con
   return nmatches;
 }
 
+int XFBmatcher::SearchByProjection(const std::vector<WindowQuery>& vQueries, const cv::Mat& descMP, const std::vector<cv::KeyPoint>& vKeysUnKF,
+                                   const cv::Mat& descKF, const std::vector<bool>& vbMatchedKF, float minX, float minY, float maxX, float maxY,
+                                   float ratioHamming, std::vector<int>& vnAssignedKF) const {
+  const Grid grid(vKeysUnKF, minX, minY, maxX, maxY);
+  std::vector<std::vector<size_t> > cand(vQueries.size());
+  std::vector<int32_t> p1, p2;
+  for (size_t iMP = 0; iMP < vQueries.size(); iMP++) {
+    const WindowQuery& q = vQueries[iMP];
+    if (!q.valid) continue;
+    for (size_t idx : grid.area(vKeysUnKF, q.u, q.v, q.radius)) {     // GetFeaturesInArea(u, v, radius): no level limits (:668)
+      const int kpLevel = vKeysUnKF[idx].octave;
+      if (kpLevel < q.predictedLevel - 1 || kpLevel > q.predictedLevel) continue;   // static filter (:688-691), applied before listing
+      cand[iMP].push_back(idx);
+      p1.push_back(static_cast<int32_t>(iMP)); p2.push_back(static_cast<int32_t>(idx));
+    }
+  }
+  const std::vector<int32_t> dist = PairDistances(descMP, descKF, p1, p2);
+  vnAssignedKF = std::vector<int>(vKeysUnKF.size(), -1);
+  std::vector<bool> matched = vbMatchedKF;
+  int nmatches = 0;
+  size_t cur = 0;
+  for (size_t iMP = 0; iMP < vQueries.size(); iMP++) {
+    if (!vQueries[iMP].valid || cand[iMP].empty()) continue;
+    int bestDist = 256, bestIdx = -1;
+    for (size_t idx : cand[iMP]) {
+      const int d = dist[cur++];
+      if (matched[idx]) continue;                                      // vpMatched[idx] (:684)
+      if (d < bestDist) { bestDist = d; bestIdx = static_cast<int>(idx); }
+    }
+    if (bestDist <= TH_LOW * ratioHamming) {                           // (:705; 100 * ratio < 256, so bestIdx is valid here)
+      vnAssignedKF[bestIdx] = static_cast<int>(iMP);
+      matched[bestIdx] = true;
+      nmatches++;
+    }
+  }
+  return nmatches;
+}
+
+void XFBmatcher::FuseSearch(const std::vector<WindowQuery>& vQueries, const cv::Mat& descMP, const std::vector<cv::KeyPoint>& vKeysUnKF,
+                            const std::vector<float>& vuRightKF, const std::vector<float>& vInvLevelSigma2, const cv::Mat& descKF, float minX,
+                            float minY, float maxX, float maxY, bool bChi2, std::vector<int>& vnBestIdx, std::vector<int>& vnBestDist) const {
+  const Grid grid(vKeysUnKF, minX, minY, maxX, maxY);
+  std::vector<std::vector<size_t> > cand(vQueries.size());
+  std::vector<int32_t> p1, p2;
+  for (size_t i = 0; i < vQueries.size(); i++) {
+    const WindowQuery& q = vQueries[i];
+    if (!q.valid) continue;
+    for (size_t idx : grid.area(vKeysUnKF, q.u, q.v, q.radius)) {
+      const cv::KeyPoint& kp = vKeysUnKF[idx];
+      const int kpLevel = kp.octave;
+      if (kpLevel < q.predictedLevel - 1 || kpLevel > q.predictedLevel) continue;
+      if (bChi2) {
+        if (vuRightKF[idx] >= 0) {   // reprojection error in stereo (:1438-1449)
+          const float ex = q.u - kp.pt.x, ey = q.v - kp.pt.y, er = q.ur - vuRightKF[idx];
+          const float e2 = ex * ex + ey * ey + er * er;
+          if (e2 * vInvLevelSigma2[kpLevel] > 7.8) continue;
+        } else {                      // (:1451-1459)
+          const float ex = q.u - kp.pt.x, ey = q.v - kp.pt.y;
+          const float e2 = ex * ex + ey * ey;
+          if (e2 * vInvLevelSigma2[kpLevel] > 5.99) continue;
+        }
+      }
+      cand[i].push_back(idx);
+      p1.push_back(static_cast<int32_t>(i)); p2.push_back(static_cast<int32_t>(idx));
+    }
+  }
+  const std::vector<int32_t> dist = PairDistances(descMP, descKF, p1, p2);
+  vnBestIdx.assign(vQueries.size(), -1);
+  vnBestDist.assign(vQueries.size(), 256);
+  size_t cur = 0;
+  for (size_t i = 0; i < vQueries.size(); i++) {
+    int bestDist = 256, bestIdx = -1;
+    for (size_t idx : cand[i]) {
+      const int d = dist[cur++];
+      if (d < bestDist) { bestDist = d; bestIdx = static_cast<int>(idx); }
+    }
+    vnBestIdx[i] = bestIdx; vnBestDist[i] = bestDist;
+  }
+}
+
 std::vector<int> XFBmatcher::ComputeDistinctiveDescriptors(const cv::Mat& desc, const std::vector<int>& offsets) const {
   const size_t nsets = offsets.empty() ? 0 : offsets.size() - 1;
   std::vector<int32_t> p1, p2;

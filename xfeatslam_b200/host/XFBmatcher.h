@@ -113,6 +113,28 @@ class XFBmatcher {
                          float maxX, float maxY, float scaleFactor, float th, float mbf, bool bForward, bool bBackward,
                          std::vector<int>& vnAssignedCur) const;
 
+  // One projected map point of the loop-closing / fusing searches: everything the reference derives from the pose and the MapPoint
+  // before it looks at descriptors (src/ORBmatcher.cc:633-668, :1363-1411)
+  struct WindowQuery {
+    bool valid;             // passed: not bad / not already found, positive depth, inside the image, distance range, viewing angle
+    float u, v;             // pKF->mpCamera->project(Tcw * p3Dw)
+    float ur;               // u - bf * invz (Fuse's stereo reprojection test)
+    float radius;           // th * pKF->mvScaleFactors[nPredictedLevel]
+    int predictedLevel;     // nPredictedLevel: candidates need octave in [predictedLevel - 1, predictedLevel]
+  };
+  // ORBmatcher::SearchByProjection(KeyFrame*, Sophus::Sim3f&, vpPoints, vpMatched, th, ratioHamming), src/ORBmatcher.cc:612-717
+  // (and :719-831, which only adds the vpMatchedKF array).  vbMatchedKF[idx] = (vpMatched[idx] != NULL) on entry;
+  // vnAssignedKF[idx] = index of the map point written to vpMatched[idx], -1 = untouched.
+  int SearchByProjection(const std::vector<WindowQuery>& vQueries, const cv::Mat& descMP, const std::vector<cv::KeyPoint>& vKeysUnKF,
+                         const cv::Mat& descKF, const std::vector<bool>& vbMatchedKF, float minX, float minY, float maxX, float maxY,
+                         float ratioHamming, std::vector<int>& vnAssignedKF) const;
+  // The candidate search of ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th) (src/ORBmatcher.cc:1413-1479; the Sim3 overload :1525-1640 has
+  // the same search without the chi-square test): closest keypoint per map point that passes the level filter and the reprojection
+  // test.  vnBestIdx / vnBestDist: -1 / 256 where nothing qualified; the caller applies `bestDist <= TH_LOW` and Replace / AddObservation.
+  void FuseSearch(const std::vector<WindowQuery>& vQueries, const cv::Mat& descMP, const std::vector<cv::KeyPoint>& vKeysUnKF,
+                  const std::vector<float>& vuRightKF, const std::vector<float>& vInvLevelSigma2, const cv::Mat& descKF, float minX, float minY,
+                  float maxX, float maxY, bool bChi2, std::vector<int>& vnBestIdx, std::vector<int>& vnBestDist) const;
+
   // MapPoint::ComputeDistinctiveDescriptors, src/MapPoint.cc:329-403, for many map points in one GPU launch: the observed
   // descriptors of map point s are the rows offsets[s] .. offsets[s+1]-1 of `desc`; returns the chosen row (relative to the set).
   std::vector<int> ComputeDistinctiveDescriptors(const cv::Mat& desc, const std::vector<int>& offsets) const;
