@@ -611,3 +611,49 @@ void mo_fuse_search(const float* Dmp, const uint8_t* valid, const float* uv, con
   free(cand);
   grid_free(&g);
 }
+
+/* One direction of ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:1690-1760 / :1762-1833): closest keypoint of the other keyframe in
+ * the window, level filter, bestDist starts at INT_MAX, accepted when <= TH_HIGH. */
+static void sim3_one_way(const float* Dmp, const uint8_t* valid, const float* uv, const float* radius, const int32_t* level, int n_mp,
+                         const float* Dkf, const float* kxy, int n_kf, int img_w, int img_h, int th_high, int* match) {
+  mo_grid g;
+  grid_build(&g, kxy, n_kf, img_w, img_h);
+  int* cand = (int*)malloc(sizeof(int) * (size_t)(n_kf > 0 ? n_kf : 1));
+  for (int i = 0; i < n_mp; ++i) {
+    match[i] = -1;
+    if (!valid[i]) continue;
+    const int nc = grid_area(&g, kxy, uv[2 * i], uv[2 * i + 1], radius[i], cand);
+    if (nc == 0) continue;
+    int bestDist = INT_MAX, bestIdx = -1;
+    for (int c = 0; c < nc; ++c) {
+      const int idx = cand[c];
+      if (0 < level[i] - 1 || 0 > level[i]) continue;   /* kp.octave (0) < nPredictedLevel - 1 || > nPredictedLevel */
+      const int dist = mo_descriptor_distance(Dmp + (size_t)i * XF_DIM, Dkf + (size_t)idx * XF_DIM);
+      if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+    }
+    if (bestDist <= th_high) match[i] = bestIdx;
+  }
+  free(cand);
+  grid_free(&g);
+}
+
+/* ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, S12, th), src/ORBmatcher.cc:1642-1859.  Per feature of KF1 (resp. KF2): valid =
+ * has a good MapPoint, not already matched, positive depth, inside the other image, distance in range (:1692-1722 / :1764-1794);
+ * uv / radius / level = its projection into the other keyframe with S21 (resp. S12); Dmp1 / Dmp2 rows = pMP->GetDescriptor().
+ * matches12[i1] (out) = idx2 where both directions agree (:1835-1850), else -1; returns nFound. */
+int mo_search_by_sim3(const float* Dmp1, const uint8_t* valid1, const float* uv1, const float* radius1, const int32_t* level1, int n1,
+                      const float* D2, const float* k2xy, const float* Dmp2, const uint8_t* valid2, const float* uv2, const float* radius2,
+                      const int32_t* level2, int n2, const float* D1, const float* k1xy, int img_w, int img_h, int th_high, int32_t* matches12) {
+  int* m1 = (int*)malloc(sizeof(int) * (size_t)(n1 > 0 ? n1 : 1));
+  int* m2 = (int*)malloc(sizeof(int) * (size_t)(n2 > 0 ? n2 : 1));
+  sim3_one_way(Dmp1, valid1, uv1, radius1, level1, n1, D2, k2xy, n2, img_w, img_h, th_high, m1);
+  sim3_one_way(Dmp2, valid2, uv2, radius2, level2, n2, D1, k1xy, n1, img_w, img_h, th_high, m2);
+  int nFound = 0;
+  for (int i1 = 0; i1 < n1; ++i1) {
+    matches12[i1] = -1;
+    const int idx2 = m1[i1];
+    if (idx2 >= 0 && m2[idx2] == i1) { matches12[i1] = idx2; nFound++; }
+  }
+  free(m1); free(m2);
+  return nFound;
+}

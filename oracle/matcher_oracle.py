@@ -174,3 +174,15 @@ def fuse_search(Dmp, valid, uv, ur, radius, level, Dkf, kxy, uright, img_w, img_
     lib().mo_fuse_search(p1, pva, pu, pur, pr, plv, Dm.shape[0], p2, pkk, prr, Dk.shape[0], int(img_w), int(img_h), ctypes.c_float(inv_sigma2_0),
                          bi.ctypes.data_as(ctypes.c_void_p), bd.ctypes.data_as(ctypes.c_void_p))
     return bi, bd
+
+
+def search_by_sim3(Dmp1, valid1, uv1, radius1, level1, D2, k2xy, Dmp2, valid2, uv2, radius2, level2, D1, k1xy, img_w, img_h, th_high=1000):
+    """ORBmatcher::SearchBySim3, src/ORBmatcher.cc:1642-1859 -> (nFound, matches12[n1])."""
+    a1, pa1 = _f(Dmp1); a2, pa2 = _f(Dmp2); d1, pd1 = _f(D1); d2, pd2 = _f(D2)
+    u1, pu1 = _f(uv1); u2, pu2 = _f(uv2); r1, pr1 = _f(radius1); r2, pr2 = _f(radius2); k1, pk1 = _f(k1xy); k2, pk2 = _f(k2xy)
+    v1, pv1 = _u8(valid1); v2, pv2 = _u8(valid2); l1, pl1 = _i(level1); l2, pl2 = _i(level2)
+    out = np.empty(a1.shape[0], np.int32)
+    L = lib(); L.mo_search_by_sim3.restype = ctypes.c_int
+    n = L.mo_search_by_sim3(pa1, pv1, pu1, pr1, pl1, a1.shape[0], pd2, pk2, pa2, pv2, pu2, pr2, pl2, a2.shape[0], pd1, pk1, int(img_w), int(img_h),
+                            int(th_high), out.ctypes.data_as(ctypes.c_void_p))
+    return n, out

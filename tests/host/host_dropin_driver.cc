@@ -244,6 +244,21 @@ int main(int argc, char** argv) {
       m.FuseSearch(qs, M, keypoints(b.get<float>("kB")), b.get<float>("uright"), sig, B, 0.f, 0.f, wh[0], wh[1], true, bi, bd);
       put(0, bi); put(0, bd);
     }
+    if (b.a.count("s3_uv1")) {  // SearchBySim3: keyframe 1 = A, keyframe 2 = B, map-point descriptors = the features' own rows
+      ORB_SLAM3::XFBmatcher m(ex.context(), 0.6f, true);
+      auto build = [&](const std::string& s, int n) {
+        const auto uv = b.get<float>("s3_uv" + s), rad = b.get<float>("s3_rad" + s);
+        const auto lvl = b.get<int>("s3_lvl" + s);
+        const auto valid = b.flags("s3_ok" + s);
+        std::vector<ORB_SLAM3::XFBmatcher::WindowQuery> q(n);
+        for (int i = 0; i < n; ++i) q[i] = {valid[i], uv[2 * i], uv[2 * i + 1], 0.f, rad[i], lvl[i]};
+        return q;
+      };
+      const auto wh = b.get<float>("img_wh");
+      std::vector<int> m12;
+      put(m.SearchBySim3(build("1", nA), A, keypoints(b.get<float>("kA")), A, build("2", nB), B, keypoints(b.get<float>("kB")), B, 0.f, 0.f, wh[0], wh[1],
+                         m12), m12);
+    }
     {  // MapPoint::ComputeDistinctiveDescriptors (batched)
       ORB_SLAM3::XFBmatcher m(ex.context(), 0.6f, true);
       std::vector<float> dS = b.get<float>("dS");

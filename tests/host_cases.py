@@ -80,6 +80,15 @@ def run_searches_case(driver, tmp_path, dA, kA, dB, kB, seed=21, frame_to_frame=
         wq_ur = projxr
         arrays.update(wq_uv=proj.reshape(-1), wq_ur=wq_ur, wq_radius=wq_radius, wq_level=wq_level, wq_valid=wq_valid, wq_ratio=np.float32([1.0]),
                       wq_invsigma2=np.float32([1.0]))
+    if frame_to_frame:
+        # SearchBySim3: every feature's map point projected into the other keyframe with a slightly wrong Sim3
+        s3_uv1 = (kA + np.array([dx, dy], np.float32) + 1.5 * rng.randn(na, 2).astype(np.float32)).astype(np.float32)
+        s3_uv2 = (kB - np.array([dx, dy], np.float32) + 1.5 * rng.randn(nb, 2).astype(np.float32)).astype(np.float32)
+        s3_ok1 = rng.rand(na) < 0.8; s3_ok2 = rng.rand(nb) < 0.8
+        s3_lvl1 = rng.choice([0, 0, 1, 2], na).astype(np.int32); s3_lvl2 = rng.choice([0, 0, 1, 2], nb).astype(np.int32)
+        s3_rad1 = (np.float32(7.5) * np.float32(1.2) ** s3_lvl1).astype(np.float32); s3_rad2 = (np.float32(7.5) * np.float32(1.2) ** s3_lvl2).astype(np.float32)
+        arrays.update(s3_uv1=s3_uv1.reshape(-1), s3_uv2=s3_uv2.reshape(-1), s3_ok1=s3_ok1, s3_ok2=s3_ok2, s3_lvl1=s3_lvl1, s3_lvl2=s3_lvl2,
+                      s3_rad1=s3_rad1, s3_rad2=s3_rad2)
     bundle(tmp_path / "in.bin", arrays)
     subprocess.run([str(driver), "searches", str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], check=True)
     res = np.fromfile(tmp_path / "out.bin", np.int32)
@@ -112,6 +121,9 @@ def run_searches_case(driver, tmp_path, dA, kA, dB, kB, seed=21, frame_to_frame=
         _, bi_ = take(); _, bd_ = take()
         wbi, wbd = mo.fuse_search(dA[src], wq_valid, proj, wq_ur, wq_radius, wq_level, dB, kB, uright, 640, 480, inv_sigma2_0=1.0)
         assert np.array_equal(bi_, wbi) and np.array_equal(bd_, wbd) and (wbd <= 100).sum() > 50
+        n, m = take()
+        wn, wm = mo.search_by_sim3(dA, s3_ok1, s3_uv1, s3_rad1, s3_lvl1, dB, kB, dB, s3_ok2, s3_uv2, s3_rad2, s3_lvl2, dA, kA, 640, 480, th_high=1000)
+        assert n == wn and np.array_equal(m, wm) and n > 50
     _, best = take()
     assert np.array_equal(best, mo.distinctive_descriptors(dS, offsets))
 

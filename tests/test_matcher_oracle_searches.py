@@ -347,3 +347,44 @@ def test_fuse_search():
             if d < wbd[m]:
                 wbd[m], wbi[m] = d, j
     assert np.array_equal(bi, wbi) and np.array_equal(bd, wbd) and (bd <= 100).sum() > 30
+
+
+def test_search_by_sim3():
+    rng, Dm, Dk, kxy, uv, valid, level, radius, cells, W, H = _window_problem(31)
+    # keyframe 2 = (Dk, kxy); keyframe 1 = the "map points" with their own positions = the projections moved back by (4, -2)
+    k1 = (uv - np.array([4, -2], np.float32)).astype(np.float32)
+    k1 = np.clip(k1, 0, [W - 1, H - 1]).astype(np.float32)
+    n1, n2 = len(Dm), len(Dk)
+    uv2 = (kxy - np.array([4, -2], np.float32) + rng.randn(n2, 2)).astype(np.float32)        # KF2 points projected into KF1
+    valid2 = (rng.rand(n2) < 0.85).astype(np.uint8)
+    level2 = rng.choice([0, 0, 1, 2], n2).astype(np.int32)
+    radius2 = (np.float32(7.5) * np.float32(1.2) ** level2).astype(np.float32)
+    radius1 = (np.float32(7.5) * np.float32(1.2) ** level).astype(np.float32)
+    n, m12 = mo.search_by_sim3(Dm, valid, uv, radius1, level, Dk, kxy, Dk, valid2, uv2, radius2, level2, Dm, k1, W, H, th_high=1000)
+    f32 = np.float32
+    wInv, hInv = f32(64) / f32(W), f32(48) / f32(H)
+    cells1 = {}
+    for i in range(n1):
+        px, py = int(math.floor(float(f32(k1[i, 0] * wInv)) + 0.5)), int(math.floor(float(f32(k1[i, 1] * hInv)) + 0.5))
+        if 0 <= px < 64 and 0 <= py < 48:
+            cells1.setdefault((px, py), []).append(i)
+
+    def one_way(Dq, ok, uvq, rad, lvl, Dt, kt, ct):
+        out = np.full(len(Dq), -1, np.int64)
+        for i in range(len(Dq)):
+            if not ok[i]:
+                continue
+            best, bi = 2 ** 31 - 1, -1
+            for j in _naive_area(kt, ct, W, H, uvq[i, 0], uvq[i, 1], rad[i], -1, -1):
+                if 0 < lvl[i] - 1 or 0 > lvl[i]:
+                    continue
+                d = mo.descriptor_distance(Dq[i], Dt[j])
+                if d < best:
+                    best, bi = d, j
+            if best <= 1000:
+                out[i] = bi
+        return out
+    a = one_way(Dm, valid, uv, radius1, level, Dk, kxy, cells)
+    b = one_way(Dk, valid2, uv2, radius2, level2, Dm, k1, cells1)
+    want = np.array([a[i] if a[i] >= 0 and b[a[i]] == i else -1 for i in range(n1)], np.int32)
+    assert n == int((want >= 0).sum()) and np.array_equal(m12, want) and n > 20

@@ -421,7 +421,7 @@ int XFBmatcher::SearchByProjection(const std::vector<WindowQuery>& vQueries, con
 
 void XFBmatcher::FuseSearch(const std::vector<WindowQuery>& vQueries, const cv::Mat& descMP, const std::vector<cv::KeyPoint>& vKeysUnKF,
                             const std::vector<float>& vuRightKF, const std::vector<float>& vInvLevelSigma2, const cv::Mat& descKF, float minX,
-                            float minY, float maxX, float maxY, bool bChi2, std::vector<int>& vnBestIdx, std::vector<int>& vnBestDist) const {
+                            float minY, float maxX, float maxY, bool bChi2, std::vector<int>& vnBestIdx, std::vector<int>& vnBestDist, int initDist) const {
   const Grid grid(vKeysUnKF, minX, minY, maxX, maxY);
   std::vector<std::vector<size_t> > cand(vQueries.size());
   std::vector<int32_t> p1, p2;
@@ -449,16 +449,38 @@ void XFBmatcher::FuseSearch(const std::vector<WindowQuery>& vQueries, const cv::
   }
   const std::vector<int32_t> dist = PairDistances(descMP, descKF, p1, p2);
   vnBestIdx.assign(vQueries.size(), -1);
-  vnBestDist.assign(vQueries.size(), 256);
+  vnBestDist.assign(vQueries.size(), initDist);
   size_t cur = 0;
   for (size_t i = 0; i < vQueries.size(); i++) {
-    int bestDist = 256, bestIdx = -1;
+    int bestDist = initDist, bestIdx = -1;
     for (size_t idx : cand[i]) {
       const int d = dist[cur++];
       if (d < bestDist) { bestDist = d; bestIdx = static_cast<int>(idx); }
     }
     vnBestIdx[i] = bestIdx; vnBestDist[i] = bestDist;
   }
+}
+
+int XFBmatcher::SearchBySim3(const std::vector<WindowQuery>& vQueries1, const cv::Mat& descMP1, const std::vector<cv::KeyPoint>& vKeysUn1,
+                             const cv::Mat& desc1, const std::vector<WindowQuery>& vQueries2, const cv::Mat& descMP2,
+                             const std::vector<cv::KeyPoint>& vKeysUn2, const cv::Mat& desc2, float minX, float minY, float maxX, float maxY,
+                             std::vector<int>& vnMatches12) const {
+  const std::vector<float> none;
+  std::vector<int> bi1, bd1, bi2, bd2;
+  // transform from KF1 to KF2 and search (:1690-1760), then from KF2 to KF1 (:1762-1833): bestDist starts at INT_MAX, no chi-square test
+  FuseSearch(vQueries1, descMP1, vKeysUn2, none, none, desc2, minX, minY, maxX, maxY, false, bi1, bd1, INT_MAX);
+  FuseSearch(vQueries2, descMP2, vKeysUn1, none, none, desc1, minX, minY, maxX, maxY, false, bi2, bd2, INT_MAX);
+  // check agreement (:1835-1850)
+  vnMatches12.assign(vQueries1.size(), -1);
+  int nFound = 0;
+  for (size_t i1 = 0; i1 < vQueries1.size(); i1++) {
+    const int idx2 = (bd1[i1] <= TH_HIGH) ? bi1[i1] : -1;
+    if (idx2 >= 0) {
+      const int idx1 = (bd2[idx2] <= TH_HIGH) ? bi2[idx2] : -1;
+      if (idx1 == static_cast<int>(i1)) { vnMatches12[i1] = idx2; nFound++; }
+    }
+  }
+  return nFound;
 }
 
 std::vector<int> XFBmatcher::ComputeDistinctiveDescriptors(const cv::Mat& desc, const std::vector<int>& offsets) const {

@@ -133,7 +133,13 @@ class XFBmatcher {
   // test.  vnBestIdx / vnBestDist: -1 / 256 where nothing qualified; the caller applies `bestDist <= TH_LOW` and Replace / AddObservation.
   void FuseSearch(const std::vector<WindowQuery>& vQueries, const cv::Mat& descMP, const std::vector<cv::KeyPoint>& vKeysUnKF,
                   const std::vector<float>& vuRightKF, const std::vector<float>& vInvLevelSigma2, const cv::Mat& descKF, float minX, float minY,
-                  float maxX, float maxY, bool bChi2, std::vector<int>& vnBestIdx, std::vector<int>& vnBestDist) const;
+                  float maxX, float maxY, bool bChi2, std::vector<int>& vnBestIdx, std::vector<int>& vnBestDist, int initDist = 256) const;
+  // ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, S12, th), src/ORBmatcher.cc:1642-1859.  vQueries1[i1] / vQueries2[i2]: the map point of
+  // that feature projected into the OTHER keyframe (valid = good MapPoint, not already matched, positive depth, in image, distance range);
+  // descMP1 / descMP2 rows = pMP->GetDescriptor().  vnMatches12[i1] = idx2 where both directions agree (vpMatches12[i1] = vpMapPoints2[idx2]).
+  int SearchBySim3(const std::vector<WindowQuery>& vQueries1, const cv::Mat& descMP1, const std::vector<cv::KeyPoint>& vKeysUn1, const cv::Mat& desc1,
+                   const std::vector<WindowQuery>& vQueries2, const cv::Mat& descMP2, const std::vector<cv::KeyPoint>& vKeysUn2, const cv::Mat& desc2,
+                   float minX, float minY, float maxX, float maxY, std::vector<int>& vnMatches12) const;
 
   // MapPoint::ComputeDistinctiveDescriptors, src/MapPoint.cc:329-403, for many map points in one GPU launch: the observed
   // descriptors of map point s are the rows offsets[s] .. offsets[s+1]-1 of `desc`; returns the chosen row (relative to the set).
