@@ -372,10 +372,12 @@ int xfb_create(xfb_ctx** out, const void* weights_blob, size_t n, int device, in
     }
     if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { c->err = cudaGetErrorString(e); r = XFB_ERR_CUDA; break; }
     c->stream = c->own_stream;
-    if (const char* md = getenv("XFB_MS_DEBUG")) {   // profiling aid (match_stream.cu): cycle counters of CTA (0,0); bit flags switch stages off (then results are WRONG)
-      c->ms_mode = atoi(md);
+    if (const char* md = getenv("XFB_MS_DEBUG")) {   // profiling aid (match_stream.cu): cycle counters of CTA (0,0) printed at xfb_destroy
+      // bit 64 also counts survivors; the other bits switch kernel stages OFF for timing ablations (results are then WRONG), so they
+      // are honoured only together with XFB_MS_DEBUG_ABLATE=1
+      c->ms_mode = atoi(md) & (getenv("XFB_MS_DEBUG_ABLATE") ? ~0 : 64);
       if ((e = cudaMalloc(&c->ms_counters, 256)) != cudaSuccess || (e = cudaMemset(c->ms_counters, 0, 256)) != cudaSuccess) { c->err = cudaGetErrorString(e); r = XFB_ERR_CUDA; break; }
-    }   // experiment switch (0 = match_tc.cu, 1 / 2 = match_stream.cu)
+    }
     if ((r = load_weights(c, static_cast<const uint8_t*>(weights_blob), n)) != XFB_OK) break;
     if ((r = alloc_buffers(c)) != XFB_OK) break;
   } while (0);
