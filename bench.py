@@ -64,6 +64,31 @@ def conv_flops_per_frame(h, w):
     return f
 
 
+STRIDE2 = {"block1.1", "block1.3", "block3.0", "block4.0", "block5.0"}   # layers whose input map is one level finer than the output
+
+
+def conv_layer_roofline(ms_per_launch, h, w, batch, peaks):
+    """T_roof of SURVEY.md 8d with measured peaks: per conv layer max(FLOP time, byte time), summed, against the measured time.
+    FLOP time: block1 on the FP32 SIMT pipe (80 TFLOP/s nominal), every other layer as 3xTF32 on the tensor cores
+    (measured bf16 peak / 2 for TF32 / 3 for the split); bytes = input + output activations once (fp32) + weights."""
+    p_tensor = peaks["bf16_tflops"] * 1e12 / 2.0 / 3.0
+    p_simt = 80e12
+    bw = peaks["hbm_gbs"] * 1e9
+    meas = roof = 0.0
+    for name, (cin, cout, k, lvl) in LAYER_GEOM.items():
+        if name not in ms_per_launch:
+            continue
+        lin = lvl - 1 if name in STRIDE2 else lvl
+        byts = 4.0 * batch * (cin * (h >> lin) * (w >> lin) + cout * (h >> lvl) * (w >> lvl)) + 4.0 * cin * cout * k * k
+        tf = layer_flops(name, h, w) * batch / (p_simt if name.startswith("block1") else p_tensor)
+        roof += max(tf, byts / bw) * 1e3
+        meas += ms_per_launch[name]
+    if meas <= 0.0:
+        return None
+    return {"layers": "the BasicLayer convolutions (block1 .. keypoint_head.2)", "measured_ms": meas, "roof_ms": roof, "frac": roof / meas,
+            "pipes": "block1: fp32 SIMT 80 TFLOP/s nominal; others: 3xTF32 = %s bf16 peak / 6; bytes at the %s copy bandwidth" % (peaks["source"], peaks["source"])}
+
+
 def measured_peaks():
     p = REPO / "MEASURED_PEAKS.json"
     if p.exists():
@@ -375,7 +400,8 @@ def run_b200(args):
                     "frac": achieved / peaks["bf16_tflops"], "traffic": traffic, "peak_source": peaks["source"] + " cuBLAS bf16 burst",
                     "pipe_used": pipe, "avg_launch_ms": avg_ms, "launches_timed": kcnt, "algorithmic_flops_per_launch": alg,
                     "share_of_step": round(kms / tot, 4), "top_shares": shares, "kernel_ms_per_step": all_ms,
-                    "whole_path_conv_tflops": conv_flops_per_frame(H, W) * value / max(world, 1) / 1e12}
+                    "whole_path_conv_tflops": conv_flops_per_frame(H, W) * value / max(world, 1) / 1e12,
+                    "conv_layer_roofline": conv_layer_roofline({k: v[0] / max(v[1], 1) for k, v in prof.items()}, H, W, Bsz, peaks)}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             ncpu = os.cpu_count() or 1

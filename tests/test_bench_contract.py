@@ -30,3 +30,13 @@ def test_b200_arm_declares_every_contract_key():
                 '"dtype"', '"data"', '"config"', '"e2e"', '"h2d_bytes_per_step"', '"d2h_bytes_per_step"', '"gpu_launches"', '"roofline"', '"bound"',
                 '"achieved"', '"peak"', '"frac"', '"traffic"', '"cpu_baseline"', '"cores"', '"kind"', '"sample"', '"clocks"', '"workload"'):
         assert key in src, key
+
+
+def test_conv_layer_roofline_arithmetic():
+    """bench.conv_layer_roofline on the committed per-kernel times reproduces profiles/r01_conv_roofline_per_layer.md (0.27)."""
+    sys.path.insert(0, str(REPO))
+    import bench
+    line = json.loads((REPO / "profiles" / "r01_bench_n1.json").read_text())
+    ms = line["roofline"]["kernel_ms_per_step"]                     # one launch of every layer per step
+    r = bench.conv_layer_roofline(ms, 480, 640, 32, {"bf16_tflops": 1604.2, "hbm_gbs": 6521.1, "source": "measured"})
+    assert 1.5 < r["measured_ms"] < 1.9 and 0.44 < r["roof_ms"] < 0.48 and 0.24 < r["frac"] < 0.30
