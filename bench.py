@@ -67,6 +67,13 @@ def conv_flops_per_frame(h, w):
 STRIDE2 = {"block1.1", "block1.3", "block3.0", "block4.0", "block5.0"}   # layers whose input map is one level finer than the output
 
 
+def conv_layer_roofline_safe(*a):
+    try:
+        return conv_layer_roofline(*a)
+    except Exception as ex:   # a reporting extra must never cost the bench line
+        return {"error": repr(ex)}
+
+
 def conv_layer_roofline(ms_per_launch, h, w, batch, peaks):
     """T_roof of SURVEY.md 8d with measured peaks: per conv layer max(FLOP time, byte time), summed, against the measured time.
     FLOP time: block1 on the FP32 SIMT pipe (80 TFLOP/s nominal), every other layer as 3xTF32 on the tensor cores
@@ -401,7 +408,7 @@ def run_b200(args):
                     "pipe_used": pipe, "avg_launch_ms": avg_ms, "launches_timed": kcnt, "algorithmic_flops_per_launch": alg,
                     "share_of_step": round(kms / tot, 4), "top_shares": shares, "kernel_ms_per_step": all_ms,
                     "whole_path_conv_tflops": conv_flops_per_frame(H, W) * value / max(world, 1) / 1e12,
-                    "conv_layer_roofline": conv_layer_roofline({k: v[0] / max(v[1], 1) for k, v in prof.items()}, H, W, Bsz, peaks)}
+                    "conv_layer_roofline": conv_layer_roofline_safe({k: v[0] / max(v[1], 1) for k, v in prof.items()}, H, W, Bsz, peaks)}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             ncpu = os.cpu_count() or 1
