@@ -657,3 +657,38 @@ int mo_search_by_sim3(const float* Dmp1, const uint8_t* valid1, const float* uv1
   free(m1); free(m2);
   return nFound;
 }
+
+/* ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist), src/ORBmatcher.cc:2074-2190
+ * (relocalisation).  Per map point of the keyframe: valid = pMP && !isBad() && !sAlreadyFound.count(pMP) && projection inside the
+ * image bounds && distance in range (:2095-2121); uv, radius = th * mvScaleFactors[nPredictedLevel], level = nPredictedLevel.
+ * occupied_in[i2] = (CurrentFrame.mvpMapPoints[i2] != NULL).  assign[i2] (out) = map point written there.  All octaves are 0 and all
+ * angles -1 (the rotation histogram removes nothing, :2165-2187). */
+int mo_search_by_projection_reloc(const float* Dmp, const uint8_t* valid, const float* uv, const float* radius, const int32_t* level, int n_mp,
+                                  const float* Dcur, const float* kxy, const uint8_t* occupied_in, int n_cur, int img_w, int img_h, int orb_dist,
+                                  int32_t* assign) {
+  mo_grid g;
+  grid_build(&g, kxy, n_cur, img_w, img_h);
+  int* cand = (int*)malloc(sizeof(int) * (size_t)(n_cur > 0 ? n_cur : 1));
+  uint8_t* occupied = (uint8_t*)malloc((size_t)(n_cur > 0 ? n_cur : 1));
+  for (int j = 0; j < n_cur; ++j) { assign[j] = -1; occupied[j] = occupied_in[j]; }
+  int nmatches = 0;
+  for (int m = 0; m < n_mp; ++m) {
+    if (!valid[m]) continue;
+    const int nPredictedLevel = level[m];
+    const int nc = grid_area_minmax(&g, kxy, uv[2 * m], uv[2 * m + 1], radius[m], nPredictedLevel - 1, nPredictedLevel + 1, cand);
+    if (nc == 0) continue;
+    int bestDist = 256, bestIdx2 = -1;
+    for (int c = 0; c < nc; ++c) {
+      const int i2 = cand[c];
+      if (occupied[i2]) continue;
+      const int dist = mo_descriptor_distance(Dmp + (size_t)m * XF_DIM, Dcur + (size_t)i2 * XF_DIM);
+      if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+    }
+    if (bestDist <= orb_dist && bestIdx2 >= 0) {   /* (bestIdx2 >= 0 matters only for ORBdist >= 256: see mo_search_by_projection_frames) */
+      assign[bestIdx2] = m; occupied[bestIdx2] = 1; nmatches++;
+    }
+  }
+  free(cand); free(occupied);
+  grid_free(&g);
+  return nmatches;
+}

@@ -186,3 +186,14 @@ def search_by_sim3(Dmp1, valid1, uv1, radius1, level1, D2, k2xy, Dmp2, valid2, u
     n = L.mo_search_by_sim3(pa1, pv1, pu1, pr1, pl1, a1.shape[0], pd2, pk2, pa2, pv2, pu2, pr2, pl2, a2.shape[0], pd1, pk1, int(img_w), int(img_h),
                             int(th_high), out.ctypes.data_as(ctypes.c_void_p))
     return n, out
+
+
+def search_by_projection_reloc(Dmp, valid, uv, radius, level, Dcur, kxy, occupied, img_w, img_h, orb_dist=100):
+    """ORBmatcher::SearchByProjection(CurrentFrame, KeyFrame*, sAlreadyFound, th, ORBdist), src/ORBmatcher.cc:2074-2190 -> (nmatches, assign)."""
+    Dm, p1 = _f(Dmp); Dc, p2 = _f(Dcur); u, pu = _f(uv); r, pr = _f(radius); kk, pkk = _f(kxy)
+    va, pva = _u8(valid); oc, poc = _u8(occupied); lv, plv = _i(level)
+    out = np.empty(Dc.shape[0], np.int32)
+    L = lib(); L.mo_search_by_projection_reloc.restype = ctypes.c_int
+    n = L.mo_search_by_projection_reloc(p1, pva, pu, pr, plv, Dm.shape[0], p2, pkk, poc, Dc.shape[0], int(img_w), int(img_h), int(orb_dist),
+                                        out.ctypes.data_as(ctypes.c_void_p))
+    return n, out

@@ -239,6 +239,7 @@ int main(int argc, char** argv) {
       const auto wh = b.get<float>("img_wh");
       std::vector<int> assigned;
       put(m.SearchByProjection(qs, M, keypoints(b.get<float>("kB")), B, b.flags("occupied"), 0.f, 0.f, wh[0], wh[1], b.scalar("wq_ratio"), assigned), assigned);
+      put(m.SearchByProjectionReloc(qs, M, keypoints(b.get<float>("kB")), B, b.flags("occupied"), 0.f, 0.f, wh[0], wh[1], 64, assigned), assigned);
       std::vector<int> bi, bd;
       const std::vector<float> sig(8, b.scalar("wq_invsigma2"));
       m.FuseSearch(qs, M, keypoints(b.get<float>("kB")), b.get<float>("uright"), sig, B, 0.f, 0.f, wh[0], wh[1], true, bi, bd);

@@ -118,6 +118,9 @@ def run_searches_case(driver, tmp_path, dA, kA, dB, kB, seed=21, frame_to_frame=
         n, m = take()
         wn, wm = mo.search_by_projection_sim3(dA[src], wq_valid, proj, wq_radius, wq_level, dB, kB, occupied, 640, 480, th_low=100, ratio_hamming=1.0)
         assert n == wn and np.array_equal(m, wm) and n > 50
+        n, m = take()
+        wn, wm = mo.search_by_projection_reloc(dA[src], wq_valid, proj, wq_radius, wq_level, dB, kB, occupied, 640, 480, orb_dist=64)
+        assert n == wn and np.array_equal(m, wm) and n > 50
         _, bi_ = take(); _, bd_ = take()
         wbi, wbd = mo.fuse_search(dA[src], wq_valid, proj, wq_ur, wq_radius, wq_level, dB, kB, uright, 640, 480, inv_sigma2_0=1.0)
         assert np.array_equal(bi_, wbi) and np.array_equal(bd_, wbd) and (wbd <= 100).sum() > 50

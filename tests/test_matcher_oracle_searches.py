@@ -388,3 +388,23 @@ def test_search_by_sim3():
     b = one_way(Dk, valid2, uv2, radius2, level2, Dm, k1, cells1)
     want = np.array([a[i] if a[i] >= 0 and b[a[i]] == i else -1 for i in range(n1)], np.int32)
     assert n == int((want >= 0).sum()) and np.array_equal(m12, want) and n > 20
+
+
+def test_search_by_projection_reloc():
+    rng, Dm, Dk, kxy, uv, valid, level, radius, cells, W, H = _window_problem(37)
+    occupied = (rng.rand(len(Dk)) < 0.15).astype(np.uint8)
+    n, a = mo.search_by_projection_reloc(Dm, valid, uv, radius, level, Dk, kxy, occupied, W, H, orb_dist=64)
+    occ = occupied.copy(); want = np.full(len(Dk), -1, np.int32); cnt = 0
+    for m in range(len(Dm)):
+        if not valid[m]:
+            continue
+        best, bi = 256, -1
+        for j in _naive_area(kxy, cells, W, H, uv[m, 0], uv[m, 1], radius[m], level[m] - 1, level[m] + 1):
+            if occ[j]:
+                continue
+            d = mo.descriptor_distance(Dm[m], Dk[j])
+            if d < best:
+                best, bi = d, j
+        if best <= 64:
+            want[bi] = m; occ[bi] = 1; cnt += 1
+    assert n == cnt and np.array_equal(a, want) and cnt > 30

@@ -381,25 +381,28 @@ int XFBmatcher::SearchByProjection(const std::vector<LastFramePoint>& vLast, con
   return nmatches;
 }
 
-int XFBmatcher::SearchByProjection(const std::vector<WindowQuery>& vQueries, const cv::Mat& descMP, const std::vector<cv::KeyPoint>& vKeysUnKF,
-                                   const cv::Mat& descKF, const std::vector<bool>& vbMatchedKF, float minX, float minY, float maxX, float maxY,
-                                   float ratioHamming, std::vector<int>& vnAssignedKF) const {
-  const Grid grid(vKeysUnKF, minX, minY, maxX, maxY);
+// The window search shared by the loop-closing (:612-717) and relocalisation (:2074-2190) SearchByProjection overloads: candidates in
+// the window whose octave lies in [predictedLevel - 1, predictedLevel + levelHiOffset], not taken yet; the closest one is taken when
+// its distance is <= threshold.
+int XFBmatcher::WindowAssign(const std::vector<WindowQuery>& vQueries, const cv::Mat& descMP, const std::vector<cv::KeyPoint>& vKeys,
+                             const cv::Mat& descKF, const std::vector<bool>& vbTaken, float minX, float minY, float maxX, float maxY,
+                             int levelHiOffset, float threshold, std::vector<int>& vnAssigned) const {
+  const Grid grid(vKeys, minX, minY, maxX, maxY);
   std::vector<std::vector<size_t> > cand(vQueries.size());
   std::vector<int32_t> p1, p2;
   for (size_t iMP = 0; iMP < vQueries.size(); iMP++) {
     const WindowQuery& q = vQueries[iMP];
     if (!q.valid) continue;
-    for (size_t idx : grid.area(vKeysUnKF, q.u, q.v, q.radius)) {     // GetFeaturesInArea(u, v, radius): no level limits (:668)
-      const int kpLevel = vKeysUnKF[idx].octave;
-      if (kpLevel < q.predictedLevel - 1 || kpLevel > q.predictedLevel) continue;   // static filter (:688-691), applied before listing
+    for (size_t idx : grid.area(vKeys, q.u, q.v, q.radius)) {
+      const int kpLevel = vKeys[idx].octave;
+      if (kpLevel < q.predictedLevel - 1 || kpLevel > q.predictedLevel + levelHiOffset) continue;   // static filter, applied before listing
       cand[iMP].push_back(idx);
       p1.push_back(static_cast<int32_t>(iMP)); p2.push_back(static_cast<int32_t>(idx));
     }
   }
   const std::vector<int32_t> dist = PairDistances(descMP, descKF, p1, p2);
-  vnAssignedKF = std::vector<int>(vKeysUnKF.size(), -1);
-  std::vector<bool> matched = vbMatchedKF;
+  vnAssigned = std::vector<int>(vKeys.size(), -1);
+  std::vector<bool> taken = vbTaken;
   int nmatches = 0;
   size_t cur = 0;
   for (size_t iMP = 0; iMP < vQueries.size(); iMP++) {
@@ -407,16 +410,30 @@ int XFBmatcher::SearchByProjection(const std::vector<WindowQuery>& vQueries, con
     int bestDist = 256, bestIdx = -1;
     for (size_t idx : cand[iMP]) {
       const int d = dist[cur++];
-      if (matched[idx]) continue;                                      // vpMatched[idx] (:684)
+      if (taken[idx]) continue;
       if (d < bestDist) { bestDist = d; bestIdx = static_cast<int>(idx); }
     }
-    if (bestDist <= TH_LOW * ratioHamming) {                           // (:705; 100 * ratio < 256, so bestIdx is valid here)
-      vnAssignedKF[bestIdx] = static_cast<int>(iMP);
-      matched[bestIdx] = true;
+    if (bestDist <= threshold && bestIdx >= 0) {      // (bestIdx >= 0 only matters for thresholds >= 256, where the reference indexes [-1])
+      vnAssigned[bestIdx] = static_cast<int>(iMP);
+      taken[bestIdx] = true;
       nmatches++;
     }
   }
   return nmatches;
+}
+
+int XFBmatcher::SearchByProjection(const std::vector<WindowQuery>& vQueries, const cv::Mat& descMP, const std::vector<cv::KeyPoint>& vKeysUnKF,
+                                   const cv::Mat& descKF, const std::vector<bool>& vbMatchedKF, float minX, float minY, float maxX, float maxY,
+                                   float ratioHamming, std::vector<int>& vnAssignedKF) const {
+  // GetFeaturesInArea(u, v, radius) + `kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel` (:668, :688-691); `bestDist <= TH_LOW * ratioHamming` (:705)
+  return WindowAssign(vQueries, descMP, vKeysUnKF, descKF, vbMatchedKF, minX, minY, maxX, maxY, 0, TH_LOW * ratioHamming, vnAssignedKF);
+}
+
+int XFBmatcher::SearchByProjectionReloc(const std::vector<WindowQuery>& vQueries, const cv::Mat& descMP, const std::vector<cv::KeyPoint>& vKeysUnCur,
+                                        const cv::Mat& descCur, const std::vector<bool>& vbOccupiedCur, float minX, float minY, float maxX, float maxY,
+                                        int ORBdist, std::vector<int>& vnAssignedCur) const {
+  // GetFeaturesInArea(u, v, radius, nPredictedLevel - 1, nPredictedLevel + 1) (:2124); `bestDist <= ORBdist` (:2147)
+  return WindowAssign(vQueries, descMP, vKeysUnCur, descCur, vbOccupiedCur, minX, minY, maxX, maxY, 1, static_cast<float>(ORBdist), vnAssignedCur);
 }
 
 void XFBmatcher::FuseSearch(const std::vector<WindowQuery>& vQueries, const cv::Mat& descMP, const std::vector<cv::KeyPoint>& vKeysUnKF,

@@ -128,6 +128,12 @@ class XFBmatcher {
   int SearchByProjection(const std::vector<WindowQuery>& vQueries, const cv::Mat& descMP, const std::vector<cv::KeyPoint>& vKeysUnKF,
                          const cv::Mat& descKF, const std::vector<bool>& vbMatchedKF, float minX, float minY, float maxX, float maxY,
                          float ratioHamming, std::vector<int>& vnAssignedKF) const;
+  // ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist), src/ORBmatcher.cc:2074-2190
+  // (relocalisation): the same window search with GetFeaturesInArea(u, v, radius, level - 1, level + 1) and `bestDist <= ORBdist`.
+  // vbOccupiedCur[i2] = (CurrentFrame.mvpMapPoints[i2] != NULL).
+  int SearchByProjectionReloc(const std::vector<WindowQuery>& vQueries, const cv::Mat& descMP, const std::vector<cv::KeyPoint>& vKeysUnCur,
+                              const cv::Mat& descCur, const std::vector<bool>& vbOccupiedCur, float minX, float minY, float maxX, float maxY,
+                              int ORBdist, std::vector<int>& vnAssignedCur) const;
   // The candidate search of ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th) (src/ORBmatcher.cc:1413-1479; the Sim3 overload :1525-1640 has
   // the same search without the chi-square test): closest keypoint per map point that passes the level filter and the reprojection
   // test.  vnBestIdx / vnBestDist: -1 / 256 where nothing qualified; the caller applies `bestDist <= TH_LOW` and Replace / AddObservation.
@@ -146,6 +152,9 @@ class XFBmatcher {
   std::vector<int> ComputeDistinctiveDescriptors(const cv::Mat& desc, const std::vector<int>& offsets) const;
 
  private:
+  int WindowAssign(const std::vector<WindowQuery>& vQueries, const cv::Mat& descMP, const std::vector<cv::KeyPoint>& vKeys, const cv::Mat& descKF,
+                   const std::vector<bool>& vbTaken, float minX, float minY, float maxX, float maxY, int levelHiOffset, float threshold,
+                   std::vector<int>& vnAssigned) const;
   std::vector<int32_t> PairDistances(const cv::Mat& desc1, const cv::Mat& desc2, const std::vector<int32_t>& i1, const std::vector<int32_t>& i2) const;
   xfb_ctx* ctx_;
   float mfNNratio;
