@@ -76,7 +76,9 @@ int xfb_extract_batch_device(xfb_ctx* ctx, const uint8_t* d_gray, int batch, siz
 
 /* Replaces ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2242-2250) for all pairs:
  * out[i*n2 + j] = int(float(||A_i - B_j||^2) * 512), A [n1,64], B [n2,64] fp32 rows
- * (cv::Mat CV_32F descriptor rows).  Bit-exact w.r.t. oracle/matcher_oracle.c. */
+ * (cv::Mat CV_32F descriptor rows).  Bit-exact w.r.t. oracle/matcher_oracle.c for FINITE rows of any
+ * norm whose distance fits an int (the tensor-core shortcut's error bound scales with |a||b| per pair;
+ * large norms simply take the exact path more often).  XFeat descriptors are unit vectors. */
 int xfb_distance_matrix(xfb_ctx* ctx, const float* A, int n1, const float* B, int n2, int32_t* out);
 int xfb_distance_matrix_device(xfb_ctx* ctx, const float* d_A, int n1, const float* d_B, int n2, int32_t* d_out);
 
@@ -100,7 +102,10 @@ int xfb_distance_pairs_device(xfb_ctx* ctx, const float* d_A, int n1, const floa
  *                     SearchForInitialization :860)
  * Outputs: best_idx[n1] (-1 = none), best_dist[n1], second_dist[n1]; best_idx_rev[n2] /
  * best_dist_rev[n2] = the same argmin taken column-wise (for mutual-NN checks, the spec of the
- * commented-out ORBmatcher::match, src/ORBmatcher.cc:340-406).  Any output may be NULL. */
+ * commented-out ORBmatcher::match, src/ORBmatcher.cc:340-406).  Any output may be NULL.
+ * Rows are finite fp32 of any norm: the fp16 tensor-core filter is used while |row|^2 < 1e5 (XFeat
+ * descriptors are unit vectors); a set with a larger row is matched on the exact path alone (slow,
+ * still bit-exact). */
 int xfb_match(xfb_ctx* ctx, const float* A, int n1, const float* B, int n2, const int32_t* group_a, const int32_t* group_b,
               int init_dist, int32_t* best_idx, int32_t* best_dist, int32_t* second_dist, int32_t* best_idx_rev,
               int32_t* best_dist_rev);
@@ -194,8 +199,9 @@ long xfb_debug_read_stats(xfb_ctx* ctx, const char* name, int frame, float* host
  * on oracle-provided inputs.  Inputs are host fp32; outputs as in xfb_extract. */
 int xfb_debug_post(xfb_ctx* ctx, int H, int W, const float* feats, const float* H1, const float* K1h, int topk, float nms_thr,
                    int32_t* n_valid, float* kpt_xy, float* score, float* desc);
-/* Largest |t - 512*float(||a-b||^2)| over all pairs, where t is the tensor-core (3xTF32) estimate the
- * matcher filters on: must stay well below the kernel's MATCH_EPS = 0.02 for the filter to be sound. */
+/* Largest |t - 512*float(||a-b||^2)| over all pairs, where t is the tensor-core estimate (bf16 two-piece split,
+ * a1.b1 + a1.b2 + a2.b1) that xfb_distance_matrix takes floor() of: must stay below the kernel's per-pair bound
+ * eps = 0.03 |a||b| + 0.01 (|a|^2 + |b|^2) + 0.005 (csrc/match_tc.cu match_eps) for the shortcut to be sound. */
 int xfb_debug_match_error(xfb_ctx* ctx, const float* A, int n1, const float* B, int n2, float* max_err);
 /* Number of NMS candidates (score > 0) of `frame` in the last extract call. */
 int xfb_debug_candidates(xfb_ctx* ctx, int frame);

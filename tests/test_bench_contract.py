@@ -38,5 +38,5 @@ def test_conv_layer_roofline_arithmetic():
     import bench
     line = json.loads((REPO / "profiles" / "r01_bench_n1.json").read_text())
     ms = line["roofline"]["kernel_ms_per_step"]                     # one launch of every layer per step
-    r = bench.conv_layer_roofline(ms, 480, 640, 32, {"bf16_tflops": 1604.2, "hbm_gbs": 6521.1, "source": "measured"})
+    r = bench.conv_layer_roofline(ms, 480, 640, 32, {"bf16_tflops": 1604.2, "hbm_gbs": 6521.1, "source": "measured"}, split_cost=6.0, split_name="3xTF32")
     assert 1.5 < r["measured_ms"] < 1.9 and 0.44 < r["roof_ms"] < 0.48 and 0.24 < r["frac"] < 0.30

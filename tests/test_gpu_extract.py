@@ -117,6 +117,42 @@ def test_end_to_end_against_reference_golden(name, tol_common):
     ctx.close()
 
 
+@pytest.mark.parametrize("name", ["vga_top4096", "vga_top1000", "hd720_top1000"])
+def test_keypoint_set_differs_only_at_the_kth_score_boundary(name):
+    """The claim behind the '>= 98 % common keypoints' tolerances, asserted: a keypoint of the reference's top-k that is
+    missing from ours (or vice versa) sits AT the k-th score boundary -- its reference score is within 2 * SCORE_TOL of the
+    reference's k-th score -- or is one of a handful of NMS flips (a 5x5 maximum / the 0.05 threshold decided by < 1e-5)."""
+    from xfeatslam_b200.capi import XFeatB200
+    g, frame, nfeat, lap = gold(name)
+    ctx = XFeatB200(max_h=frame.shape[0], max_w=frame.shape[1], max_batch=1, max_topk=8192)
+    full = ctx.extract(frame, 8192)                                          # our candidates in score order (all of them at VGA)
+    n_full = int(full["n_valid"])
+    ours_all = {(int(x), int(y)): float(s) for (x, y), s in zip(full["kpts"][:n_full], full["scores"][:n_full])}
+    ours_top = {(int(x), int(y)) for x, y in full["kpts"][:nfeat]}           # top-k is a prefix (test_topk_8192_returns_every_candidate)
+    ref_all = {(int(x), int(y)): float(s) for (x, y), s in zip(g["nms_kpts"][0], g["scores_all"][0]) if s > 0}
+    gk = g["out_keypoints"]
+    gk = gk[gk[:, 2] > 0]
+    ref_top = {(int(x), int(y)) for x, y in gk[:, :2]}
+    assert len(ref_top) == nfeat and len(ours_top) == nfeat
+    kth_ref = float(gk[:, 2].min())
+    flips = 0
+    for p in ref_top - ours_top:
+        if p not in ours_all and n_full < 8192:
+            flips += 1
+            continue
+        assert ref_all[p] - kth_ref <= 2 * SCORE_TOL, ("reference keypoint missing although well above the cut-off", p, ref_all[p], kth_ref)
+    for p in ours_top - ref_top:
+        if p not in ref_all:
+            flips += 1
+            continue
+        assert kth_ref - ref_all[p] <= 2 * SCORE_TOL, ("extra keypoint although well below the reference's cut-off", p, ref_all[p], kth_ref)
+    print("%s: |ref - ours| = %d, |ours - ref| = %d, NMS flips = %d" % (name, len(ref_top - ours_top), len(ours_top - ref_top), flips))
+    assert flips <= 3
+    common = sorted(ours_top & ref_top)
+    np.testing.assert_allclose([ours_all[p] for p in common], [ref_all[p] for p in common], atol=SCORE_TOL, rtol=0)
+    ctx.close()
+
+
 def test_batch_equals_single_frames(xfb_vga):
     """Per-frame BatchNorm statistics: a batch launch equals B batch-1 runs, bit for bit."""
     frames = synthetic_frames(40, 3, 480, 640)

@@ -109,7 +109,8 @@ def test_node_gated_and_window_searches_replay_the_oracle(driver, tmp_path):
     with pytest.raises(RuntimeError):
         ctx.distance_pairs(dA, dB, np.array([na], np.int32), np.array([0], np.int32))  # index out of range -> XFB_ERR_ARG
     ctx.close()
-    host_cases.run_searches_case(driver, tmp_path, dA, kA, dB, kB)
+    # frame_to_frame=True: every M5 replay (SearchByProjection x5, Fuse x2, SearchBySim3) runs over the B200's distances too
+    host_cases.run_searches_case(driver, tmp_path, dA, kA, dB, kB, frame_to_frame=True)
 
 
 def test_vocabulary_transform_on_device(driver, tmp_path):

@@ -93,7 +93,7 @@ def test_full_size_4096_properties(ctx):
 
 def test_tensor_core_estimate_error_bound(ctx):
     """The matcher filters on a tensor-core estimate t of 512*d (bf16 split a1.b1 + a1.b2 + a2.b1); the filter is
-    sound while |t - 512*float(S)| < MATCH_EPS = 0.04 (csrc/match_tc.cu).  Measure the actual maximum over all pairs."""
+    sound while |t - 512*float(S)| < match_eps(|a|^2, |b|^2) = 0.055 for unit rows (csrc/match_tc.cu).  Measure the actual maximum."""
     rng = np.random.RandomState(13)
     A = unit(rng, 1024)
     B = np.concatenate([related(rng, A, 512, 0.02), related(rng, A, 256, 0.3), unit(rng, 256)]).astype(np.float32)
@@ -101,3 +101,22 @@ def test_tensor_core_estimate_error_bound(ctx):
     B[4] = A[0]                                            # exact duplicate -> distance 0
     err = ctx.match_error(A, B)
     assert err < 0.02, err
+
+
+@pytest.mark.parametrize("scale_a,scale_b", [(3.0, 0.25), (40.0, 40.0), (1e-3, 1.0), (400.0, 1.0)])
+def test_non_unit_norm_rows_bit_exact(ctx, scale_a, scale_b):
+    """The C-ABI takes arbitrary finite fp32 rows: the tensor-core shortcuts carry PER-PAIR error bounds that scale with
+    |a||b| (csrc/match_tc.cu match_eps, csrc/match_stream.cu e / `wild`), so results stay bit-exact off the unit sphere
+    (rows with |x|^2 >= 1e5 leave the fp16 filter's range and are verified exhaustively)."""
+    rng = np.random.RandomState(int(scale_a * 1000 + scale_b * 10) % 2 ** 31)
+    A = (unit(rng, 300) * scale_a * rng.uniform(0.5, 1.5, (300, 1))).astype(np.float32)
+    B = (related(rng, unit(rng, 300), 260, 0.05) * scale_b * rng.uniform(0.5, 1.5, (260, 1))).astype(np.float32)
+    B[5] = A[7]                                            # an exact duplicate across the sets -> distance 0
+    # distances stay inside the int range: ||a-b||^2 * 512 < 2^31
+    assert (np.linalg.norm(A, axis=1).max() + np.linalg.norm(B, axis=1).max()) ** 2 * 512 < 2 ** 31
+    assert np.array_equal(ctx.distance_matrix(A, B), mo.distance_matrix(A, B))
+    for init in (INT_MAX, 256):
+        got = ctx.match(A, B, init=init)
+        want = mo.bruteforce(A, B, init=init)
+        for name, g, w in zip(("best_idx", "best_dist", "second_dist", "rev_idx", "rev_dist"), got, want):
+            assert np.array_equal(g, w), (name, init)

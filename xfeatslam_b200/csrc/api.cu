@@ -66,7 +66,7 @@ static const float* blob_find(const uint8_t* blob, size_t n, const std::string& 
     std::memcpy(nm, e.name, 48);
     nm[48] = 0;
     if (name == nm) {
-      if (e.offset + e.nbytes > n || e.nbytes != expect_elems * 4 || (e.offset & 3)) return nullptr;
+      if (e.offset > n || e.nbytes > n - e.offset || e.nbytes != expect_elems * 4 || (e.offset & 3)) return nullptr;
       return reinterpret_cast<const float*>(blob + e.offset);
     }
   }
@@ -247,6 +247,8 @@ static int tc_matrix_generic(Ctx* c, const float* dA, int n1, const float* dB, i
 // frames of the last extract: pairs (host) -> outputs [n_pairs][K] (device pointers, nullable)
 static int tc_match_frames(Ctx* c, const int32_t* pairs, int n_pairs, int init, int32_t* o[5]) {
   const int K = c->last_topk, P = pad128(K);
+  // xfb_submit runs its matcher on s_match: any other stream must not touch the shared per-frame images before that is done
+  if (c->ev_match_free && c->stream != c->s_match) XFB_CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_match_free, 0));
   if (!c->ms_fimg || c->ms_frows < P) {
     if (c->ms_fimg) cudaFree(c->ms_fimg);
     if (c->tc_fnrm) cudaFree(c->tc_fnrm);

@@ -10,7 +10,7 @@
 //       as a COLUMN: [ b_0 .. b_63 | p1 p2 p3 0 ... ],  p1 + p2 + p3 = -|b|^2 / 2  (three fp16 pieces, residual 2^-33)
 //     so the K = 80 GEMM yields  u_ij = a_i.b_j - |b_j|^2 / 2  directly and  t_ij = 512 |a_i|^2 - 1024 u_ij  ~  512 d_ij
 //     with  |t - 512 float(d)| <= e_i = 1.05 sqrt(|a_i|^2 max|b|^2) + small  (fp16 rounding of both operands, rigorous;
-//     descriptors must fit fp16: |x| < 6e4 -- XFeat descriptors are unit vectors).  Images are in the canonical K-major
+//     a row with |x|^2 >= 1e5 does not fit the fp16 images -- its candidates are then ALL verified exactly, see `wild`).  Images are in the canonical K-major
 //     no-swizzle UMMA layout (16-byte K chunks 2048 B apart, 8-row groups 128 B apart): a 128-row block = one 20 KB bulk copy.
 //   * ms_kernel, one CTA per (128 rows, frame pair): the row block is copied ONCE into tensor memory (tcgen05.st, columns
 //     384..423) and used as the A operand from there (tcgen05.mma with A in TMEM), so each 128 x 128 x 16 MMA reads only its
@@ -381,8 +381,10 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ms_kernel(const MatchTcArgs a) 
     const int row = row0 + rs;
     const bool ok = row < nA;
     float base = 0.f, margin = 0.f, cap = -CUDART_INF_F;
+    bool wild = false;   // operands outside the fp16 filter's range (the column tail -|b|^2/2 must fit fp16): verify every column exactly
     if (ok) {
       const float na = a.nrmA[(size_t)setA * a.rows_padded_A + row], nbm = a.nrm_max_B[setB];
+      wild = !(na < 1.0e5f && nbm < 1.0e5f);
       const float e = 1.05f * sqrtf(na * nbm) + 0.02f * (na + nbm + 1.0f);   // |t - 512 float(d)| <= e
       base = 512.0f * na;
       margin = 2.0f * e + 1.0f;
@@ -443,7 +445,7 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ms_kernel(const MatchTcArgs a) 
       uint32_t wneed = 0;
 #pragma unroll
       for (int part = 0; part < MS_PARTS; ++part) {
-        const bool need = (use_rec && passes == 2) ? (__half2float(sRec[(c * MS_PARTS + part) * NROW + rs]) > tau) : ok;
+        const bool need = (use_rec && passes == 2 && !wild) ? (__half2float(sRec[(c * MS_PARTS + part) * NROW + rs]) > tau) : ok;
         wneed |= __any_sync(0xffffffffu, need) ? (1u << part) : 0u;
       }
       if (a.ms_mode & 1) wneed = 0;                 // (timing experiment)
@@ -459,6 +461,7 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ms_kernel(const MatchTcArgs a) 
         uint32_t mask = 0;
 #pragma unroll
         for (int e = 0; e < 32; ++e) mask |= (vv[e] > tau) ? (1u << e) : 0u;
+        if (wild) mask = 0xffffffffu;
         const int j0 = c * MS_ROWS + part * 32;
         if (j0 + 32 > nB) mask &= (nB > j0) ? (0xffffffffu >> (32 - (nB - j0))) : 0u;   // padded columns
         if (GROUPED) {   // vocabulary-node gating: drop the columns of other nodes

@@ -8,8 +8,8 @@
 //      images in the canonical K-major no-swizzle UMMA layout ([16-byte K chunk][8-row group][8 rows][16 B]; LBO = 2048 B,
 //      SBO = 128 B), so a 128-row block is ONE contiguous bulk copy; |a|^2.
 //   1. match_tc_kernel: dot(a_i, b_j) ~ a1.b1 + a1.b2 + a2.b1 (three bf16 UTCHMMA per 16 k; |error| < 3 * 2^-18 |a||b|), fp32
-//      accumulators in TMEM;  t_ij = 512 (|a_i|^2 + |b_j|^2 - 2 dot) ~ 512 d_ij within +-MATCH_EPS.  Epilogue (one thread per
-//      row = TMEM lane): D = floor(t) when t is farther than MATCH_EPS from an integer (92 % of the pairs), else the exact
+//      accumulators in TMEM;  t_ij = 512 (|a_i|^2 + |b_j|^2 - 2 dot) ~ 512 d_ij within +-eps(|a|,|b|) (match_eps).  Epilogue (one thread per
+//      row = TMEM lane): D = floor(t) when t is farther than eps from an integer (92 % of the pairs), else the exact
 //      fp64 re-evaluation from the original fp32 rows.
 //
 // Warp roles (576 threads): warp 0 = loader (cp.async.bulk + mbarrier complete_tx), warp 1 = TMEM allocator + tcgen05.mma
@@ -27,7 +27,10 @@ constexpr int TC_ROWS = 128;                      // rows (or columns) per opera
 constexpr int TC_PIECE_BYTES = TC_ROWS * 64 * 2;  // one bf16 piece image of a block = 16 KB
 constexpr int TC_BLK_BYTES = 2 * TC_PIECE_BYTES;  // [a1 | a2] = 32 KB
 constexpr int TC_BLK_STRIDE = TC_BLK_BYTES / 4;   // in floats (the image buffers are addressed as float*)
-constexpr float MATCH_EPS = 0.04f;                // bound on |t - 512*float(S)| (rigorous ~0.013 + fp32 accumulation; measured, see xfb_debug_match_error)
+// |t - 512*float(S)| <= eps(a, b): the bf16 two-piece split leaves |dot error| <= 3 * 2^-18 |a||b| (x 1024 = 0.0117 |a||b|), the fp32
+// accumulation / re-association a few ulps of the operands' scale.  The bound is PER PAIR (it scales with the norms), so the
+// floor() shortcut is sound for descriptors of any norm; when eps >= 0.5 every pair takes the exact path.
+__device__ __forceinline__ float match_eps(float na, float nb) { return 0.03f * sqrtf(na * nb) + 2e-5f * 512.0f * (na + nb) + 0.005f; }
 constexpr int TC_PARTS = 4;                       // 32-column slices per block = epilogue threads per row
 constexpr int TC_EPI_WARPS = 4 * TC_PARTS;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
@@ -188,7 +191,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(const MatchTcAr
     const int r = quad * 32 + lane;                  // row inside the tile
     const int row = row0 + r;
     const bool row_ok = row < nA;
-    const float base = row_ok ? 512.0f * a.nrmA[(size_t)setA * a.rows_padded_A + row] : 0.f;
+    const float na = row_ok ? a.nrmA[(size_t)setA * a.rows_padded_A + row] : 0.f;
+    const float base = 512.0f * na;
     const float* nrmB = nb_smem ? sNb : a.nrmB + (size_t)setB * a.rows_padded_B;
     const float* rawB = a.rawB + (size_t)setB * a.raw_stride_B;
     const float* arow = a.rawA + (size_t)setA * a.raw_stride_A + (size_t)(row_ok ? row : 0) * 64;
@@ -222,8 +226,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(const MatchTcAr
             for (int q = 1; q < 32; ++q) ue = (q == e) ? v[q] : ue;
             const float t = fmaf(-1024.0f, ue, base);
             const float f = floorf(t), fr = t - f;
+            const float eps = match_eps(na, nrmB[j]);           // NaN / inf (huge norms) fail both comparisons -> exact path
             int D;
-            if (fr > MATCH_EPS && fr < 1.0f - MATCH_EPS && t > 0.5f) D = (int)f;
+            if (fr > eps && fr < 1.0f - eps && t > 0.5f) D = (int)f;
             else D = exact_distance(arow, rawB + (size_t)j * 64);
             a.matrix[(size_t)row * nB + j] = D;
             if (a.dbg_maxerr) dbg_max = fmaxf(dbg_max, fabsf(t - exact_scaled(arow, rawB + (size_t)j * 64)));

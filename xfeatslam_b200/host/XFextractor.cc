@@ -5,6 +5,7 @@
 // its mono / lapping-area placement (:310-356).
 #include "XFextractor.h"
 
+#include <algorithm>
 #include <cassert>
 #include <cmath>
 #include <cstdlib>
@@ -65,6 +66,9 @@ XFextractor::~XFextractor() { xfb_destroy(ctx_); }
 
 void XFextractor::EnsureContext(int h, int w) {
   if (ctx_ && h <= ctx_h_ && w <= ctx_w_) return;
+  // grow only: keep the capacity of every size seen so far, so that alternating sizes (480x752, then 512x640) re-create once
+  h = std::max(h, ctx_h_);
+  w = std::max(w, ctx_w_);
   xfb_destroy(ctx_);
   ctx_ = nullptr;
   int device = 0;
