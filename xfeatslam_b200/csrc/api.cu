@@ -107,6 +107,10 @@ static int load_weights(Ctx* c, const uint8_t* blob, size_t n) {
       conv_tc_pack_weights(L, src, sp.cout, sp.cin, sp.ks, img);
       XFB_ALLOC(c, c->wimg[L], img.size() * 4);
       XFB_CUDA_OK(c, cudaMemcpy(c->wimg[L], img.data(), img.size() * 4, cudaMemcpyHostToDevice));
+      std::vector<unsigned char> img2;
+      c->wscale2[L] = conv_tc2_pack_weights(L, src, sp.cout, sp.cin, sp.ks, img2);
+      XFB_ALLOC(c, c->wimg2[L], img2.size());
+      XFB_CUDA_OK(c, cudaMemcpy(c->wimg2[L], img2.data(), img2.size(), cudaMemcpyHostToDevice));
     }
     if (!is_basic) {
       const std::string bname = std::string(sp.ref_name) + ".bias";
@@ -144,6 +148,7 @@ static int alloc_buffers(Ctx* c) {
   size_t pe = conv_part_elems((int)H, (int)W);
   if (conv_tc_part_elems((int)H, (int)W) > pe) pe = conv_tc_part_elems((int)H, (int)W);
   if (conv_small_part_elems((int)H, (int)W) > pe) pe = conv_small_part_elems((int)H, (int)W);
+  if ((conv_tc2_part_floats((int)H, (int)W) + 1) / 2 > pe) pe = (conv_tc2_part_floats((int)H, (int)W) + 1) / 2;
   const size_t prep_pe = ((HW + 2047) / 2048) * 2;
   if (prep_pe > pe) pe = prep_pe;
   c->part_elems = pe;
@@ -297,7 +302,7 @@ static int run_dense(Ctx* c, const uint8_t* d_gray, size_t frame_stride, int str
                                L_B4_0, L_B4_1, L_B4_2, L_B5_0, L_B5_1, L_B5_2, L_B5_3};
   auto conv = [&](int L) {
     if (c->force_simt) return launch_conv_layer(c, L);                 // generic FP32 SIMT kernels (A/B reference)
-    if (conv_tc_handles(L)) return launch_conv_tc_layer(c, L);         // tcgen05 implicit GEMM (Cin >= 24)
+    if (conv_tc_handles(L)) return c->conv_tc_version == 2 ? launch_conv_tc2_layer(c, L) : launch_conv_tc_layer(c, L);   // tcgen05 implicit GEMM (Cin >= 24)
     if (conv_small_handles(L)) return launch_conv_small_layer(c, L);   // block1: bandwidth-shaped SIMT
     return launch_conv_layer(c, L);
   };
@@ -309,7 +314,7 @@ static int run_dense(Ctx* c, const uint8_t* d_gray, size_t frame_stride, int str
   static const int order3[] = {L_KP_0, L_KP_1, L_KP_2};
   for (int L : order3) XFB_CUDA_OK(c, conv(L));
   if (c->force_simt) XFB_CUDA_OK(c, launch_keypoint_out(c));
-  else XFB_CUDA_OK(c, launch_conv_tc_layer(c, L_KP_3));
+  else XFB_CUDA_OK(c, c->conv_tc_version == 2 ? launch_conv_tc2_layer(c, L_KP_3) : launch_conv_tc_layer(c, L_KP_3));
   return XFB_OK;
 }
 
@@ -372,6 +377,8 @@ int xfb_create(xfb_ctx** out, const void* weights_blob, size_t n, int device, in
       r = XFB_ERR_CUDA;
       break;
     }
+    c->num_sms = prop.multiProcessorCount;
+    if (const char* cv = getenv("XFB_CONV_TC")) c->conv_tc_version = (atoi(cv) == 1) ? 1 : 2;   // A/B: 1 = the round-1 one-tile-per-CTA 3xTF32 kernels
     if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { c->err = cudaGetErrorString(e); r = XFB_ERR_CUDA; break; }
     c->stream = c->own_stream;
     if (const char* md = getenv("XFB_MS_DEBUG")) {   // profiling aid (match_stream.cu): cycle counters of CTA (0,0) printed at xfb_destroy
@@ -397,7 +404,7 @@ void xfb_destroy(xfb_ctx* c) {
   cudaSetDevice(c->device);
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
   auto fr = [](void* p) { if (p) cudaFree(p); };
-  for (int L = 0; L < L_NUM; ++L) { fr(c->w[L]); fr(c->bias[L]); fr(c->act[L]); fr(c->wimg[L]); }
+  for (int L = 0; L < L_NUM; ++L) { fr(c->w[L]); fr(c->bias[L]); fr(c->act[L]); fr(c->wimg[L]); fr(c->wimg2[L]); }
   for (int L = 0; L < L_NUM_BN; ++L) { fr(c->bn[L].mean); fr(c->bn[L].rstd); }
   fr(c->d_gray); fr(c->xraw); fr(c->xn); fr(c->avg4); fr(c->pyr); fr(c->k1h); fr(c->in_mean); fr(c->in_rstd); fr(c->part);
   fr(c->ticket); fr(c->cand); fr(c->cand_count); fr(c->cand_count_last); fr(c->o_nvalid); fr(c->o_xy); fr(c->o_score); fr(c->o_desc);

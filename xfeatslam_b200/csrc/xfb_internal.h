@@ -77,6 +77,10 @@ struct Ctx {
   float* w[L_NUM] = {};
   float* bias[L_NUM] = {};
   float* wimg[L_NUM] = {};        // tensor-core layers: per-tap hi/lo UMMA operand images (conv_tc.cu)
+  unsigned char* wimg2[L_NUM] = {};   // persistent kernel (conv_tc2.cu): fp16 hi/lo operand images, resident in shared memory
+  float wscale2[L_NUM] = {};      // its epilogue factor 1 / (activation scale * weight scale)
+  int conv_tc_version = 2;        // 2 = conv_tc2.cu (default), 1 = conv_tc.cu (XFB_CONV_TC=1: A/B reference)
+  int num_sms = 148;
   bool force_simt = false;        // debug: run every conv on the FP32 SIMT kernels (A/B parity tests)
 
   // geometry of the last extract call
@@ -234,6 +238,9 @@ cudaError_t launch_conv_small_layer(Ctx* c, int layer);
 bool conv_tc_handles(int layer);
 void conv_tc_pack_weights(int layer, const float* oihw, int cout, int cin, int ks, std::vector<float>& img);
 cudaError_t launch_conv_tc_layer(Ctx* c, int layer);  // partial-sum scratch (doubles) needed per frame
+size_t conv_tc2_part_floats(int H, int W);
+float conv_tc2_pack_weights(int layer, const float* oihw, int cout, int cin, int ks, std::vector<unsigned char>& img);
+cudaError_t launch_conv_tc2_layer(Ctx* c, int layer);
 
 }  // namespace xfb
 
