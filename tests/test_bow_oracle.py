@@ -64,3 +64,57 @@ def test_real_orbvoc_shape():
     d = z["out_descriptors"][:200]
     leaf, nid = mo.bow_transform(d, v["node_desc"], v["child_start"], v["child_index"], v["L"], 4)
     assert np.all(v["is_leaf"][leaf] == 1) and np.all(nid > 0)
+
+
+# ---- the pin: the reference's OWN DBoW2 (thirdparty/DBoW2 compiled unchanged -> oracle/_ref/ref_dbow2) -------------------------
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def assemble(desc, voc, levelsup):
+    """BowVector / FeatureVector of TemplatedVocabulary::transform (TemplatedVocabulary.h:1147-1193, TF_IDF + L1) from the oracle's walk."""
+    wl, wn = mo.bow_transform(desc, voc["node_desc"], voc["child_start"], voc["child_index"], voc["L"], levelsup)
+    v, fv = {}, {}
+    for i in range(len(desc)):
+        w = float(voc["weight"][wl[i]])
+        if w > 0:
+            wid = int(voc["word_id"][wl[i]])
+            v[wid] = v.get(wid, 0.0) + w
+            fv.setdefault(int(wn[i]), []).append(i)
+    norm = 0.0
+    for k in sorted(v):
+        norm += abs(v[k])
+    bow = np.array([[k, v[k] / norm] for k in sorted(v)], np.float64).reshape(-1, 2)
+    flat = []
+    for k in sorted(fv):
+        flat += [k, len(fv[k])] + fv[k]
+    return wl, wn, bow, np.array(flat, np.int32)
+
+
+@pytest.mark.parametrize("name", ["dbow2_k10L4", "dbow2_k4L5", "dbow2_k3L2"])
+def test_oracle_walk_pinned_against_reference_dbow2_golden(name):
+    """tests/golden/dbow2_*.npz = outputs of the reference's own TemplatedVocabulary<FORB>::transform (tools/make_golden_dbow2.py):
+    word id, node id, BowVector (bit-identical doubles) and FeatureVector must be reproduced by the oracle restatement."""
+    from tools.make_golden_dbow2 import descriptors
+    z = np.load(GOLD / (name + ".npz"))
+    k, L, seed, n, levelsup = [int(x) for x in z["meta"]]
+    voc = orbvoc.synthetic(k=k, L=L, seed=seed)
+    desc = descriptors(seed, n)
+    wl, wn, bow, fv = assemble(desc, voc, levelsup)
+    assert np.array_equal(voc["word_id"][wl], z["leaf"][:, 0])                       # WordId of every feature
+    assert np.array_equal(wn, z["leaf"][:, 1])                                       # NodeId at level L - levelsup
+    assert np.array_equal((voc["weight"][wl] > 0).astype(np.int32), z["leaf"][:, 2])
+    assert np.array_equal(bow, z["bow"])                                             # same doubles, same order
+    assert np.array_equal(fv, z["fv"])
+
+
+@pytest.mark.skipif(not (Path(__file__).resolve().parents[1] / "oracle" / "_ref" / "ref_dbow2").exists(), reason="oracle/_ref/ref_dbow2 is built where the reference tree is mounted")
+def test_oracle_walk_against_reference_dbow2_live():
+    """The same comparison on fresh inputs, running the reference binary now (other seeds, levelsup = 0 .. L + 1)."""
+    from tools.make_golden_dbow2 import descriptors, run_reference
+    voc = orbvoc.synthetic(k=5, L=3, seed=11)
+    desc = descriptors(77, 300)
+    for levelsup in (0, 1, 2, 3, 4):
+        leaf, bow_ref, fv_ref = run_reference(voc, desc, levelsup)
+        wl, wn, bow, fv = assemble(desc, voc, levelsup)
+        assert np.array_equal(voc["word_id"][wl], leaf[:, 0]) and np.array_equal(wn, leaf[:, 1])
+        assert np.array_equal(bow, bow_ref) and np.array_equal(fv, fv_ref)

@@ -387,6 +387,9 @@ int xfb_create(xfb_ctx** out, const void* weights_blob, size_t n, int device, in
       c->ms_mode = atoi(md) & (getenv("XFB_MS_DEBUG_ABLATE") ? ~0 : 64);
       if ((e = cudaMalloc(&c->ms_counters, 256)) != cudaSuccess || (e = cudaMemset(c->ms_counters, 0, 256)) != cudaSuccess) { c->err = cudaGetErrorString(e); r = XFB_ERR_CUDA; break; }
     }
+    if (getenv("XFB_T2_DEBUG")) {   // profiling aid (conv_tc2.cu): per-role cycle counters of CTA 0, printed per layer at xfb_destroy
+      if ((e = cudaMalloc(&c->t2_counters, L_NUM * 32 * 8)) != cudaSuccess || (e = cudaMemset(c->t2_counters, 0, L_NUM * 32 * 8)) != cudaSuccess) { c->err = cudaGetErrorString(e); r = XFB_ERR_CUDA; break; }
+    }
     if ((r = load_weights(c, static_cast<const uint8_t*>(weights_blob), n)) != XFB_OK) break;
     if ((r = alloc_buffers(c)) != XFB_OK) break;
   } while (0);
@@ -411,6 +414,21 @@ void xfb_destroy(xfb_ctx* c) {
   fr(c->m_a); fr(c->m_b); fr(c->m_ga); fr(c->m_gb); fr(c->m_matrix);
   for (int i = 0; i < 5; ++i) { fr(c->m_out[i]); fr(c->m_pairs_out[i]); }
   for (int i = 0; i < 2; ++i) { fr(c->tc_img[i]); fr(c->tc_nrm[i]); }
+  if (c->t2_counters) {
+    std::vector<unsigned long long> h(L_NUM * 32);
+    cudaMemcpy(h.data(), c->t2_counters, h.size() * 8, cudaMemcpyDeviceToHost);
+    for (int L = 0; L < L_NUM; ++L) {
+      const unsigned long long* q = &h[(size_t)L * 32];
+      if (!q[0]) continue;
+      const double n = (double)q[0], tl = q[16] ? (double)q[16] : 1.0, st = q[5] ? (double)q[5] : 1.0;
+      fprintf(stderr, "[xfb t2] %-16s launches %llu | CTA0 cycles/launch %.0f, tiles/launch %.1f | producer per stage: wait_free %.0f work %.0f fence+arrive %.0f | "
+              "mma per tile: wait_in %.0f wait_acce %.0f issue %.0f wait_w(total/launch) %.0f | epilogue per tile: wait_accf %.0f ld+store %.0f stats %.0f "
+              "part+fence %.0f ticket %.0f fold+loop %.0f\n",
+              kLayers[L].ref_name, q[0], q[1] / n, tl / n, q[2] / st, q[3] / st, q[4] / st, q[6] / tl, q[7] / tl, q[8] / tl, q[9] / n, q[10] / tl, q[11] / tl,
+              q[12] / tl, q[13] / tl, q[14] / tl, q[15] / tl);
+    }
+    cudaFree(c->t2_counters);
+  }
   if (c->ms_counters) {
     unsigned long long h[32] = {};
     cudaMemcpy(h, c->ms_counters, 256, cudaMemcpyDeviceToHost);

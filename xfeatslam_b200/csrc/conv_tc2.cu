@@ -95,7 +95,14 @@ struct ConvTc2Args {
   int full_w;               // T2IN_UNFOLD / KPSOFTMAX: width of xn / K1h
   int tiles_x, tiles;       // tiles per frame
   float out_scale;          // 1 / (activation scale * weight scale), an exact power of two
+  unsigned long long* dbg;  // XFB_T2_DEBUG: cycle counters of CTA 0 (32 per layer), else nullptr
 };
+
+// debug: add the cycles since `t0` to counter `slot` (one designated thread per role) and restart the clock
+#define T2_TICK(slot)                                                                  \
+  do {                                                                                 \
+    if (dbg_me) { const long long _n = clock64(); atomicAdd(a.dbg + (slot), (unsigned long long)(_n - t0)); t0 = _n; } \
+  } while (0)
 
 struct f8 { float4 a, b; };
 __device__ __forceinline__ f8 ldg256(const float* p) {
@@ -178,6 +185,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
   uint32_t* s_flag = s_tmem + 1;
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const long long t_kernel0 = clock64();
   // work items: (tile of a frame, output group).  A CTA keeps ONE output group (its weights stay resident) and walks the
   // tiles of all frames with stride gridDim.x / NSPLIT.
   const int split = blockIdx.x % C::NSPLIT;
@@ -202,6 +210,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
     const int kc = pt % KCS;                         // this thread's 8-channel chunk inside a phase (constant)
     constexpr int ITEMS = NSUB * NPIX * KCS;
     int it = 0;
+    const bool dbg_me = a.dbg != nullptr && blockIdx.x == 0 && pt == 0;
+    long long t0 = dbg_me ? clock64() : 0;
     for (int tile = first; tile < n_tiles; tile += stride) {
       const int b = tile / a.tiles, tf = tile - b * a.tiles;
       const int oy0 = (C::KS == 1) ? 0 : (tf / a.tiles_x) * C::TH, ox0 = (C::KS == 1) ? 0 : (tf % a.tiles_x) * C::TW;
@@ -222,7 +232,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
             sb[0] = bb.a.x; sb[1] = bb.a.y; sb[2] = bb.a.z; sb[3] = bb.a.w; sb[4] = bb.b.x; sb[5] = bb.b.y; sb[6] = bb.b.z; sb[7] = bb.b.w;
           }
         }
+        T2_TICK(3);
         if (it >= NBUF) mbar_wait(bar_free + buf, ((it / NBUF) - 1) & 1);      // the MMAs that read this buffer are done
+        T2_TICK(2);
         for (int base = 0; base < ITEMS; base += T2_PROD * T2_UNR) {
           f8 v[T2_UNR];
           float av[T2_UNR];
@@ -275,8 +287,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
             *reinterpret_cast<uint4*>(dst_hi + C::IN_BYTES + off[u]) = lo;
           }
         }
+        T2_TICK(3);
         fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async-proxy reads
         mbar_arrive(bar_in + buf);
+        T2_TICK(4);
+        if (dbg_me) atomicAdd(a.dbg + 5, 1ull);
       }
     }
   } else if (warp == 4) {
@@ -299,15 +314,22 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
     constexpr uint64_t A_LO = (uint64_t)C::IN_BYTES >> 4, A_BUF = (uint64_t)C::BUF_BYTES >> 4;
     constexpr uint64_t W_UNIT = (uint64_t)C::W_UNIT_BYTES >> 4;
     int it = 0, n = 0;
+    const bool dbg_me = a.dbg != nullptr && blockIdx.x == 0 && leader;
+    long long t0 = dbg_me ? clock64() : 0;
     for (int tile = first; tile < n_tiles; tile += stride, ++n) {
       const int acc = n & 1;
+      T2_TICK(8);
       if (n >= 2) mbar_wait(bar_acce + acc, ((n >> 1) - 1) & 1);                 // the epilogue has drained this accumulator
+      T2_TICK(7);
       tc_fence_after();
       const uint32_t d = tmem_base + (uint32_t)acc * C::ACC_STRIDE;
       for (int ph = 0; ph < NPHASE; ++ph, ++it) {
         const int buf = it % NBUF;
+        T2_TICK(8);
         if (n == 0) mbar_wait(bar_w + ph, 0);
+        T2_TICK(9);
         mbar_wait(bar_in + buf, (it / NBUF) & 1);
+        T2_TICK(6);
         tc_fence_after();
         if (leader) {
           const uint64_t dah = da0 + (uint64_t)buf * A_BUF, dal = dah + A_LO;
@@ -342,16 +364,21 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
     const int p = quad * 32 + lane;                     // pixel of the tile = TMEM lane
     const int cbase = split * C::NOUT;                  // first output channel of this CTA's group
     int n = 0;
+    const bool dbg_me = a.dbg != nullptr && blockIdx.x == 0 && t == 0;
+    long long t0 = dbg_me ? clock64() : 0;
     for (int tile = first; tile < n_tiles; tile += stride, ++n) {
       const int acc = n & 1;
       const int b = tile / a.tiles, tf = tile - b * a.tiles;
+      if (dbg_me) atomicAdd(a.dbg + 16, 1ull);
       int oy, ox;
       if (C::KS == 1) { const int lin = tf * 128 + p; oy = lin / a.Wout; ox = lin - oy * a.Wout; }
       else { oy = (tf / a.tiles_x) * C::TH + (p >> 3); ox = (tf % a.tiles_x) * C::TW + (p & 7); }
       const bool valid = oy < a.Hout && ox < a.Wout;
       const uint32_t tq = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * C::ACC_STRIDE;
+      T2_TICK(15);
       mbar_wait(bar_accf + acc, (n >> 1) & 1);
       tc_fence_after();
+      T2_TICK(10);
       if constexpr (OUTMODE == T2OUT_KPSOFTMAX) {
         // keypoint_head.3 epilogue: + bias, softmax over the 65 logits, drop the dustbin, 8x8 fold
         // (src/XFeat.cc:85-90, XFextractor::getKptsHeatmap src/XFextractor.cc:204-217); one thread per cell
@@ -400,6 +427,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
                 stg256(orow + ci * 32 + q, v[ci][q], v[ci][q + 1], v[ci][q + 2], v[ci][q + 3], v[ci][q + 4], v[ci][q + 5], v[ci][q + 6], v[ci][q + 7]);
           }
         }
+        T2_TICK(11);
         if constexpr (OUTMODE == T2OUT_STATS) {
           // per-channel sum / sum of squares over the valid pixels of this warp's quadrant: lane j <- channel ci * 32 + j
 #pragma unroll
@@ -412,6 +440,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
             *reinterpret_cast<float2*>(sQ + ((quad * 64) + ci * 32 + lane) * 2) = make_float2(s1, s2);
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");
+          T2_TICK(12);
           // tile partial = the four quadrants in fixed order -> part[b][tile][channel]
           float* part_b = a.part + (size_t)b * a.tiles * C::COUT * 2;
           if (t < C::NOUT) {
@@ -422,11 +451,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
           }
           __threadfence();
           asm volatile("bar.sync 1, 128;" ::: "memory");
+          T2_TICK(13);
           if (t == 0) {
             const unsigned int prev = atomicAdd(a.ticket + b * XFB_TICKET_STRIDE, 1u);
             *s_flag = (prev == (unsigned int)(a.tiles * C::NSPLIT - 1)) ? 1u : 0u;
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");
+          T2_TICK(14);
           if (*s_flag) {
             __threadfence();
             // last work item of the frame: fixed-order fold of all tile partials (slice-strided, then slice order), in double
@@ -434,7 +465,15 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
             if (t < NSL * C::COUT) {
               const int c = t % C::COUT, sl = t / C::COUT;
               double d1 = 0.0, d2 = 0.0;
-              for (int i = sl; i < a.tiles; i += NSL) {
+              int i = sl;
+              for (; i + 7 * NSL < a.tiles; i += 8 * NSL) {        // 8 independent loads in flight, summed in index order
+                float2 x[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) x[q] = __ldcg(reinterpret_cast<const float2*>(part_b + ((size_t)(i + q * NSL) * C::COUT + c) * 2));
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { d1 += (double)x[q].x; d2 += (double)x[q].y; }
+              }
+              for (; i < a.tiles; i += NSL) {
                 const float2 x = __ldcg(reinterpret_cast<const float2*>(part_b + ((size_t)i * C::COUT + c) * 2));
                 d1 += (double)x.x; d2 += (double)x.y;
               }
@@ -460,6 +499,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
   }
   tc_fence_before();
   __syncthreads();
+  if (a.dbg != nullptr && blockIdx.x == 0 && t == 0) { atomicAdd(a.dbg + 0, 1ull); atomicAdd(a.dbg + 1, (unsigned long long)(clock64() - t_kernel0)); }
   if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -569,6 +609,7 @@ cudaError_t launch_conv_tc2_layer(Ctx* c, int L) {
   a.out = c->act[L];
   a.part = reinterpret_cast<float*>(c->part); a.ticket = c->ticket;
   a.full_w = c->W;
+  a.dbg = c->t2_counters ? c->t2_counters + (size_t)L * 32 : nullptr;
   if (L < L_NUM_BN) { a.out_mean = c->bn[L].mean; a.out_rstd = c->bn[L].rstd; }
   auto from = [&](int P) { a.in = c->act[P]; a.in_mean = c->bn[P].mean; a.in_rstd = c->bn[P].rstd; };
   switch (L) {

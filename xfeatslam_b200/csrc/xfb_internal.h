@@ -81,6 +81,7 @@ struct Ctx {
   float wscale2[L_NUM] = {};      // its epilogue factor 1 / (activation scale * weight scale)
   int conv_tc_version = 2;        // 2 = conv_tc2.cu (default), 1 = conv_tc.cu (XFB_CONV_TC=1: A/B reference)
   int num_sms = 148;
+  unsigned long long* t2_counters = nullptr;   // XFB_T2_DEBUG: [L_NUM][32] cycle counters of CTA 0 (conv_tc2.cu), printed at xfb_destroy
   bool force_simt = false;        // debug: run every conv on the FP32 SIMT kernels (A/B parity tests)
 
   // geometry of the last extract call
