@@ -197,6 +197,11 @@ static int tc_ensure_generic(Ctx* c, int n1, int n2) {
     for (int i = 0; i < 2; ++i) { XFB_ALLOC(c, c->tc_img[i], (size_t)need * 64 * 4); XFB_ALLOC(c, c->tc_nrm[i], (size_t)need * 4); }
     c->tc_cap = need;
   }
+  if (c->mm_cap < need) {
+    for (int i = 0; i < 2; ++i) { if (c->mm_img[i]) cudaFree(c->mm_img[i]); c->mm_img[i] = nullptr; }
+    for (int i = 0; i < 2; ++i) XFB_ALLOC(c, c->mm_img[i], mm_image_bytes(need));
+    c->mm_cap = need;
+  }
   for (int i = 0; i < 2; ++i) if (!c->tc_nmax[i]) XFB_ALLOC(c, c->tc_nmax[i], 16);
   if (!c->tc_dbg) XFB_ALLOC(c, c->tc_dbg, 16);
   if (c->ms_cap < need) {
@@ -207,18 +212,51 @@ static int tc_ensure_generic(Ctx* c, int n1, int n2) {
   return XFB_OK;
 }
 
+// per-pair column scratch of the mutual matcher: 64 pairs x `rows` columns, in its between-launches state
+static int mm_ensure_cols(Ctx* c, int rows) {
+  if (rows <= c->mm_col_rows) return XFB_OK;
+  auto fr = [](void* p) { if (p) cudaFree(p); };
+  fr(c->mm_colg); fr(c->mm_colk); fr(c->mm_done);
+  c->mm_colg = nullptr; c->mm_colk = nullptr; c->mm_done = nullptr; c->mm_col_rows = 0;
+  XFB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  XFB_ALLOC(c, c->mm_colg, (size_t)64 * rows * 4);
+  XFB_ALLOC(c, c->mm_colk, (size_t)64 * rows * 8);
+  XFB_ALLOC(c, c->mm_done, 64 * 4);
+  XFB_CUDA_OK(c, cudaMemset(c->mm_colg, 0, (size_t)64 * rows * 4));
+  XFB_CUDA_OK(c, cudaMemset(c->mm_colk, 0xff, (size_t)64 * rows * 8));
+  XFB_CUDA_OK(c, cudaMemset(c->mm_done, 0, 64 * 4));
+  c->mm_col_rows = rows;
+  return XFB_OK;
+}
+
 // A [n1,64], B [n2,64] device fp32; outputs device int32 (nullable)
 static int tc_match_generic(Ctx* c, const float* dA, int n1, const float* dB, int n2, const int32_t* ga, const int32_t* gb, int init,
                             int32_t* bi, int32_t* bd, int32_t* sd, int32_t* ri, int32_t* rd) {
   int r = tc_ensure_generic(c, n1, n2);
   if (r != XFB_OK) return r;
   const int p1 = pad128(n1), p2 = pad128(n2);
+  const bool grouped = ga && gb;
+  if (!grouped) {
+    // one streamed GEMM: row-wise best / second-best and column-wise best together (match_mutual.cu)
+    if ((r = mm_ensure_cols(c, p2)) != XFB_OK) return r;
+    XFB_CUDA_OK(c, launch_mm_prep(c, dA, 0, 1, nullptr, n1, p1, c->mm_img[0], 0, c->tc_nrm[0], c->tc_nmax[0]));
+    XFB_CUDA_OK(c, launch_mm_prep(c, dB, 0, 1, nullptr, n2, p2, c->mm_img[1], 0, c->tc_nrm[1], c->tc_nmax[1]));
+    MatchTcArgs m = {};
+    m.init = init;
+    m.imgA = (const float*)c->mm_img[0]; m.imgB = (const float*)c->mm_img[1]; m.nrmA = c->tc_nrm[0]; m.nrmB = c->tc_nrm[1]; m.rawA = dA; m.rawB = dB;
+    m.nA_host = n1; m.nB_host = n2; m.rows_padded_A = p1; m.rows_padded_B = p2;
+    m.out_stride = n1; m.out_stride_cols = n2;         // one pair: outputs are plain arrays of n1 (rows) / n2 (columns) entries
+    m.best_idx = bi; m.best_dist = bd; m.second_dist = sd; m.rev_idx = ri; m.rev_dist = rd;
+    m.nrm_max_A = c->tc_nmax[0]; m.nrm_max_B = c->tc_nmax[1];
+    m.col_g = c->mm_colg; m.col_k = c->mm_colk; m.pair_done = c->mm_done;
+    XFB_CUDA_OK(c, launch_match_mutual(c, m, 1, ri || rd));
+    return XFB_OK;
+  }
   XFB_CUDA_OK(c, launch_ms_prep(c, dA, 0, 1, nullptr, n1, p1, c->ms_img[0], 0, c->tc_nrm[0], c->tc_nmax[0]));
   XFB_CUDA_OK(c, launch_ms_prep(c, dB, 0, 1, nullptr, n2, p2, c->ms_img[1], 0, c->tc_nrm[1], c->tc_nmax[1]));
   MatchTcArgs a = {};
   a.init = init;
   a.ms_counters = c->ms_counters; a.ms_mode = c->ms_mode;
-  const bool grouped = ga && gb;
   if (n1 > 0 && (bi || bd || sd)) {
     a.imgA = (const float*)c->ms_img[0]; a.imgB = (const float*)c->ms_img[1]; a.nrmA = c->tc_nrm[0]; a.nrmB = c->tc_nrm[1]; a.rawA = dA; a.rawB = dB;
     a.gA = ga; a.gB = gb; a.nA_host = n1; a.nB_host = n2; a.rows_padded_A = p1; a.rows_padded_B = p2; a.out_stride = n1;
@@ -254,43 +292,39 @@ static int tc_match_frames(Ctx* c, const int32_t* pairs, int n_pairs, int init, 
   const int K = c->last_topk, P = pad128(K);
   // xfb_submit runs its matcher on s_match: any other stream must not touch the shared per-frame images before that is done
   if (c->ev_match_free && c->stream != c->s_match) XFB_CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_match_free, 0));
-  if (!c->ms_fimg || c->ms_frows < P) {
-    if (c->ms_fimg) cudaFree(c->ms_fimg);
+  if (!c->mm_fimg || c->mm_frows < P) {
+    if (c->mm_fimg) cudaFree(c->mm_fimg);
     if (c->tc_fnrm) cudaFree(c->tc_fnrm);
     if (c->tc_fnmax) cudaFree(c->tc_fnmax);
-    c->ms_fimg = nullptr; c->tc_fnrm = nullptr; c->tc_fnmax = nullptr;
+    c->mm_fimg = nullptr; c->tc_fnrm = nullptr; c->tc_fnmax = nullptr;
     const int PM = pad128(c->max_topk);
-    XFB_ALLOC(c, c->ms_fimg, (size_t)c->max_batch * ms_image_bytes(PM));
+    XFB_ALLOC(c, c->mm_fimg, (size_t)c->max_batch * mm_image_bytes(PM));
     XFB_ALLOC(c, c->tc_fnrm, (size_t)c->max_batch * PM * 4);
     XFB_ALLOC(c, c->tc_fnmax, (size_t)c->max_batch * 4);
-    c->ms_frows = PM;
+    c->mm_frows = PM;
     c->tc_fvalid = false;
   }
-  const size_t img_bytes = ms_image_bytes(P);
+  int r = mm_ensure_cols(c, pad128(c->max_topk));
+  if (r != XFB_OK) return r;
+  const size_t img_bytes = mm_image_bytes(P);
   if (!c->tc_fvalid) {   // operand images of every frame of the batch, once per extract
-    XFB_CUDA_OK(c, launch_ms_prep(c, c->last_desc, (size_t)K * 64, c->B, c->last_nvalid, K, P, c->ms_fimg, img_bytes, c->tc_fnrm, c->tc_fnmax));
+    XFB_CUDA_OK(c, launch_mm_prep(c, c->last_desc, (size_t)K * 64, c->B, c->last_nvalid, K, P, c->mm_fimg, img_bytes, c->tc_fnrm, c->tc_fnmax));
     c->tc_fvalid = true;
   }
   for (int p0 = 0; p0 < n_pairs; p0 += 64) {
     const int np = (n_pairs - p0) < 64 ? (n_pairs - p0) : 64;
     MatchTcArgs a = {};
-    a.imgA = a.imgB = (const float*)c->ms_fimg; a.nrmA = a.nrmB = c->tc_fnrm; a.rawA = a.rawB = c->last_desc;
+    a.imgA = a.imgB = (const float*)c->mm_fimg; a.nrmA = a.nrmB = c->tc_fnrm; a.rawA = a.rawB = c->last_desc;
     a.nA_dev = a.nB_dev = c->last_nvalid; a.nA_host = a.nB_host = K; a.rows_padded_A = a.rows_padded_B = P;
     a.img_stride_A = a.img_stride_B = img_bytes; a.raw_stride_A = a.raw_stride_B = (size_t)K * 64;
-    a.init = init; a.out_stride = K;
-    a.nrm_max_B = c->tc_fnmax;
-    a.ms_counters = c->ms_counters; a.ms_mode = c->ms_mode;
-    if (o[0] || o[1] || o[2]) {
-      for (int p = 0; p < np; ++p) { a.pairs[2 * p] = pairs[2 * (p0 + p)]; a.pairs[2 * p + 1] = pairs[2 * (p0 + p) + 1]; }
-      a.best_idx = o[0] ? o[0] + (size_t)p0 * K : nullptr; a.best_dist = o[1] ? o[1] + (size_t)p0 * K : nullptr;
-      a.second_dist = o[2] ? o[2] + (size_t)p0 * K : nullptr;
-      XFB_CUDA_OK(c, launch_match_stream(c, a, np, false));
-    }
-    if (o[3] || o[4]) {   // column-wise best = row-wise best of the transposed problem
-      for (int p = 0; p < np; ++p) { a.pairs[2 * p] = pairs[2 * (p0 + p) + 1]; a.pairs[2 * p + 1] = pairs[2 * (p0 + p)]; }
-      a.best_idx = o[3] ? o[3] + (size_t)p0 * K : nullptr; a.best_dist = o[4] ? o[4] + (size_t)p0 * K : nullptr; a.second_dist = nullptr;
-      XFB_CUDA_OK(c, launch_match_stream(c, a, np, false));
-    }
+    a.init = init; a.out_stride = K; a.out_stride_cols = K;
+    a.nrm_max_A = a.nrm_max_B = c->tc_fnmax;
+    a.col_g = c->mm_colg; a.col_k = c->mm_colk; a.pair_done = c->mm_done;
+    for (int p = 0; p < np; ++p) { a.pairs[2 * p] = pairs[2 * (p0 + p)]; a.pairs[2 * p + 1] = pairs[2 * (p0 + p) + 1]; }
+    auto at = [&](int i) { return o[i] ? o[i] + (size_t)p0 * K : nullptr; };
+    a.best_idx = at(0); a.best_dist = at(1); a.second_dist = at(2); a.rev_idx = at(3); a.rev_dist = at(4);
+    // ONE launch per 64 pairs: row-wise best / second-best and column-wise best from one streamed GEMM per pair (match_mutual.cu)
+    XFB_CUDA_OK(c, launch_match_mutual(c, a, np, o[3] || o[4]));
   }
   return XFB_OK;
 }
@@ -439,7 +473,7 @@ void xfb_destroy(xfb_ctx* c) {
             h[12] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n, h[7] / n, h[8] / n, h[9] / n, h[10] / n, h[11] / n);
     fprintf(stderr, "[xfb] CTA(0,0) mma thread: cycles in tcgen05.mma issue %.0f, in tcgen05.commit %.0f, in tcgen05.fence %.0f, loop tail %.0f\n", h[14] / n, h[15] / n, h[16] / n, h[17] / n);
   }
-  fr(c->ms_img[0]); fr(c->ms_img[1]); fr(c->ms_fimg); fr(c->ms_counters); fr(c->p_idx); fr(c->p_out); fr(c->g_buf); fr(c->v_desc); fr(c->v_start); fr(c->v_child); fr(c->v_out);
+  fr(c->ms_img[0]); fr(c->ms_img[1]); fr(c->ms_fimg); fr(c->mm_img[0]); fr(c->mm_img[1]); fr(c->mm_fimg); fr(c->mm_colg); fr(c->mm_colk); fr(c->mm_done); fr(c->ms_counters); fr(c->p_idx); fr(c->p_out); fr(c->g_buf); fr(c->v_desc); fr(c->v_start); fr(c->v_child); fr(c->v_out);
   fr(c->tc_fnrm); fr(c->tc_pairs); fr(c->tc_dbg); fr(c->tc_fnmax); fr(c->tc_nmax[0]); fr(c->tc_nmax[1]);
   for (auto& s : c->slots) {
     fr(s.d_gray); fr(s.nvalid); fr(s.xy); fr(s.score); fr(s.desc);

@@ -5,22 +5,29 @@
 // written NHWC fp32, and per-(frame, channel) sum / sum-of-squares go through a fixed-order fold, so a batch of B frames
 // equals B batch-1 calls bit for bit.
 //
-// What is new (round 2):
+// Design (round 2):
 //   * fp16 two-piece split instead of 3xTF32.  x*16 = hi + lo (hi = fp16 RN, lo = fp16 RN of the exact remainder), weights
-//     likewise after an exact power-of-two scale per layer; D += hi*hi + hi*lo + lo*hi with kind::f16 (K = 16 per UTCHMMA).
-//     Same ~2^-22 relative operand precision as the TF32 split, at HALF the tensor-pipe time (3 fp16 MMA passes instead
-//     of 3 TF32 passes at half rate) and HALF the shared-memory bytes (2 + 2 instead of 4 + 4 bytes per element).
-//   * Persistent CTAs (one per SM) looping over 128-pixel output tiles; the layer's weights are loaded into shared memory
-//     ONCE per CTA and stay resident (layers whose weight image exceeds shared memory split their output channels over
-//     CTAs: COUT_SPLIT); three pipeline stages run concurrently on different tiles:
-//        7 producer warps   stage tile i+1 (LDG.256 -> BN/ReLU -> hi/lo split -> STS.128) into a ring of NBUF buffers,
-//        1 MMA warp         multiplies tile i   (one elected lane; accumulator = TMEM stage i & 1),
-//        4 epilogue warps   drain tile i-1      (tcgen05.ld -> scale -> STG.256 + per-channel statistics).
+//     likewise after an exact power-of-two scale per layer; D = hi*hi + hi*lo + lo*hi with kind::f16 (K = 16 per UTCHMMA).
+//     Same ~2^-22 relative operand precision as the TF32 split at half the tensor-pipe time and half the shared-memory
+//     bytes.  The hi and lo weight rows are CONCATENATED along N: one MMA computes A_hi x [W_hi ; W_lo] (N = 2*NP, the
+//     A operand is fetched from shared memory once for two products), a second one adds A_lo x W_hi into the first NP
+//     accumulator columns; the epilogue sums the two column groups.
+//   * Persistent CTAs (one per SM), each walking a CONTIGUOUS range of 128-pixel output tiles; the layer's weights are
+//     loaded into shared memory ONCE per CTA and stay resident (layers whose weight image exceeds shared memory split their
+//     output channels over CTAs: NSPLIT).  Three pipeline stages run concurrently on different tiles:
+//        7 producer warps   stage tile i+1: LDG.256 (issued one unit AHEAD, software-pipelined in registers) -> BN / ReLU ->
+//                           hi / lo split -> STS.128 into a ring of NBUF (tile, channel phase) buffers,
+//        1 MMA warp         multiplies tile i (one elected lane; accumulator = TMEM stage i & 1),
+//        4 epilogue warps   drain tile i-1: tcgen05.ld -> scale -> 128B-swizzled staging tile in shared memory ->
+//                           ONE TMA tensor store per 32-channel half (cp.async.bulk.tensor, clipped at the image border by
+//                           the hardware) + per-channel statistics read back column-wise from the staging tile.
 //   * No im2col, as before: the halo tile is staged as channel-chunk planes [cin/8][pixel][8 halfs], which IS the canonical
 //     K-major no-swizzle UMMA layout, so filter tap (ky, kx) is the same buffer with the descriptor start address advanced
 //     by (ky * tile_width + kx) * 16 B; stride-2 layers stage four parity planes.  1x1 layers tile the frame linearly.
-//   * Statistics without a shared-memory staging tile: each epilogue lane owns one pixel (TMEM lane) and 32 channels; a
-//     31-shuffle transpose-reduce leaves the sum of channel j in lane j.
+//   * Train-mode BatchNorm statistics: per-tile partial sums -> global scratch with plain stores; a CTA publishes them ONCE per
+//     frame it touched (its tile range is contiguous: one or two frames) with a barrier + one fence + one ticket atomic; the
+//     CTA that completes a frame folds the frame's partials in fixed order (double).
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -37,21 +44,21 @@ enum Tc2InMode { T2IN_PLAIN = 0, T2IN_BN = 1, T2IN_BN_SKIP = 2, T2IN_UNFOLD = 3 
 enum Tc2OutMode { T2OUT_STATS = 0, T2OUT_BIAS = 1, T2OUT_KPSOFTMAX = 2 };
 
 constexpr float T2_ACT_SCALE = 16.0f;        // activations are staged as x * 16 (exact), |x| < 4094 fits fp16
-constexpr int T2_PROD_WARPS = 7;           // 12 warps in all: the register file is allocated per 4 warps, so 13 warps would cap a thread at 128 registers
+constexpr int T2_PROD_WARPS = 7;             // 12 warps in all: the register file is allocated per 4 warps, 13 warps would cap a thread at 128 registers
 constexpr int T2_PROD = 32 * T2_PROD_WARPS;  // producer threads
 constexpr int T2_EPI = 128;                  // epilogue threads (warps 0-3: TMEM lane quadrant = warp id)
 constexpr int T2_THREADS = T2_EPI + 32 + T2_PROD;   // warps 0-3 epilogue, warp 4 MMA issuer, warps 5-11 producers
-constexpr int T2_UNR = 4;                    // independent 32-byte global loads in flight per producer thread
 
 // CIN: real input channels; CINP: padded to a multiple of 16 (zero chunks); COUT: real outputs; NSPLIT: output-channel
-// groups processed by different CTAs; CSTAGE: input channels per staged buffer (channel phase); NBUF: ring depth.
-template <int CIN_, int COUT_, int KS_, int S_, int CSTAGE_, int NBUF_, int NSPLIT_>
+// groups processed by different CTAs; CSTAGE: input channels per staged buffer (channel phase); NBUF: ring depth;
+// UNR: 32-byte global loads in flight per producer thread and unit.
+template <int CIN_, int COUT_, int KS_, int S_, int CSTAGE_, int NBUF_, int NSPLIT_, int UNR_>
 struct T2Cfg {
-  static constexpr int CIN = CIN_, COUT = COUT_, KS = KS_, S = S_, CSTAGE = CSTAGE_, NBUF = NBUF_, NSPLIT = NSPLIT_;
+  static constexpr int CIN = CIN_, COUT = COUT_, KS = KS_, S = S_, CSTAGE = CSTAGE_, NBUF = NBUF_, NSPLIT = NSPLIT_, UNR = UNR_;
   static constexpr int CINP = (CIN + 15) / 16 * 16;
   static constexpr int NOUT = COUT / NSPLIT;                                      // real output channels per CTA
-  static constexpr int NP = NOUT <= 32 ? 32 : (NOUT + 15) / 16 * 16;              // UMMA N (M = 128 needs N % 16 == 0)
-  static constexpr int ACC_STRIDE = NP <= 32 ? 32 : (NP <= 64 ? 64 : 128);        // TMEM columns per accumulator stage
+  static constexpr int NP = NOUT <= 32 ? 32 : (NOUT + 15) / 16 * 16;              // padded outputs; UMMA N = 2 * NP (hi rows | lo rows) and NP
+  static constexpr int ACC_STRIDE = 2 * NP <= 64 ? 64 : (2 * NP <= 128 ? 128 : 256);   // TMEM columns per accumulator stage
   static constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int TW = 8, TH = 16, PAD = KS / 2;
   static constexpr int NSUB = S == 2 ? 4 : 1;                                     // parity planes
@@ -68,28 +75,36 @@ struct T2Cfg {
   static constexpr int BUF_BYTES = 2 * IN_BYTES;
   static constexpr int TAPS = KS * KS;
   static constexpr int NPHASE = CINP / CSTAGE;
-  static constexpr int W_UNIT_BYTES = CSTAGE * NP * 2;                            // one of hi / lo of one (phase, tap)
-  static constexpr int W_BYTES = NPHASE * TAPS * 2 * W_UNIT_BYTES;                // resident weight image of one output group
+  static constexpr int W_UNIT_BYTES = CSTAGE * 2 * NP * 2;                        // [hi rows | lo rows] of one (phase, tap)
+  static constexpr int W_BYTES = NPHASE * TAPS * W_UNIT_BYTES;                    // resident weight image of one output group
   static constexpr uint32_t LBO_A = PS, SBO_A = WT * 16;
-  static constexpr uint32_t LBO_B = (NP / 8) * 128, SBO_B = 128;
-  static constexpr int STAT_BYTES = 4 * 64 * 2 * 4 + 128 * 2 * 8;                 // quadrant sums [4][64][2] (float) + fold scratch [128][2] (double)
-  static constexpr size_t SMEM_BYTES = (size_t)W_BYTES + (size_t)NBUF * BUF_BYTES + STAT_BYTES + 256;
-  static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NP >> 3) << 17) | ((128u >> 4) << 24);   // kind::f16, F16 x F16 -> F32, K-major
+  static constexpr uint32_t LBO_B = (2 * NP / 8) * 128, SBO_B = 128;
+  static constexpr int ITEMS = NSUB * NPIX * KCS;                                 // (pixel, 8-channel chunk) items per staged buffer
+  static constexpr int ROUNDS = (ITEMS + T2_PROD * UNR - 1) / (T2_PROD * UNR);    // units per staged buffer
+  static constexpr bool HAS_STG = COUT != 65;                                     // keypoint_head.3 writes its own folded output
+  static constexpr int NHALF = HAS_STG ? (NOUT + 31) / 32 : 0;                    // 32-channel TMA boxes per tile
+  static constexpr int STG_BYTES = NHALF * 16384;                                 // staging tile(s): [128 px][32 ch] fp32, 128B-swizzled
+  static constexpr int FOLD_BYTES = 128 * 2 * 8;
+  static constexpr size_t SMEM_BYTES = (size_t)STG_BYTES + W_BYTES + (size_t)NBUF * BUF_BYTES + FOLD_BYTES + 256;
+  // kind::f16, F16 x F16 -> F32, both K-major, M = 128
+  static constexpr uint32_t IDESC_2N = (1u << 4) | ((uint32_t)(2 * NP >> 3) << 17) | ((128u >> 4) << 24);
+  static constexpr uint32_t IDESC_1N = (1u << 4) | ((uint32_t)(NP >> 3) << 17) | ((128u >> 4) << 24);
   static_assert(CSTAGE % 16 == 0 && CINP % CSTAGE == 0 && COUT % NSPLIT == 0 && (NOUT % 8 == 0 || NOUT == 65) && NOUT <= 80, "shape");
+  static_assert(2 * NP <= 256 && (2 * NP) % 16 == 0, "UMMA N");
   static_assert(S == 1 || KS == 3, "stride 2 is implemented for 3x3 only");
   static_assert(T2_PROD % KCS == 0, "a producer thread keeps one channel chunk");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-  static_assert(PS % 16 == 0 && W_UNIT_BYTES % 16 == 0, "descriptor alignment");
+  static_assert(PS % 16 == 0 && W_UNIT_BYTES % 16 == 0 && W_BYTES % 1024 == 0, "descriptor alignment");
 };
 
 struct ConvTc2Args {
   const float* in;          // NHWC raw producer output (or plain values), or xn for T2IN_UNFOLD
-  const unsigned char* wimg;   // [split][phase][tap][hi | lo][cstage/8][np/8][8][8 halfs]
+  const unsigned char* wimg;   // [split][phase][tap][cstage/8][2*np/8][8][8 halfs]  (rows 0..np-1 = hi, np..2np-1 = lo)
   const float* bias;
-  float* out;
+  float* out;               // keypoint_head.3 only (every other layer stores through the tensor map)
   const float* in_mean; const float* in_rstd;
   const float* skip_avg; const float* skip_w; const float* skip_b;
-  float* part;              // per-tile channel sums [B][tiles][COUT][2] (float)
+  float* part;              // per-tile channel sums [B][tiles][2 pixel halves][COUT][2] (float)
   unsigned int* ticket; float* out_mean; float* out_rstd;
   int B, Hin, Win, Hout, Wout;
   int full_w;               // T2IN_UNFOLD / KPSOFTMAX: width of xn / K1h
@@ -152,29 +167,40 @@ __device__ __forceinline__ void tmem_ld32_nw(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_fence() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// Sum over the 32 lanes of v[j] for every j: afterwards lane j holds the total of column j.  31 shuffles.
-__device__ __forceinline__ float transpose_reduce32(float* v, int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float keep = up ? v[i + off] : v[i];
-      const float send = up ? v[i] : v[i + off];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0];
+// TMA tensor stores (shared -> global through a CUtensorMap; out-of-range parts of the box are clipped by the hardware)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1),
+               "r"(c2), "r"(smem)
+               : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3), "r"(smem)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// One unit of producer work held in registers: UNR (pixel, 8-channel chunk) items of one staged buffer.
+template <int UNR>
+struct ProdRegs {
+  f8 v[UNR];
+  float av[UNR];
+  int off[UNR];           // byte offset inside the hi plane set, -1 = no item
+  unsigned inside;        // bit u: the item lies inside the image (else zeros are staged)
+};
+struct ProdPos { int tile, ph, rnd, it; };   // it = staged-buffer counter of this CTA
 
 template <class C, int INMODE, int OUTMODE>
-__global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Args a) {
-  constexpr int KCS = C::KCS, PS = C::PS, WT = C::WT, NPIX = C::NPIX, TAPS = C::TAPS, NBUF = C::NBUF, NPHASE = C::NPHASE, NSUB = C::NSUB;
+__global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Args a, const __grid_constant__ CUtensorMap tmap) {
+  constexpr int KCS = C::KCS, PS = C::PS, WT = C::WT, NPIX = C::NPIX, TAPS = C::TAPS, NBUF = C::NBUF, NPHASE = C::NPHASE, UNR = C::UNR,
+                ROUNDS = C::ROUNDS, ITEMS = C::ITEMS;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* sW = smem_raw;                                   // resident weights of this CTA's output group
-  unsigned char* sA = smem_raw + C::W_BYTES;                      // NBUF x [hi | lo] staged tiles
-  float* sQ = reinterpret_cast<float*>(sA + (size_t)NBUF * C::BUF_BYTES);     // [4][64][2] quadrant sums
-  double* sFold = reinterpret_cast<double*>(sQ + 4 * 64 * 2);                  // [128][2]
+  unsigned char* sStg = smem_raw;                                 // staging tile(s) for the TMA store (1024-byte aligned: 128B swizzle)
+  unsigned char* sW = smem_raw + C::STG_BYTES;                    // resident weights of this CTA's output group
+  unsigned char* sA = sW + C::W_BYTES;                            // NBUF x [hi | lo] staged tiles
+  double* sFold = reinterpret_cast<double*>(sA + (size_t)NBUF * C::BUF_BYTES);   // [128][2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sFold + 128 * 2);
   uint64_t* bar_in = bars + 0;          // [NBUF] tile staged (T2_PROD arrivals)
   uint64_t* bar_free = bars + 4;        // [NBUF] tensor core finished reading the staged buffer
@@ -186,11 +212,12 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const long long t_kernel0 = clock64();
-  // work items: (tile of a frame, output group).  A CTA keeps ONE output group (its weights stay resident) and walks the
-  // tiles of all frames with stride gridDim.x / NSPLIT.
+  // work items: (tile of a frame, output group).  A CTA keeps ONE output group (its weights stay resident) and walks a
+  // contiguous range of the tiles of all frames (neighbouring tiles share halo rows in L2 and BatchNorm parameters in L1).
   const int split = blockIdx.x % C::NSPLIT;
-  const int first = blockIdx.x / C::NSPLIT, stride = gridDim.x / C::NSPLIT;
+  const int gidx = blockIdx.x / C::NSPLIT, gcnt = gridDim.x / C::NSPLIT;
   const int n_tiles = a.B * a.tiles;
+  const int tile_begin = (int)(((long long)gidx * n_tiles) / gcnt), tile_end = (int)(((long long)(gidx + 1) * n_tiles) / gcnt);
 
   if (t == 0) {
     for (int s = 0; s < NBUF; ++s) { mbar_init(bar_in + s, T2_PROD); mbar_init(bar_free + s, 1); }
@@ -205,104 +232,169 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
   const uint32_t tmem_base = *s_tmem;
 
   if (warp >= 5) {
-    // ===================== producers: stage (tile, channel phase) buffers =====================
+    // ===================== producers: stage (tile, channel phase) buffers, global loads one unit ahead =====================
     const int pt = t - (T2_EPI + 32);
     const int kc = pt % KCS;                         // this thread's 8-channel chunk inside a phase (constant)
-    constexpr int ITEMS = NSUB * NPIX * KCS;
-    int it = 0;
     const bool dbg_me = a.dbg != nullptr && blockIdx.x == 0 && pt == 0;
     long long t0 = dbg_me ? clock64() : 0;
-    for (int tile = first; tile < n_tiles; tile += stride) {
+
+    // L2 prefetch of the input rows a tile reads (issued two tiles ahead by the first threads: one row each)
+    auto prefetch_tile = [&](int tile) {
       const int b = tile / a.tiles, tf = tile - b * a.tiles;
+      if (INMODE == T2IN_UNFOLD) {
+        // 128 consecutive cells -> the xn rows of the cell rows they touch (full rows: full_w floats)
+        const int cy0 = (tf * 128) / a.Win, cy1 = min(a.Hin - 1, (tf * 128 + 127) / a.Win);
+        const int nrow = (cy1 - cy0 + 1) * 8;
+        if (pt < nrow) {
+          const float* p = a.in + ((size_t)b * (a.Hin * 8) + (size_t)cy0 * 8 + pt) * a.full_w;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((uint32_t)a.full_w * 4u) : "memory");
+        }
+      } else if (C::KS == 1) {
+        const int px0 = tf * 128, npx = min(128, a.Hin * a.Win - px0);
+        if (pt < 8 && npx > 0) {      // 8 slices of the contiguous pixel range
+          const int per = (npx + 7) / 8, s0 = pt * per, cnt = min(per, npx - s0);
+          if (cnt > 0) {
+            const float* p = a.in + ((size_t)b * a.Hin * a.Win + px0 + s0) * C::CIN;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((uint32_t)(cnt * C::CIN * 4)) : "memory");
+          }
+        }
+      } else {
+        const int oy0 = (tf / a.tiles_x) * C::TH, ox0 = (tf % a.tiles_x) * C::TW;
+        const int y0 = (C::S == 1) ? oy0 - 1 : 2 * oy0 - 1, ny = (C::S == 1) ? C::TH + 2 : 2 * C::TH + 1;
+        const int x0 = max(0, (C::S == 1) ? ox0 - 1 : 2 * ox0 - 1), x1 = min(a.Win, (C::S == 1) ? ox0 + C::TW + 1 : 2 * (ox0 + C::TW));
+        const int iy = y0 + pt;
+        if (pt < ny && iy >= 0 && iy < a.Hin && x1 > x0) {
+          const float* p = a.in + (((size_t)b * a.Hin + iy) * a.Win + x0) * C::CIN;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((uint32_t)((x1 - x0) * C::CIN * 4)) : "memory");
+        }
+      }
+    };
+    // decode a unit and issue its global loads
+    auto issue = [&](const ProdPos& u, ProdRegs<UNR>& R) {
+      const int b = u.tile / a.tiles, tf = u.tile - b * a.tiles;
       const int oy0 = (C::KS == 1) ? 0 : (tf / a.tiles_x) * C::TH, ox0 = (C::KS == 1) ? 0 : (tf % a.tiles_x) * C::TW;
       const float* in_b = (INMODE == T2IN_UNFOLD) ? a.in + (size_t)b * (a.Hin * 8) * a.full_w : a.in + (size_t)b * a.Hin * a.Win * C::CIN;
-      for (int ph = 0; ph < NPHASE; ++ph, ++it) {
-        const int buf = it % NBUF;
-        unsigned char* dst_hi = sA + (size_t)buf * C::BUF_BYTES;
-        const int ch = ph * C::CSTAGE + kc * 8;      // first of this thread's 8 channels
-        const bool ch_ok = ch < C::CIN;              // padded chunks (Cin 24 -> 32) are zero
-        float m[8], r[8], sw[8], sb[8];
-        if ((INMODE == T2IN_BN || INMODE == T2IN_BN_SKIP) && ch_ok) {
-          const f8 mm = ldg256(a.in_mean + b * C::CIN + ch), rr = ldg256(a.in_rstd + b * C::CIN + ch);
-          m[0] = mm.a.x; m[1] = mm.a.y; m[2] = mm.a.z; m[3] = mm.a.w; m[4] = mm.b.x; m[5] = mm.b.y; m[6] = mm.b.z; m[7] = mm.b.w;
-          r[0] = rr.a.x; r[1] = rr.a.y; r[2] = rr.a.z; r[3] = rr.a.w; r[4] = rr.b.x; r[5] = rr.b.y; r[6] = rr.b.z; r[7] = rr.b.w;
-          if (INMODE == T2IN_BN_SKIP) {
-            const f8 ww = ldg256(a.skip_w + ch), bb = ldg256(a.skip_b + ch);
-            sw[0] = ww.a.x; sw[1] = ww.a.y; sw[2] = ww.a.z; sw[3] = ww.a.w; sw[4] = ww.b.x; sw[5] = ww.b.y; sw[6] = ww.b.z; sw[7] = ww.b.w;
-            sb[0] = bb.a.x; sb[1] = bb.a.y; sb[2] = bb.a.z; sb[3] = bb.a.w; sb[4] = bb.b.x; sb[5] = bb.b.y; sb[6] = bb.b.z; sb[7] = bb.b.w;
+      const int ch = u.ph * C::CSTAGE + kc * 8;      // first of this thread's 8 channels
+      const bool ch_ok = ch < C::CIN;                // padded chunks (Cin 24 -> 32) are zero
+      R.inside = 0u;
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) {
+        const int idx = (u.rnd * UNR + q) * T2_PROD + pt;
+        R.v[q].a = make_float4(0.f, 0.f, 0.f, 0.f); R.v[q].b = R.v[q].a;
+        R.av[q] = 0.f; R.off[q] = -1;
+        if (idx < ITEMS) {
+          const int rest = idx / KCS;                // idx % KCS == kc
+          const int pix = rest % NPIX, sub = rest / NPIX;
+          int iy, ix;
+          if (C::KS == 1) { const int lin = tf * 128 + pix; iy = lin / a.Win; ix = lin - iy * a.Win; }
+          else if (C::S == 1) { iy = oy0 - C::PAD + pix / WT; ix = ox0 - C::PAD + pix % WT; }
+          else { iy = 2 * (oy0 - 1 + pix / WT) + (sub >> 1); ix = 2 * (ox0 - 1 + pix % WT) + (sub & 1); }
+          R.off[q] = sub * C::SUB_BYTES + kc * PS + pix * 16;
+          if (ch_ok && iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win) {
+            R.inside |= 1u << q;
+            if (INMODE == T2IN_UNFOLD) {
+              // XFeatModel::unfold2d(x, 8), src/XFeat.cc:124-133: channel c = (y % 8) * 8 + x % 8 -> chunk kc = row iy * 8 + kc of xn
+              R.v[q] = ldg256(in_b + (size_t)(iy * 8 + (ch >> 3)) * a.full_w + ix * 8);
+            } else {
+              R.v[q] = ldg256(in_b + ((size_t)iy * a.Win + ix) * C::CIN + ch);
+              if (INMODE == T2IN_BN_SKIP) R.av[q] = a.skip_avg[((size_t)b * a.Hin + iy) * a.Win + ix];
+            }
           }
         }
+      }
+    };
+    // transform the loaded unit and store it into its staged buffer
+    auto consume = [&](const ProdPos& u, const ProdRegs<UNR>& R) {
+      const int buf = u.it % NBUF;
+      unsigned char* dst_hi = sA + (size_t)buf * C::BUF_BYTES;
+      const int b = u.tile / a.tiles;
+      const int ch = u.ph * C::CSTAGE + kc * 8;
+      float m[8], r[8], sw[8], sb[8];
+      if ((INMODE == T2IN_BN || INMODE == T2IN_BN_SKIP) && ch < C::CIN) {      // (L1-resident: neighbouring tiles belong to the same frame)
+        const f8 mm = ldg256(a.in_mean + b * C::CIN + ch), rr = ldg256(a.in_rstd + b * C::CIN + ch);
+        m[0] = mm.a.x; m[1] = mm.a.y; m[2] = mm.a.z; m[3] = mm.a.w; m[4] = mm.b.x; m[5] = mm.b.y; m[6] = mm.b.z; m[7] = mm.b.w;
+        r[0] = rr.a.x; r[1] = rr.a.y; r[2] = rr.a.z; r[3] = rr.a.w; r[4] = rr.b.x; r[5] = rr.b.y; r[6] = rr.b.z; r[7] = rr.b.w;
+        // relu((x - mean) * rstd) * 16 = max(fma(x, 16 rstd, -16 mean rstd), 0): the scale / shift form ATen's batch_norm uses
+        // (alpha = invstd, beta = -mean * invstd), with the exact activation scale folded in
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { r[e] *= T2_ACT_SCALE; m[e] = -m[e] * r[e]; }
+        if (INMODE == T2IN_BN_SKIP) {
+          const f8 ww = ldg256(a.skip_w + ch), bb = ldg256(a.skip_b + ch);
+          sw[0] = ww.a.x; sw[1] = ww.a.y; sw[2] = ww.a.z; sw[3] = ww.a.w; sw[4] = ww.b.x; sw[5] = ww.b.y; sw[6] = ww.b.z; sw[7] = ww.b.w;
+          sb[0] = bb.a.x; sb[1] = bb.a.y; sb[2] = bb.a.z; sb[3] = bb.a.w; sb[4] = bb.b.x; sb[5] = bb.b.y; sb[6] = bb.b.z; sb[7] = bb.b.w;
+        }
+      }
+      if (u.rnd == 0) {
+        if (u.ph == 0 && u.tile + 2 < tile_end) prefetch_tile(u.tile + 2);
         T2_TICK(3);
-        if (it >= NBUF) mbar_wait(bar_free + buf, ((it / NBUF) - 1) & 1);      // the MMAs that read this buffer are done
+        if (u.it >= NBUF) mbar_wait(bar_free + buf, ((u.it / NBUF) - 1) & 1);   // the MMAs that read this buffer are done
         T2_TICK(2);
-        for (int base = 0; base < ITEMS; base += T2_PROD * T2_UNR) {
-          f8 v[T2_UNR];
-          float av[T2_UNR];
-          int off[T2_UNR];
-          bool inside[T2_UNR];
-          // all loads of the batch first (memory-level parallelism), then transform and store
+      }
 #pragma unroll
-          for (int u = 0; u < T2_UNR; ++u) {
-            const int idx = base + u * T2_PROD + pt;
-            v[u].a = make_float4(0.f, 0.f, 0.f, 0.f); v[u].b = v[u].a;
-            av[u] = 0.f; off[u] = -1; inside[u] = false;
-            if (idx < ITEMS) {
-              const int rest = idx / KCS;            // idx % KCS == kc
-              const int pix = rest % NPIX, sub = rest / NPIX;
-              int iy, ix;
-              if (C::KS == 1) { const int lin = tf * 128 + pix; iy = lin / a.Win; ix = lin - iy * a.Win; }
-              else if (C::S == 1) { iy = oy0 - C::PAD + pix / WT; ix = ox0 - C::PAD + pix % WT; }
-              else { iy = 2 * (oy0 - 1 + pix / WT) + (sub >> 1); ix = 2 * (ox0 - 1 + pix % WT) + (sub & 1); }
-              off[u] = sub * C::SUB_BYTES + kc * PS + pix * 16;
-              if (ch_ok && iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win) {
-                inside[u] = true;
-                if (INMODE == T2IN_UNFOLD) {
-                  // XFeatModel::unfold2d(x, 8), src/XFeat.cc:124-133: channel c = (y % 8) * 8 + x % 8 -> chunk kc = row iy * 8 + kc of xn
-                  v[u] = ldg256(in_b + (size_t)(iy * 8 + (ch >> 3)) * a.full_w + ix * 8);
-                } else {
-                  v[u] = ldg256(in_b + ((size_t)iy * a.Win + ix) * C::CIN + ch);
-                  if (INMODE == T2IN_BN_SKIP) av[u] = a.skip_avg[((size_t)b * a.Hin + iy) * a.Win + ix];
-                }
-              }
+      for (int q = 0; q < UNR; ++q) {
+        if (R.off[q] < 0) continue;
+        float x[8] = {R.v[q].a.x, R.v[q].a.y, R.v[q].a.z, R.v[q].a.w, R.v[q].b.x, R.v[q].b.y, R.v[q].b.z, R.v[q].b.w};
+        if ((R.inside >> q) & 1u) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (INMODE == T2IN_BN || INMODE == T2IN_BN_SKIP) {
+              x[e] = fmaxf(fmaf(x[e], r[e], m[e]), 0.f);
+              // x1 + skip1(x), src/XFeat.cc:153; skip1 = AvgPool2d(4,4) + Conv2d(1,24,1) (:36-39)
+              if (INMODE == T2IN_BN_SKIP) x[e] = fmaf(fmaf(R.av[q], sw[e], sb[e]), T2_ACT_SCALE, x[e]);
+            } else {
+              x[e] *= T2_ACT_SCALE;
             }
-          }
-#pragma unroll
-          for (int u = 0; u < T2_UNR; ++u) {
-            if (off[u] < 0) continue;
-            float x[8] = {v[u].a.x, v[u].a.y, v[u].a.z, v[u].a.w, v[u].b.x, v[u].b.y, v[u].b.z, v[u].b.w};
-            if (inside[u]) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                if (INMODE == T2IN_BN || INMODE == T2IN_BN_SKIP) {
-                  x[e] = fmaxf((x[e] - m[e]) * r[e], 0.f);
-                  // x1 + skip1(x), src/XFeat.cc:153; skip1 = AvgPool2d(4,4) + Conv2d(1,24,1) (:36-39)
-                  if (INMODE == T2IN_BN_SKIP) x[e] += av[u] * sw[e] + sb[e];
-                }
-                x[e] *= T2_ACT_SCALE;
-              }
-            }
-            uint4 hi, lo;
-            split2(x[0], x[1], hi.x, lo.x); split2(x[2], x[3], hi.y, lo.y); split2(x[4], x[5], hi.z, lo.z); split2(x[6], x[7], hi.w, lo.w);
-            *reinterpret_cast<uint4*>(dst_hi + off[u]) = hi;
-            *reinterpret_cast<uint4*>(dst_hi + C::IN_BYTES + off[u]) = lo;
           }
         }
+        uint4 hi, lo;
+        split2(x[0], x[1], hi.x, lo.x); split2(x[2], x[3], hi.y, lo.y); split2(x[4], x[5], hi.z, lo.z); split2(x[6], x[7], hi.w, lo.w);
+        *reinterpret_cast<uint4*>(dst_hi + R.off[q]) = hi;
+        *reinterpret_cast<uint4*>(dst_hi + C::IN_BYTES + R.off[q]) = lo;
+      }
+      if (u.rnd == ROUNDS - 1) {
         T2_TICK(3);
         fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async-proxy reads
         mbar_arrive(bar_in + buf);
         T2_TICK(4);
         if (dbg_me) atomicAdd(a.dbg + 5, 1ull);
       }
+    };
+    auto advance = [&](ProdPos& u) {
+      if (++u.rnd == ROUNDS) {
+        u.rnd = 0; ++u.it;
+        if (++u.ph == NPHASE) { u.ph = 0; ++u.tile; }
+      }
+    };
+
+    ProdRegs<UNR> ra, rb;
+    ProdPos u = {tile_begin, 0, 0, 0};
+    if (u.tile < tile_end) {
+      issue(u, ra);
+      while (true) {
+        ProdPos un = u;
+        advance(un);
+        bool more = un.tile < tile_end;
+        if (more) issue(un, rb);           // the next unit's loads fly while this one is transformed
+        consume(u, ra);
+        if (!more) break;
+        u = un;
+        advance(un);
+        more = un.tile < tile_end;
+        if (more) issue(un, ra);
+        consume(u, rb);
+        if (!more) break;
+        u = un;
+      }
     }
   } else if (warp == 4) {
     // ===================== weights (once) + MMA issue: the whole warp runs the uniform loop, ONE elected lane issues ===========
     const bool leader = elect_one_sync();
-    if (leader && first < n_tiles) {
+    if (leader && tile_begin < tile_end) {
       const unsigned char* wsrc = a.wimg + (size_t)split * C::W_BYTES;
-      constexpr uint32_t PH_BYTES = (uint32_t)TAPS * 2 * C::W_UNIT_BYTES;
+      constexpr uint32_t PH_BYTES = (uint32_t)TAPS * C::W_UNIT_BYTES;
       for (int ph = 0; ph < NPHASE; ++ph) {
         mbar_expect_tx(bar_w + ph, PH_BYTES);
-        for (int u = 0; u < TAPS * 2; ++u)
+        for (int u = 0; u < TAPS; ++u)
           bulk_g2s(sW + (size_t)ph * PH_BYTES + (size_t)u * C::W_UNIT_BYTES, wsrc + (size_t)ph * PH_BYTES + (size_t)u * C::W_UNIT_BYTES, C::W_UNIT_BYTES,
                    bar_w + ph);
       }
@@ -316,7 +408,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
     int it = 0, n = 0;
     const bool dbg_me = a.dbg != nullptr && blockIdx.x == 0 && leader;
     long long t0 = dbg_me ? clock64() : 0;
-    for (int tile = first; tile < n_tiles; tile += stride, ++n) {
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++n) {
       const int acc = n & 1;
       T2_TICK(8);
       if (n >= 2) mbar_wait(bar_acce + acc, ((n >> 1) - 1) & 1);                 // the epilogue has drained this accumulator
@@ -344,12 +436,12 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
               tap_off = (uint32_t)((py * 2 + px) * C::SUB_BYTES) + (uint32_t)(dy * WT + dx) * 16u;
             }
             const uint64_t ah = dah + (tap_off >> 4), al = dal + (tap_off >> 4);
-            const uint64_t bh = db0 + (uint64_t)((ph * TAPS + tap) * 2) * W_UNIT, bl = bh + W_UNIT;
+            const uint64_t bw = db0 + (uint64_t)(ph * TAPS + tap) * W_UNIT;
 #pragma unroll
             for (int k16 = 0; k16 < C::CSTAGE / 16; ++k16) {
-              umma_f16_ss(d, ah + k16 * KA, bh + k16 * KB, C::IDESC, (ph > 0 || tap > 0 || k16 > 0) ? 1u : 0u);
-              umma_f16_ss(d, ah + k16 * KA, bl + k16 * KB, C::IDESC, 1u);
-              umma_f16_ss(d, al + k16 * KA, bh + k16 * KB, C::IDESC, 1u);
+              // columns [0, NP) += A_hi W_hi, [NP, 2NP) += A_hi W_lo: one fetch of A_hi for two products; then [0, NP) += A_lo W_hi
+              umma_f16_ss(d, ah + k16 * KA, bw + k16 * KB, C::IDESC_2N, (ph > 0 || tap > 0 || k16 > 0) ? 1u : 0u);
+              umma_f16_ss(d, al + k16 * KA, bw + k16 * KB, C::IDESC_1N, 1u);
             }
           }
           umma_commit(bar_free + buf);                // the staged buffer may be refilled once these MMAs have read it
@@ -359,21 +451,74 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
       }
     }
   } else {
-    // ===================== epilogue: TMEM -> registers -> global (+ statistics) =====================
+    // ===================== epilogue: TMEM -> registers -> staging tile -> TMA store (+ statistics) =====================
     const int quad = warp;                              // TMEM lane quadrant (hardware: warp id % 4)
     const int p = quad * 32 + lane;                     // pixel of the tile = TMEM lane
     const int cbase = split * C::NOUT;                  // first output channel of this CTA's group
     int n = 0;
     const bool dbg_me = a.dbg != nullptr && blockIdx.x == 0 && t == 0;
     long long t0 = dbg_me ? clock64() : 0;
-    for (int tile = first; tile < n_tiles; tile += stride, ++n) {
+    int run_b = -1, run_cnt = 0;                        // tiles of frame run_b this CTA has written partials for, not yet published
+    const int items_per_frame = a.tiles * C::NSPLIT;
+
+    // the frame's last work item: fixed-order fold of all tile partials (slice-strided, then slice order), in double
+    auto fold = [&](int b) {
+      constexpr int NSL = C::COUT >= 128 ? 1 : (C::COUT >= 64 ? 2 : 4);
+      const float* part_b = a.part + (size_t)b * a.tiles * 2 * C::COUT * 2;
+      const int entries = a.tiles * 2;
+      if (t < NSL * C::COUT) {
+        const int c = t % C::COUT, sl = t / C::COUT;
+        double d1 = 0.0, d2 = 0.0;
+        int i = sl;
+        for (; i + 7 * NSL < entries; i += 8 * NSL) {          // 8 independent loads in flight, summed in index order
+          float2 x[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) x[q] = __ldcg(reinterpret_cast<const float2*>(part_b + ((size_t)(i + q * NSL) * C::COUT + c) * 2));
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { d1 += (double)x[q].x; d2 += (double)x[q].y; }
+        }
+        for (; i < entries; i += NSL) {
+          const float2 x = __ldcg(reinterpret_cast<const float2*>(part_b + ((size_t)i * C::COUT + c) * 2));
+          d1 += (double)x.x; d2 += (double)x.y;
+        }
+        sFold[t * 2] = d1; sFold[t * 2 + 1] = d2;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (t < C::COUT) {
+        double d1 = 0.0, d2 = 0.0;
+        for (int sl = 0; sl < NSL; ++sl) { d1 += sFold[(sl * C::COUT + t) * 2]; d2 += sFold[(sl * C::COUT + t) * 2 + 1]; }
+        const double cnt = (double)a.Hout * (double)a.Wout;
+        const double mean = d1 / cnt;
+        double var = d2 / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        a.out_mean[b * C::COUT + t] = (float)mean;
+        a.out_rstd[b * C::COUT + t] = (float)(1.0 / sqrt(var + 1e-5));
+      }
+      if (t == 0) a.ticket[b * XFB_TICKET_STRIDE] = 0u;
+      asm volatile("bar.sync 1, 128;" ::: "memory");     // sFold is reused
+    };
+    // Publish this CTA's partials of frame b (cnt work items): the barrier orders every thread's partial stores before thread 0's
+    // fence + ticket (cumulative at gpu scope); whoever completes the frame folds it.  Once per (CTA, frame), not per tile.
+    auto publish = [&](int b, int cnt) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (t == 0) {
+        __threadfence();
+        const unsigned int prev = atomicAdd(a.ticket + b * XFB_TICKET_STRIDE, (unsigned int)cnt);
+        *s_flag = (prev + (unsigned int)cnt == (unsigned int)items_per_frame) ? 1u : 0u;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (*s_flag) { __threadfence(); fold(b); }
+    };
+
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++n) {
       const int acc = n & 1;
       const int b = tile / a.tiles, tf = tile - b * a.tiles;
       if (dbg_me) atomicAdd(a.dbg + 16, 1ull);
-      int oy, ox;
-      if (C::KS == 1) { const int lin = tf * 128 + p; oy = lin / a.Wout; ox = lin - oy * a.Wout; }
-      else { oy = (tf / a.tiles_x) * C::TH + (p >> 3); ox = (tf % a.tiles_x) * C::TW + (p & 7); }
-      const bool valid = oy < a.Hout && ox < a.Wout;
+      if constexpr (OUTMODE == T2OUT_STATS) {
+        if (run_b >= 0 && b != run_b) { publish(run_b, run_cnt); run_cnt = 0; }
+        run_b = b;
+      }
+      const int oy0 = (C::KS == 1) ? 0 : (tf / a.tiles_x) * C::TH, ox0 = (C::KS == 1) ? 0 : (tf % a.tiles_x) * C::TW;
       const uint32_t tq = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * C::ACC_STRIDE;
       T2_TICK(15);
       mbar_wait(bar_accf + acc, (n >> 1) & 1);
@@ -382,9 +527,24 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
       if constexpr (OUTMODE == T2OUT_KPSOFTMAX) {
         // keypoint_head.3 epilogue: + bias, softmax over the 65 logits, drop the dustbin, 8x8 fold
         // (src/XFeat.cc:85-90, XFextractor::getKptsHeatmap src/XFextractor.cc:204-217); one thread per cell
+        const int lin = tf * 128 + p;
+        const int oy = lin / a.Wout, ox = lin - oy * a.Wout;
         float v[80];
-        tmem_ld32_nw(tq, v); tmem_ld32_nw(tq + 32u, v + 32); tmem_ld16(tq + 64u, v + 64);
-        tmem_ld_fence();
+        {
+          float w[32];
+          tmem_ld32_nw(tq, v); tmem_ld32_nw(tq + (uint32_t)C::NP, w);                 // [0, NP): A_hi W_hi + A_lo W_hi; [NP, 2NP): A_hi W_lo
+          tmem_ld_fence();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] += w[c];
+          tmem_ld32_nw(tq + 32u, v + 32); tmem_ld32_nw(tq + (uint32_t)C::NP + 32u, w);
+          tmem_ld_fence();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[32 + c] += w[c];
+          tmem_ld16(tq + 64u, v + 64); tmem_ld16(tq + (uint32_t)C::NP + 64u, w);
+          tmem_ld_fence();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) v[64 + c] += w[c];
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_acce + acc);
@@ -393,109 +553,88 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
         for (int c = 0; c < 65; ++c) { v[c] = fmaf(v[c], a.out_scale, a.bias[c]); mx = fmaxf(mx, v[c]); }
         float sum = 0.f;
 #pragma unroll
-        for (int c = 0; c < 65; ++c) { v[c] = expf(v[c] - mx); sum += v[c]; }
-        if (valid) {
+        for (int c = 0; c < 65; ++c) { v[c] = __expf(v[c] - mx); sum += v[c]; }
+        const float inv = 1.0f / sum;
+        if (oy < a.Hout) {
           float* dst = a.out + (size_t)b * (a.Hout * 8) * a.full_w + (size_t)(oy * 8) * a.full_w + ox * 8;
 #pragma unroll
           for (int ry = 0; ry < 8; ++ry)
-            stg256(dst + (size_t)ry * a.full_w, v[ry * 8 + 0] / sum, v[ry * 8 + 1] / sum, v[ry * 8 + 2] / sum, v[ry * 8 + 3] / sum, v[ry * 8 + 4] / sum,
-                   v[ry * 8 + 5] / sum, v[ry * 8 + 6] / sum, v[ry * 8 + 7] / sum);
+            stg256(dst + (size_t)ry * a.full_w, v[ry * 8 + 0] * inv, v[ry * 8 + 1] * inv, v[ry * 8 + 2] * inv, v[ry * 8 + 3] * inv, v[ry * 8 + 4] * inv,
+                   v[ry * 8 + 5] * inv, v[ry * 8 + 6] * inv, v[ry * 8 + 7] * inv);
         }
       } else {
-        constexpr int NCH = C::NP / 32;                 // 32-column chunks (NP is 32 or 64 here)
+        constexpr int NCH = C::NP / 32;                 // 32-column chunks of real outputs (NP is 32 or 64 here)
         static_assert(C::NP % 32 == 0, "epilogue chunking");
         float v[NCH][32];
 #pragma unroll
-        for (int ci = 0; ci < NCH; ++ci) tmem_ld32_nw(tq + (uint32_t)ci * 32u, v[ci]);
-        tmem_ld_fence();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_acce + acc);     // values are in registers: the tensor core may reuse the accumulator
-        float* orow = a.out + (((size_t)b * a.Hout + oy) * a.Wout + ox) * C::COUT + cbase;
-#pragma unroll
         for (int ci = 0; ci < NCH; ++ci) {
+          float w[32];
+          tmem_ld32_nw(tq + (uint32_t)ci * 32u, v[ci]);
+          tmem_ld32_nw(tq + (uint32_t)C::NP + (uint32_t)ci * 32u, w);       // the A_hi x W_lo columns
+          tmem_ld_fence();
 #pragma unroll
           for (int q = 0; q < 32; ++q) {
-            float x = v[ci][q] * a.out_scale;
+            float x = (v[ci][q] + w[q]) * a.out_scale;
             if (OUTMODE == T2OUT_BIAS && ci * 32 + q < C::NOUT) x += a.bias[cbase + ci * 32 + q];
             v[ci][q] = x;
           }
-          if (valid) {
-#pragma unroll
-            for (int q = 0; q < 32; q += 8)
-              if (ci * 32 + q < C::NOUT)
-                stg256(orow + ci * 32 + q, v[ci][q], v[ci][q + 1], v[ci][q + 2], v[ci][q + 3], v[ci][q + 4], v[ci][q + 5], v[ci][q + 6], v[ci][q + 7]);
-          }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acce + acc);     // values are in registers: the tensor core may reuse the accumulator
         T2_TICK(11);
+        // the staging tile is free once the previous tile's TMA store has READ it (and every thread is done with its column sums)
+        if (t == 0) bulk_wait_read0();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        T2_TICK(14);
+        // registers -> staging: [128 px][32 ch] fp32 per 32-channel half, 16-byte chunk c of pixel row p at chunk (c ^ (p & 7))
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+          unsigned char* row = sStg + (size_t)ci * 16384 + (size_t)p * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(row + ((c ^ (p & 7)) << 4)) = make_float4(v[ci][4 * c], v[ci][4 * c + 1], v[ci][4 * c + 2], v[ci][4 * c + 3]);
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (t == 0) {
+#pragma unroll
+          for (int h = 0; h < C::NHALF; ++h) {
+            if (C::KS == 1) tma_store_3d(&tmap, smem_u32(sStg + (size_t)h * 16384), cbase + h * 32, tf * 128, b);
+            else tma_store_4d(&tmap, smem_u32(sStg + (size_t)h * 16384), cbase + h * 32, ox0, oy0, b);
+          }
+          bulk_commit();
+        }
+        T2_TICK(12);
         if constexpr (OUTMODE == T2OUT_STATS) {
-          // per-channel sum / sum of squares over the valid pixels of this warp's quadrant: lane j <- channel ci * 32 + j
-#pragma unroll
-          for (int ci = 0; ci < NCH; ++ci) {
-            float sq[32];
-#pragma unroll
-            for (int q = 0; q < 32; ++q) { const float x = valid ? v[ci][q] : 0.f; v[ci][q] = x; sq[q] = x * x; }
-            const float s1 = transpose_reduce32(v[ci], lane);
-            const float s2 = transpose_reduce32(sq, lane);
-            *reinterpret_cast<float2*>(sQ + ((quad * 64) + ci * 32 + lane) * 2) = make_float2(s1, s2);
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          T2_TICK(12);
-          // tile partial = the four quadrants in fixed order -> part[b][tile][channel]
-          float* part_b = a.part + (size_t)b * a.tiles * C::COUT * 2;
-          if (t < C::NOUT) {
+          // per-channel sum / sum of squares over the valid pixels: thread = (channel, pixel half), columns of the staging tile
+          const int c = t % C::NOUT, half = t / C::NOUT;
+          if (half < 2) {
+            int rows_ok, cols_ok;
+            if (C::KS == 1) { rows_ok = 16; cols_ok = 8; }
+            else { rows_ok = min(16, a.Hout - oy0); cols_ok = min(8, a.Wout - ox0); }
+            const int lin_ok = (C::KS == 1) ? min(128, a.Hout * a.Wout - tf * 128) : 128;
+            const unsigned char* colp = sStg + (size_t)(c >> 5) * 16384 + (size_t)(c & 3) * 4;
+            const int cc = (c & 31) >> 2;
             float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd) { const float2 x = *reinterpret_cast<const float2*>(sQ + ((qd * 64) + t) * 2); s1 += x.x; s2 += x.y; }
-            *reinterpret_cast<float2*>(part_b + ((size_t)tf * C::COUT + cbase + t) * 2) = make_float2(s1, s2);
+#pragma unroll 8
+            for (int pp = half * 64; pp < half * 64 + 64; ++pp) {
+              const bool ok = (C::KS == 1) ? (pp < lin_ok) : ((pp >> 3) < rows_ok && (pp & 7) < cols_ok);
+              const float x = *reinterpret_cast<const float*>(colp + (size_t)pp * 128 + ((cc ^ (pp & 7)) << 4));
+              if (ok) { s1 += x; s2 = fmaf(x, x, s2); }
+            }
+            float* part_b = a.part + (size_t)b * a.tiles * 2 * C::COUT * 2;
+            *reinterpret_cast<float2*>(part_b + ((size_t)(tf * 2 + half) * C::COUT + cbase + c) * 2) = make_float2(s1, s2);
           }
-          __threadfence();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          ++run_cnt;
           T2_TICK(13);
-          if (t == 0) {
-            const unsigned int prev = atomicAdd(a.ticket + b * XFB_TICKET_STRIDE, 1u);
-            *s_flag = (prev == (unsigned int)(a.tiles * C::NSPLIT - 1)) ? 1u : 0u;
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          T2_TICK(14);
-          if (*s_flag) {
-            __threadfence();
-            // last work item of the frame: fixed-order fold of all tile partials (slice-strided, then slice order), in double
-            constexpr int NSL = C::COUT >= 128 ? 1 : (C::COUT >= 64 ? 2 : 4);
-            if (t < NSL * C::COUT) {
-              const int c = t % C::COUT, sl = t / C::COUT;
-              double d1 = 0.0, d2 = 0.0;
-              int i = sl;
-              for (; i + 7 * NSL < a.tiles; i += 8 * NSL) {        // 8 independent loads in flight, summed in index order
-                float2 x[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) x[q] = __ldcg(reinterpret_cast<const float2*>(part_b + ((size_t)(i + q * NSL) * C::COUT + c) * 2));
-#pragma unroll
-                for (int q = 0; q < 8; ++q) { d1 += (double)x[q].x; d2 += (double)x[q].y; }
-              }
-              for (; i < a.tiles; i += NSL) {
-                const float2 x = __ldcg(reinterpret_cast<const float2*>(part_b + ((size_t)i * C::COUT + c) * 2));
-                d1 += (double)x.x; d2 += (double)x.y;
-              }
-              sFold[t * 2] = d1; sFold[t * 2 + 1] = d2;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (t < C::COUT) {
-              double d1 = 0.0, d2 = 0.0;
-              for (int sl = 0; sl < NSL; ++sl) { d1 += sFold[(sl * C::COUT + t) * 2]; d2 += sFold[(sl * C::COUT + t) * 2 + 1]; }
-              const double cnt = (double)a.Hout * (double)a.Wout;
-              const double mean = d1 / cnt;
-              double var = d2 / cnt - mean * mean;
-              if (var < 0.0) var = 0.0;
-              a.out_mean[b * C::COUT + t] = (float)mean;
-              a.out_rstd[b * C::COUT + t] = (float)(1.0 / sqrt(var + 1e-5));
-            }
-            if (t == 0) a.ticket[b * XFB_TICKET_STRIDE] = 0u;
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");   // sQ / sFold / s_flag are reused by the next tile
         }
       }
     }
+    if constexpr (OUTMODE == T2OUT_STATS) {
+      if (run_b >= 0) publish(run_b, run_cnt);
+    }
+    if (C::HAS_STG && t == 0) bulk_wait0();            // the last stores have left shared memory and are complete
   }
   tc_fence_before();
   __syncthreads();
@@ -507,19 +646,19 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
 }
 
 // ---------------------------------------------------------------------------------------------------
-//                        CIN COUT KS S CSTAGE NBUF NSPLIT
-using T2B2x = T2Cfg<24, 24, 3, 1, 32, 3, 1>;      // block2.0/.1                   120x160         (Cin padded 24 -> 32)
-using T2B30 = T2Cfg<24, 64, 3, 2, 16, 3, 1>;      // block3.0                      -> 60x80
-using T2C33 = T2Cfg<64, 64, 3, 1, 32, 3, 1>;      // block3.1, block4.1/.2, block_fusion.0/.1   (147 KB of weights resident)
-using T2C11 = T2Cfg<64, 64, 1, 1, 64, 3, 1>;      // block3.2, block_fusion.2, heatmap_head.0/.1, keypoint_head.0/.1/.2
-using T2B40 = T2Cfg<64, 64, 3, 2, 16, 2, 1>;      // block4.0                      -> 30x40
-using T2B50 = T2Cfg<64, 128, 3, 2, 16, 2, 2>;     // block5.0                      -> 15x20        (two output groups of 64)
-using T2B5x = T2Cfg<128, 128, 3, 1, 32, 3, 4>;    // block5.1/.2                                   (four output groups of 32)
-using T2B53 = T2Cfg<128, 64, 1, 1, 64, 3, 1>;     // block5.3
-using T2KP3 = T2Cfg<64, 65, 1, 1, 64, 3, 1>;      // keypoint_head.3 (65 outputs, N padded to 80) + softmax / fold epilogue
+//                        CIN COUT KS S CSTAGE NBUF NSPLIT UNR
+using T2B2x = T2Cfg<24, 24, 3, 1, 32, 3, 1, 4>;      // block2.0/.1                   120x160         (Cin padded 24 -> 32)
+using T2B30 = T2Cfg<24, 64, 3, 2, 16, 3, 1, 3>;      // block3.0                      -> 60x80
+using T2C33 = T2Cfg<64, 64, 3, 1, 32, 2, 1, 4>;      // block3.1, block4.1/.2, block_fusion.0/.1   (147 KB of weights resident)
+using T2C11 = T2Cfg<64, 64, 1, 1, 64, 3, 1, 3>;      // block3.2, block_fusion.2, heatmap_head.0/.1, keypoint_head.0/.1/.2
+using T2B40 = T2Cfg<64, 64, 3, 2, 16, 2, 2, 3>;      // block4.0                      -> 30x40        (two output groups of 32)
+using T2B50 = T2Cfg<64, 128, 3, 2, 16, 2, 4, 3>;     // block5.0                      -> 15x20        (four output groups of 32)
+using T2B5x = T2Cfg<128, 128, 3, 1, 32, 2, 4, 4>;    // block5.1/.2                                   (four output groups of 32)
+using T2B53 = T2Cfg<128, 64, 1, 1, 64, 3, 1, 3>;     // block5.3
+using T2KP3 = T2Cfg<64, 65, 1, 1, 64, 3, 1, 3>;      // keypoint_head.3 (65 outputs, N padded to 80) + softmax / fold epilogue
 
-struct T2LayerInfo { int cstage, np, nsplit, cinp; };
-template <class C> static T2LayerInfo t2_info_of() { return {C::CSTAGE, C::NP, C::NSPLIT, C::CINP}; }
+struct T2LayerInfo { int cstage, np, nsplit, cinp, ks; };
+template <class C> static T2LayerInfo t2_info_of() { return {C::CSTAGE, C::NP, C::NSPLIT, C::CINP, C::KS}; }
 static T2LayerInfo t2_info(int L) {
   switch (L) {
     case L_B2_0: case L_B2_1: return t2_info_of<T2B2x>();
@@ -534,6 +673,52 @@ static T2LayerInfo t2_info(int L) {
   }
 }
 
+// ---- tensor maps of the layer outputs (host) -------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static_assert(sizeof(CUtensorMap) == sizeof(Ctx::TmapSlot::blob), "tensor map storage");
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// NHWC fp32 output [B][H][W][C]: 3x3 layers store 8 x 16-pixel tiles (4-D map {C, W, H, B}), 1x1 layers 128 consecutive pixels
+// (3-D map {C, H*W, B}); box = 32 channels (128 bytes, 128B swizzle), clipped at the frame border by the hardware.
+static cudaError_t output_tmap(Ctx* c, int L, float* out, int B, int H, int W, int C, bool linear, const CUtensorMap** map) {
+  Ctx::TmapSlot& s = c->tmap[L];
+  if (s.ptr != out || s.B != B || s.H != H || s.W != W) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return cudaErrorNotSupported;
+    CUtensorMap m;
+    CUresult r;
+    if (linear) {
+      const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)H * W, (cuuint64_t)B};
+      const cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)H * W * C * 4};
+      const cuuint32_t box[3] = {32, 128, 1}, es[3] = {1, 1, 1};
+      r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+      const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+      const cuuint32_t box[4] = {32, 8, 16, 1}, es[4] = {1, 1, 1, 1};
+      r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    std::memcpy(s.blob, &m, sizeof(m));
+    s.ptr = out; s.B = B; s.H = H; s.W = W;
+  }
+  *map = reinterpret_cast<const CUtensorMap*>(s.blob);
+  return cudaSuccess;
+}
+
 template <class C, int INMODE, int OUTMODE>
 static cudaError_t run_tc2(Ctx* c, ConvTc2Args& a, int tag) {
   auto kern = conv_tc2_kernel<C, INMODE, OUTMODE>;
@@ -546,31 +731,37 @@ static cudaError_t run_tc2(Ctx* c, ConvTc2Args& a, int tag) {
   a.B = c->B;
   if (C::KS == 1) { a.tiles_x = 1; a.tiles = (a.Hout * a.Wout + 127) / 128; }
   else { a.tiles_x = (a.Wout + C::TW - 1) / C::TW; a.tiles = a.tiles_x * ((a.Hout + C::TH - 1) / C::TH); }
+  const CUtensorMap* map = reinterpret_cast<const CUtensorMap*>(c->tmap[tag].blob);     // (unused by keypoint_head.3)
+  if (C::HAS_STG) {
+    cudaError_t e = output_tmap(c, tag, a.out, a.B, a.Hout, a.Wout, C::COUT, C::KS == 1, &map);
+    if (e != cudaSuccess) return e;
+  }
   const int items = a.B * a.tiles * C::NSPLIT;
   int grid = c->num_sms - c->num_sms % C::NSPLIT;            // persistent: one CTA per SM, a multiple of the output groups
   if (grid > items) grid = items;                            // (items is a multiple of NSPLIT)
   prof_begin(c, tag);
-  kern<<<grid, T2_THREADS, C::SMEM_BYTES, c->stream>>>(a);
+  kern<<<grid, T2_THREADS, C::SMEM_BYTES, c->stream>>>(a, *map);
   prof_end(c);
   c->launches++;
   return cudaGetLastError();
 }
 
-// floats of partial-sum scratch per frame: [tiles][COUT][2]
+// floats of partial-sum scratch per frame: [tiles][2 pixel halves][COUT][2]
 size_t conv_tc2_part_floats(int H, int W) {
   size_t m = 0;
   auto upd = [&](int lvl, int cout, bool linear) {
     const int h = H >> lvl, w = W >> lvl;
     const size_t tiles = linear ? (size_t)(h * w + 127) / 128 : (size_t)((w + 7) / 8) * ((h + 15) / 16);
-    const size_t v = tiles * cout * 2;
+    const size_t v = tiles * 2 * cout * 2;
     if (v > m) m = v;
   };
   upd(2, 24, false); upd(3, 64, false); upd(3, 64, true); upd(4, 64, false); upd(5, 128, false); upd(5, 64, true);
   return m;
 }
 
-// Host side of xfb_create: OIHW fp32 weights -> [split][phase][tap][hi | lo][cstage/8][np/8][8][8 halfs] UMMA operand images of
-// w * 2^k (k chosen so that max |w| * 2^k is in [1024, 2048)); returns the epilogue factor 1 / (16 * 2^k).
+// Host side of xfb_create: OIHW fp32 weights -> [split][phase][tap][cstage/8][2*np/8][8][8 halfs] UMMA operand images of
+// w * 2^k (k chosen so that max |w| * 2^k is in [1024, 2048)): rows [0, np) hold the fp16 hi pieces, rows [np, 2np) the lo
+// pieces.  Returns the epilogue factor 1 / (16 * 2^k).
 float conv_tc2_pack_weights(int L, const float* oihw, int cout, int cin, int ks, std::vector<unsigned char>& img) {
   const T2LayerInfo li = t2_info(L);
   const int taps = ks * ks, nphase = li.cinp / li.cstage, nout = cout / li.nsplit;
@@ -579,8 +770,8 @@ float conv_tc2_pack_weights(int L, const float* oihw, int cout, int cin, int ks,
   int k = 0;
   if (wmax > 0.f) { int e; std::frexp(wmax, &e); k = 11 - e; }           // wmax = f * 2^e, f in [0.5, 1)  ->  wmax * 2^k in [1024, 2048)
   const float wscale = std::ldexp(1.0f, k);
-  const size_t unit = (size_t)li.cstage * li.np * 2;                     // bytes of one hi (or lo) image of a (phase, tap)
-  const size_t group = (size_t)nphase * taps * 2 * unit;
+  const size_t unit = (size_t)li.cstage * 2 * li.np * 2;                 // bytes of one (phase, tap) image
+  const size_t group = (size_t)nphase * taps * unit;
   img.assign((size_t)li.nsplit * group, 0);
   for (int tap = 0; tap < taps; ++tap)
     for (int co = 0; co < cout; ++co)
@@ -590,10 +781,10 @@ float conv_tc2_pack_weights(int L, const float* oihw, int cout, int cin, int ks,
         const __half lo = __float2half_rn(w - __half2float(hi));
         const int sp = co / nout, col = co % nout;
         const int ph = ci / li.cstage, cil = ci % li.cstage;
-        const size_t off = ((size_t)(cil >> 3) * (li.np >> 3) + (col >> 3)) * 128 + (size_t)(col & 7) * 16 + (size_t)(cil & 7) * 2;
-        const size_t base = (size_t)sp * group + ((size_t)ph * taps + tap) * 2 * unit;
-        std::memcpy(&img[base + off], &hi, 2);
-        std::memcpy(&img[base + unit + off], &lo, 2);
+        const size_t base = (size_t)sp * group + ((size_t)ph * taps + tap) * unit;
+        auto at = [&](int row) { return base + ((size_t)(cil >> 3) * (2 * li.np >> 3) + (row >> 3)) * 128 + (size_t)(row & 7) * 16 + (size_t)(cil & 7) * 2; };
+        std::memcpy(&img[at(col)], &hi, 2);
+        std::memcpy(&img[at(li.np + col)], &lo, 2);
       }
   return 1.0f / (T2_ACT_SCALE * wscale);
 }

@@ -1,0 +1,509 @@
+// match_mutual.cu -- mutual brute-force matching (row-wise best / second-best AND column-wise best) of two 64-D descriptor
+// sets in ONE pass over ONE streamed GEMM per pair, on the tcgen05 tensor cores.
+//
+// Output contract (unchanged, bit-exact w.r.t. oracle/matcher_oracle.c): the reference's INTEGER distance
+// (ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:2242-2250: int(float(||a-b||^2) * 512)), its best / second-best scan per row
+// (src/ORBmatcher.cc:476-486: strict '<', ascending index) and the column-wise argmin of the same matrix (the mutual-NN check of
+// the commented-out ORBmatcher::match, src/ORBmatcher.cc:340-406).  As in match_stream.cu the tensor cores FILTER and the few
+// survivors are VERIFIED with the exact arithmetic; what is new is that everything happens in one stream of the column set:
+//
+//   * Operand images: every descriptor x is ONE fp16 row of K = 80: [x_0 .. x_63 | tail], and carries BOTH tails:
+//       as a ROW    vector: [ p1 p2 p3 1 1 1 0 0 ]        as a COLUMN vector: [ 1 1 1 p1 p2 p3 0 0 ],   p1 + p2 + p3 = -|x|^2 / 2
+//     so the GEMM yields  u_ij = a_i.b_j - |a_i|^2/2 - |b_j|^2/2 = -||a_i - b_j||^2 / 2  directly:  512 d_ij ~ t_ij = -1024 u_ij
+//     with |t - 512 float(d)| <= e = 1.05 |a||b| + small (fp16 rounding of both operands).  Larger u = smaller distance, for rows
+//     and columns alike, no per-row / per-column offset.  Padded rows / columns carry a tail of -60000 and never win.
+//   * Per (128 rows of A, pair) one CTA streams the 128-column blocks of B ONCE through a ring of bulk copies and issues, per
+//     block, TWO accumulators: D1 = A_blk B_c^T (TMEM lane = row, columns = the block's columns) and D2 = B_c A_blk^T (lane =
+//     column, columns = the CTA's rows) -- the same inner products, transposed by the tensor core, so that BOTH directions get the
+//     cheap "one lane owns one line of 128 values" epilogue.  Two accumulator stages of 2 x 128 TMEM columns.
+//   * Row direction (8 warps, two groups alternating blocks): running top-2 of the 32-column slice maxima per row (the
+//     second-largest slice maximum is attained by another column than the largest, so it bounds the row's second-smallest t);
+//     a column is a CANDIDATE when u > (running bound) - (2e + 1)/1024.  The bound only tightens; candidates are queued with the
+//     slice maximum as an upper bound of their u and re-filtered against the FINAL bound before the exact verification.
+//   * Column direction (8 warps): per block and column the maximum over the CTA's 128 rows; rows within (2e + 1)/1024 of it are
+//     queued.  The per-column maxima of all CTAs of a pair meet in a global array (atomicMax); at the end a CTA verifies only the
+//     queued rows that are still within the margin of the GLOBAL maximum, and merges exact (distance, row) keys with a 64-bit
+//     global atomicMin -- the total order (distance, index) of the reference's scan.  The last CTA of a pair writes the column
+//     outputs and resets the scratch.
+//   * Verification: 32 queued pairs at a time, one per lane (the 64-step fp64 chain is paid once per 32).
+//
+// Warp roles (576 threads): warp 0 loader, warp 1 TMEM allocator + MMA issuer (one elected lane), warps 2-9 row direction,
+// warps 10-17 column direction (TMEM lane quadrant = warp id % 4).  Vocabulary-node gated searches (group ids) and descriptor
+// sets outside the fp16 range keep using match_stream.cu.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "tc_ptx.cuh"
+#include "xfb_internal.h"
+
+namespace xfb {
+
+constexpr int MM_ROWS = 128;
+constexpr int MM_CHUNKS = 11;                          // 8 data chunks (8 fp16 each) + row tail + column tail + zeros
+constexpr int MM_BLK_BYTES = MM_CHUNKS * 2048;         // one 128-descriptor block: 22 KB, one bulk copy
+constexpr uint32_t MM_LBO = 2048, MM_SBO = 128;        // bytes between 16-byte K chunks / between 8-row groups
+constexpr int MM_STAGES = 4;                           // column blocks in flight
+constexpr int MM_EPI_WARPS = 16;
+constexpr int MM_THREADS = 64 + 32 * MM_EPI_WARPS;
+constexpr int MM_Q1 = 512, MM_Q2 = 768;                // queue entries per row-direction / column-direction warp
+constexpr float MM_PAD_TAIL = -60000.0f;
+constexpr uint32_t MM_IDESC = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);   // kind::f16, F16 x F16 -> F32, M = N = 128
+
+size_t mm_image_bytes(int rows_padded) { return (size_t)(rows_padded / MM_ROWS) * MM_BLK_BYTES; }
+
+// ---- operand images: one thread per (row, 4 consecutive k); rows >= n (per set) are zero with the padding tails ----------
+__global__ void __launch_bounds__(256) mm_prep_kernel(const float* desc, size_t set_stride, const int32_t* n_dev, int n_host, int rows_padded,
+                                                      unsigned char* img, size_t img_set_bytes, float* nrm, float* nrm_max) {
+  const int set = blockIdx.y;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;   // row * 16 + kq
+  const int row = g >> 4, kq = g & 15;
+  if (row >= rows_padded) return;
+  const int n = n_dev ? min(n_host, n_dev[set]) : n_host;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row < n) v = *reinterpret_cast<const float4*>(desc + (size_t)set * set_stride + (size_t)row * 64 + kq * 4);
+  const int blk = row >> 7, r = row & 127;
+  unsigned char* base = img + (size_t)set * img_set_bytes + (size_t)blk * MM_BLK_BYTES;
+  const size_t roff = (size_t)(r >> 3) * MM_SBO + (size_t)(r & 7) * 16;
+  const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<const unsigned int*>(&h01);
+  pk.y = *reinterpret_cast<const unsigned int*>(&h23);
+  *reinterpret_cast<uint2*>(base + (size_t)(kq >> 1) * MM_LBO + roff + (size_t)(kq & 1) * 8) = pk;
+  double s = (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 16);
+  if (kq == 0) {
+    const float nf = (float)s;
+    nrm[(size_t)set * rows_padded + row] = (row < n) ? nf : CUDART_INF_F;
+    if (s > 0.0 && row < n) atomicMax(reinterpret_cast<unsigned int*>(nrm_max + set), __float_as_uint(nf));
+    float x = (row < n) ? -0.5f * nf : MM_PAD_TAIL;       // -|x|^2/2 = p1 + p2 + p3 (fp16 pieces, residual 2^-33)
+    const __half p1 = __float2half_rn(x);
+    x -= __half2float(p1);
+    const __half p2 = __float2half_rn(x);
+    x -= __half2float(p2);
+    const __half p3 = __float2half_rn(x);
+    const unsigned int p12 = (unsigned int)__half_as_ushort(p1) | ((unsigned int)__half_as_ushort(p2) << 16);
+    const unsigned int p3u = (unsigned int)__half_as_ushort(p3);
+    // row-role tail [p1 p2 p3 1 | 1 1 0 0], column-role tail [1 1 1 p1 | p2 p3 0 0]; 1.0 = 0x3C00
+    *reinterpret_cast<uint4*>(base + 8 * MM_LBO + roff) = make_uint4(p12, p3u | 0x3C000000u, 0x3C003C00u, 0u);
+    *reinterpret_cast<uint4*>(base + 9 * MM_LBO + roff) = make_uint4(0x3C003C00u, 0x00003C00u | (p12 << 16), (p12 >> 16) | (p3u << 16), 0u);
+    *reinterpret_cast<uint4*>(base + 10 * MM_LBO + roff) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+__device__ __forceinline__ void mm_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(MM_IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mm_ld32(uint32_t taddr, float* v) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
+      "%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]), "=r"(u[10]),
+        "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]),
+        "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]),
+        "=r"(u[31])
+      : "r"(taddr));
+  // the wait is tied to the 32 destination registers, so that no use of them can be scheduled above it
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(u[0]), "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]), "+r"(u[8]), "+r"(u[9]), "+r"(u[10]),
+                 "+r"(u[11]), "+r"(u[12]), "+r"(u[13]), "+r"(u[14]), "+r"(u[15]), "+r"(u[16]), "+r"(u[17]), "+r"(u[18]), "+r"(u[19]), "+r"(u[20]),
+                 "+r"(u[21]), "+r"(u[22]), "+r"(u[23]), "+r"(u[24]), "+r"(u[25]), "+r"(u[26]), "+r"(u[27]), "+r"(u[28]), "+r"(u[29]), "+r"(u[30]),
+                 "+r"(u[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ float mm_max32(const float* v) {
+  float mg[8];
+#pragma unroll
+  for (int g = 0; g < 8; ++g) mg[g] = fmaxf(fmaxf(v[4 * g], v[4 * g + 1]), fmaxf(v[4 * g + 2], v[4 * g + 3]));
+  return fmaxf(fmaxf(fmaxf(mg[0], mg[1]), fmaxf(mg[2], mg[3])), fmaxf(fmaxf(mg[4], mg[5]), fmaxf(mg[6], mg[7])));
+}
+// order-preserving float -> unsigned (0 is below every value)
+__device__ __forceinline__ unsigned int mm_ord(float u) {
+  const unsigned int b = __float_as_uint(u);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float mm_unord(unsigned int o) {
+  if (o == 0u) return -CUDART_INF_F;
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+// exact ORBmatcher::DescriptorDistance of two fp32 rows (same op order as oracle/matcher_oracle.c)
+__device__ __forceinline__ int mm_exact_distance(const float* arow, const float* brow) {
+  double s = 0.0;
+#pragma unroll 4
+  for (int kq = 0; kq < 16; ++kq) {
+    const float4 x = *reinterpret_cast<const float4*>(arow + kq * 4);
+    const float4 b = *reinterpret_cast<const float4*>(brow + kq * 4);
+    float d;
+    d = x.x - b.x; s = fma((double)d, (double)d, s);
+    d = x.y - b.y; s = fma((double)d, (double)d, s);
+    d = x.z - b.z; s = fma((double)d, (double)d, s);
+    d = x.w - b.w; s = fma((double)d, (double)d, s);
+  }
+  return (int)(__double2float_rn(s) * 512.0f);
+}
+
+struct MmShared {
+  uint64_t bar_a, bar_full[MM_STAGES], bar_empty[MM_STAGES], bar_accf1[2], bar_acce1[2], bar_accf2[2], bar_acce2[2];
+  uint32_t tmem, flag;
+};
+
+template <bool MUTUAL>
+__global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* sA = smem_raw;                                                   // the CTA's 128-row block
+  unsigned char* sB0 = sA + MM_BLK_BYTES;                                         // MM_STAGES column blocks
+  unsigned long long* sQ1 = reinterpret_cast<unsigned long long*>(sB0 + MM_STAGES * MM_BLK_BYTES);   // [8][MM_Q1] (slice max bits << 32 | row << 24 | column)
+  unsigned long long* sQ2 = sQ1 + 8 * MM_Q1;                                      // [8][MM_Q2]
+  unsigned long long* sK1 = sQ2 + 8 * MM_Q2;                                      // [128] exact best key of the row
+  unsigned long long* sK2 = sK1 + MM_ROWS;                                        // [128] exact second key
+  float2* sM = reinterpret_cast<float2*>(sK2 + MM_ROWS);                          // [2][128] running (largest, second-largest) slice maximum per group
+  float* sTau = reinterpret_cast<float*>(sM + 2 * MM_ROWS);                       // [2][128] current candidate bound per group; [0] = final after the stream
+  MmShared* sh = reinterpret_cast<MmShared*>(sTau + 2 * MM_ROWS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.y;
+  const int setA = a.pairs[2 * pair], setB = a.pairs[2 * pair + 1];
+  const int nA = a.nA_dev ? min(a.nA_host, a.nA_dev[setA]) : a.nA_host;
+  const int nB = a.nB_dev ? min(a.nB_host, a.nB_dev[setB]) : a.nB_host;
+  const int row0 = blockIdx.x * MM_ROWS;
+  const int nblk = (row0 < nA) ? (nB + MM_ROWS - 1) / MM_ROWS : 0;                // column blocks
+  const unsigned char* imgA = reinterpret_cast<const unsigned char*>(a.imgA) + (size_t)setA * a.img_stride_A + (size_t)blockIdx.x * MM_BLK_BYTES;
+  const unsigned char* imgB = reinterpret_cast<const unsigned char*>(a.imgB) + (size_t)setB * a.img_stride_B;
+  const float* rawA = a.rawA + (size_t)setA * a.raw_stride_A;
+  const float* rawB = a.rawB + (size_t)setB * a.raw_stride_B;
+  const unsigned int init_u = (unsigned int)a.init;
+  unsigned int* colG = a.col_g + (size_t)pair * a.rows_padded_B;
+  unsigned long long* colK = a.col_k + (size_t)pair * a.rows_padded_B;
+
+  if (threadIdx.x < MM_ROWS) {
+    const unsigned long long k0 = ((unsigned long long)init_u << 32) | 0xffffffffull;
+    sK1[threadIdx.x] = k0; sK2[threadIdx.x] = k0;
+    sTau[threadIdx.x] = -CUDART_INF_F; sTau[MM_ROWS + threadIdx.x] = -CUDART_INF_F;     // (an overflow drain before the first bound is stored verifies everything)
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&sh->bar_a, 1);
+    for (int s = 0; s < MM_STAGES; ++s) { mbar_init(&sh->bar_full[s], 1); mbar_init(&sh->bar_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sh->bar_accf1[s], 1); mbar_init(&sh->bar_acce1[s], 4);
+      mbar_init(&sh->bar_accf2[s], 1); mbar_init(&sh->bar_acce2[s], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&sh->tmem, 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh->tmem;
+
+  // error scale of the tensor-core estimate (see header): per row for the row direction, per set for the column direction
+  const float nbm = (nblk > 0) ? a.nrm_max_B[setB] : 0.f;
+  const float nam = (nblk > 0) ? a.nrm_max_A[setA] : 0.f;
+  const bool wild_set = !(nam < 1.0e5f && nbm < 1.0e5f);      // outside the fp16 images' range: every pair is verified
+
+  if (warp == 0) {
+    // ===== loader (one elected lane) =====
+    if (elect_one_sync() && nblk > 0) {
+      mbar_expect_tx(&sh->bar_a, MM_BLK_BYTES);
+      bulk_g2s(sA, imgA, MM_BLK_BYTES, &sh->bar_a);
+      for (int k = 0; k < nblk; ++k) {
+        const int s = k % MM_STAGES;
+        if (k >= MM_STAGES) mbar_wait(&sh->bar_empty[s], ((k / MM_STAGES) - 1) & 1);
+        mbar_expect_tx(&sh->bar_full[s], MM_BLK_BYTES);
+        bulk_g2s(sB0 + (size_t)s * MM_BLK_BYTES, imgB + (size_t)k * MM_BLK_BYTES, MM_BLK_BYTES, &sh->bar_full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: ONE elected lane runs the whole loop =====
+    if (elect_one_sync() && nblk > 0) {
+      mbar_wait(&sh->bar_a, 0);
+      tc_fence_after();
+      const uint32_t aAddr = smem_u32(sA);
+      const uint64_t dA0 = umma_desc_kmajor(aAddr, MM_LBO, MM_SBO);
+      const uint64_t dAt = umma_desc_kmajor(aAddr + 8 * MM_LBO, 2 * MM_LBO, MM_SBO);        // row tail, then the zero chunk
+      constexpr uint64_t KSTEP = (2u * MM_LBO) >> 4;
+#pragma unroll 1
+      for (int k = 0; k < nblk; ++k) {
+        const int s = k % MM_STAGES, st = k & 1;
+        mbar_wait(&sh->bar_full[s], (k / MM_STAGES) & 1);
+        if (k >= 2) {
+          mbar_wait(&sh->bar_acce1[st], ((k >> 1) - 1) & 1);
+          if (MUTUAL) mbar_wait(&sh->bar_acce2[st], ((k >> 1) - 1) & 1);
+        }
+        tc_fence_after();
+        const uint32_t bAddr = smem_u32(sB0 + (size_t)s * MM_BLK_BYTES);
+        const uint64_t dB0 = umma_desc_kmajor(bAddr, MM_LBO, MM_SBO);
+        const uint64_t dBt = umma_desc_kmajor(bAddr + 9 * MM_LBO, MM_LBO, MM_SBO);          // column tail, then the zero chunk
+        const uint32_t d1 = tmem_base + (uint32_t)st * 256u, d2 = d1 + 128u;
+        // D1[row][column] = a.b + rowtail.coltail
+        mm_umma(d1, dA0, dB0, 0u);
+        mm_umma(d1, dA0 + KSTEP, dB0 + KSTEP, 1u);
+        mm_umma(d1, dA0 + 2 * KSTEP, dB0 + 2 * KSTEP, 1u);
+        mm_umma(d1, dA0 + 3 * KSTEP, dB0 + 3 * KSTEP, 1u);
+        mm_umma(d1, dAt, dBt, 1u);
+        umma_commit(&sh->bar_accf1[st]);
+        if (MUTUAL) {
+          // D2[column][row]: the same products with the operands swapped
+          mm_umma(d2, dB0, dA0, 0u);
+          mm_umma(d2, dB0 + KSTEP, dA0 + KSTEP, 1u);
+          mm_umma(d2, dB0 + 2 * KSTEP, dA0 + 2 * KSTEP, 1u);
+          mm_umma(d2, dB0 + 3 * KSTEP, dA0 + 3 * KSTEP, 1u);
+          mm_umma(d2, dBt, dAt, 1u);
+          umma_commit(&sh->bar_accf2[st]);
+        }
+        umma_commit(&sh->bar_empty[s]);     // the column block may be overwritten once these MMAs have read it
+      }
+    }
+    __syncwarp();
+  } else {
+    const int ew = warp - 2;                       // 0..15
+    const bool dir2 = ew >= 8;                     // column direction
+    const int group = (ew >> 2) & 1;               // which accumulator stage / which half of the blocks
+    const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
+    const int ln = quad * 32 + lane;               // line of the accumulator this lane owns
+    const uint32_t tq = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)group * 256u + (dir2 ? 128u : 0u);
+    unsigned long long* q = dir2 ? sQ2 + (size_t)(ew - 8) * MM_Q2 : sQ1 + (size_t)ew * MM_Q1;
+    const int qcap = dir2 ? MM_Q2 : MM_Q1;
+    int qn = 0;                                    // warp-uniform fill count
+    const float e_col = 1.05f * sqrtf(nam * nbm) + 0.02f * (nam + nbm + 1.0f);
+    const float margin_col = wild_set ? CUDART_INF_F : (2.0f * e_col + 1.0f) * (1.0f / 1024.0f);
+
+    // exact verification of queued (row, column) pairs, 32 at a time; `final` = the stream is over (tight filters)
+    auto drain = [&](bool final) {
+      __syncwarp();
+      for (int i = lane; i < qn; i += 32) {
+        const unsigned long long ent = q[i];
+        const int r = (int)((ent >> 24) & 0x7full), j = (int)(ent & 0xffffffull);
+        const float ub = __uint_as_float((unsigned int)(ent >> 32));        // upper bound of the pair's u
+        if (!dir2) {
+          const float tau = final ? sTau[r] : sTau[group * MM_ROWS + r];
+          if (!(ub > tau) && !wild_set) continue;
+          const int D = mm_exact_distance(rawA + (size_t)(row0 + r) * 64, rawB + (size_t)j * 64);
+          if ((unsigned int)D < init_u) {
+            const unsigned long long key = ((unsigned long long)(unsigned int)D << 32) | (unsigned int)j;
+            const unsigned long long old = atomicMin(&sK1[r], key);
+            atomicMin(&sK2[r], max(old, key));
+          }
+        } else {
+          const float gmax = mm_unord(__ldcg(colG + j));                    // largest estimate any CTA has seen for this column
+          if (!(ub >= gmax - margin_col) && !wild_set) continue;
+          const int D = mm_exact_distance(rawA + (size_t)(row0 + r) * 64, rawB + (size_t)j * 64);
+          if ((unsigned int)D < init_u) atomicMin(colK + j, ((unsigned long long)(unsigned int)D << 32) | (unsigned int)(row0 + r));
+        }
+      }
+      qn = 0;
+      __syncwarp();
+    };
+    // warp-uniform append (no atomics): every round, each lane with candidates left contributes its lowest one
+    // entry e of the mask is the pair (row_base + e * row_step, col_base + e * col_step)
+    auto append = [&](uint32_t mask, int row_base, int row_step, int col_base, int col_step, float ub) {
+      const unsigned long long hi = (unsigned long long)__float_as_uint(ub) << 32;
+      while (__any_sync(0xffffffffu, mask != 0u)) {
+        if (qn > qcap - 32) drain(false);
+        const bool has = mask != 0u;
+        const uint32_t bal = __ballot_sync(0xffffffffu, has);
+        if (has) {
+          const int e = __ffs(mask) - 1;
+          mask &= mask - 1u;
+          const unsigned int r = (unsigned int)(row_base + e * row_step), j = (unsigned int)(col_base + e * col_step);
+          q[qn + __popc(bal & ((1u << lane) - 1u))] = hi | ((unsigned long long)r << 24) | j;
+        }
+        qn += __popc(bal);
+      }
+    };
+
+    if (!dir2) {
+      // ===== row direction: lane = row =====
+      const int row = row0 + ln;
+      const bool ok = row < nA;
+      float margin = 0.f, cap = CUDART_INF_F;
+      bool wild = wild_set;
+      if (ok && nblk > 0) {
+        const float na = a.nrmA[(size_t)setA * a.rows_padded_A + row];
+        const float e = 1.05f * sqrtf(na * nbm) + 0.02f * (na + nbm + 1.0f);     // |t - 512 float(d)| <= e
+        margin = (2.0f * e + 1.0f) * (1.0f / 1024.0f);
+        cap = (a.init == 0x7fffffff) ? -CUDART_INF_F : -((float)a.init + e) * (1.0f / 1024.0f);   // t < init + e  <=>  u > cap
+        wild = wild || !(na < 1.0e5f);
+      }
+      const bool need2 = a.second_dist != nullptr;
+      float m1 = -CUDART_INF_F, m2 = -CUDART_INF_F;
+      auto bound = [&]() {
+        if (!ok) return CUDART_INF_F;
+        if (wild) return -CUDART_INF_F;
+        return fmaxf((need2 ? m2 : m1) - margin, cap);
+      };
+#pragma unroll 1
+      for (int k = group; k < nblk; k += 2) {
+        mbar_wait(&sh->bar_accf1[group], (uint32_t)(k >> 1) & 1u);
+        __syncwarp();
+        tc_fence_after();
+        float v[32];
+        if (k == group) {
+          // seed the running top-2 from this block before collecting candidates from it
+#pragma unroll 1
+          for (int part = 0; part < 4; ++part) {
+            mm_ld32(tq + (uint32_t)part * 32u, v);
+            const float m = mm_max32(v);
+            const float lo = fminf(m1, m);
+            m1 = fmaxf(m1, m);
+            m2 = fmaxf(m2, lo);
+          }
+        }
+#pragma unroll 1
+        for (int part = 0; part < 4; ++part) {
+          const float tau = bound();
+          mm_ld32(tq + (uint32_t)part * 32u, v);
+          const float m = mm_max32(v);
+          uint32_t mask = 0;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) mask |= (v[e] > tau) ? (1u << e) : 0u;
+          if (wild && ok) mask = 0xffffffffu;
+          const int j0 = k * MM_ROWS + part * 32;
+          if (j0 + 32 > nB) mask &= (nB > j0) ? (0xffffffffu >> (32 - (nB - j0))) : 0u;     // padded columns
+          if (k != group) {            // (the seeding block's maxima are already in)
+            const float lo = fminf(m1, m);
+            m1 = fmaxf(m1, m);
+            m2 = fmaxf(m2, lo);
+          }
+          append(mask, ln, 0, j0, 1, m);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh->bar_acce1[group]);
+        sTau[group * MM_ROWS + ln] = bound();          // what an overflow drain of this group filters with
+      }
+      // ---- the stream is over: merge the two groups' slice maxima into the final bound of every row ----
+      sM[group * MM_ROWS + ln] = make_float2(m1, m2);
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (group == 0) {
+        const float2 o = sM[MM_ROWS + ln];
+        const float M1 = fmaxf(m1, o.x), M2 = fmaxf(fminf(m1, o.x), fmaxf(m2, o.y));
+        m1 = M1; m2 = M2;
+        sTau[ln] = bound();
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      drain(true);
+    } else if (MUTUAL) {
+      // ===== column direction: lane = column of the block =====
+      const int rows_ok = min(MM_ROWS, nA - row0);
+#pragma unroll 1
+      for (int k = group; k < nblk; k += 2) {
+        const int j = k * MM_ROWS + ln;
+        const bool colok = j < nB;
+        mbar_wait(&sh->bar_accf2[group], (uint32_t)(k >> 1) & 1u);
+        __syncwarp();
+        tc_fence_after();
+        float v[32];
+        float cmax = -CUDART_INF_F;
+#pragma unroll 1
+        for (int part = 0; part < 4; ++part) {
+          mm_ld32(tq + (uint32_t)part * 32u, v);
+          cmax = fmaxf(cmax, mm_max32(v));
+        }
+        if (colok) atomicMax(colG + j, mm_ord(cmax));
+        const float thr = cmax - margin_col;
+#pragma unroll 1
+        for (int part = 0; part < 4; ++part) {
+          mm_ld32(tq + (uint32_t)part * 32u, v);
+          uint32_t mask = 0;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) mask |= (v[e] > thr) ? (1u << e) : 0u;
+          if (wild_set) mask = 0xffffffffu;
+          const int r0 = part * 32;
+          if (r0 + 32 > rows_ok) mask &= (rows_ok > r0) ? (0xffffffffu >> (32 - (rows_ok - r0))) : 0u;   // padded rows
+          if (!colok) mask = 0u;
+          append(mask, r0, 1, j, 0, cmax);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh->bar_acce2[group]);
+      }
+      drain(true);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < MM_ROWS) {
+    const int r = threadIdx.x, row = row0 + r;
+    if (row < a.out_stride) {
+      const bool row_ok = row < nA;
+      const unsigned long long k1 = sK1[r], k2 = sK2[r];
+      const size_t o = (size_t)pair * a.out_stride + row;
+      if (a.best_idx) a.best_idx[o] = row_ok ? (int)(unsigned int)(k1 & 0xffffffffull) : -1;   // 0xffffffff = -1: none
+      if (a.best_dist) a.best_dist[o] = row_ok ? (int)(k1 >> 32) : a.init;
+      if (a.second_dist) a.second_dist[o] = row_ok ? (int)(k2 >> 32) : a.init;
+    }
+  }
+  if (MUTUAL) {
+    // the last CTA of the pair turns the merged column keys into the outputs and resets the scratch for the next launch
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int prev = atomicAdd(a.pair_done + pair, 1u);
+      sh->flag = (prev == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (sh->flag) {
+      __threadfence();
+      for (int j = threadIdx.x; j < a.rows_padded_B; j += MM_THREADS) {
+        const unsigned long long key = __ldcg(colK + j);
+        if (j < a.out_stride_cols) {
+          const bool have = j < nB && key != ~0ull;
+          const size_t o = (size_t)pair * a.out_stride_cols + j;
+          if (a.rev_idx) a.rev_idx[o] = have ? (int)(unsigned int)(key & 0xffffffffull) : -1;
+          if (a.rev_dist) a.rev_dist[o] = have ? (int)(key >> 32) : a.init;
+        }
+        colK[j] = ~0ull;
+        colG[j] = 0u;
+      }
+      if (threadIdx.x == 0) a.pair_done[pair] = 0u;
+    }
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+constexpr size_t MM_SMEM = (size_t)(1 + MM_STAGES) * MM_BLK_BYTES + (size_t)8 * (MM_Q1 + MM_Q2) * 8 + (size_t)MM_ROWS * (8 + 8 + 2 * 8 + 2 * 4) +
+                           sizeof(MmShared) + 64;
+static_assert(MM_SMEM <= 227 * 1024, "shared memory budget");
+
+cudaError_t launch_mm_prep(Ctx* c, const float* desc, size_t set_stride, int n_sets, const int32_t* n_dev, int n_host, int rows_padded,
+                           void* img, size_t img_set_bytes, float* nrm, float* nrm_max) {
+  dim3 grid((rows_padded * 16 + 255) / 256, n_sets);
+  cudaError_t e0 = cudaMemsetAsync(nrm_max, 0, (size_t)n_sets * 4, c->stream);
+  if (e0 != cudaSuccess) return e0;
+  prof_begin(c, P_MATCH_PREP);
+  mm_prep_kernel<<<grid, 256, 0, c->stream>>>(desc, set_stride, n_dev, n_host, rows_padded, reinterpret_cast<unsigned char*>(img), img_set_bytes, nrm, nrm_max);
+  prof_end(c);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+// a.img_stride_* in BYTES; a.col_g / a.col_k / a.pair_done: per-pair column scratch (zero / all-ones / zero between launches)
+cudaError_t launch_match_mutual(Ctx* c, const MatchTcArgs& a, int n_pairs, bool mutual) {
+  static unsigned long long attr_mask = 0;
+  if (!((attr_mask >> c->device) & 1ull)) {
+    cudaError_t e = cudaFuncSetAttribute(mm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MM_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MM_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_mask |= 1ull << c->device;
+  }
+  prof_begin(c, P_MATCH_TILE);
+  if (mutual) mm_kernel<true><<<dim3(a.rows_padded_A / MM_ROWS, n_pairs), MM_THREADS, MM_SMEM, c->stream>>>(a);
+  else mm_kernel<false><<<dim3(a.rows_padded_A / MM_ROWS, n_pairs), MM_THREADS, MM_SMEM, c->stream>>>(a);
+  prof_end(c);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+}  // namespace xfb

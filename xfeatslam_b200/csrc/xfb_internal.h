@@ -81,6 +81,8 @@ struct Ctx {
   float wscale2[L_NUM] = {};      // its epilogue factor 1 / (activation scale * weight scale)
   int conv_tc_version = 2;        // 2 = conv_tc2.cu (default), 1 = conv_tc.cu (XFB_CONV_TC=1: A/B reference)
   int num_sms = 148;
+  struct TmapSlot { alignas(64) unsigned char blob[128]; const void* ptr; int B, H, W; };   // CUtensorMap of a layer's output + what it was encoded for
+  TmapSlot tmap[L_NUM] = {};
   unsigned long long* t2_counters = nullptr;   // XFB_T2_DEBUG: [L_NUM][32] cycle counters of CTA 0 (conv_tc2.cu), printed at xfb_destroy
   bool force_simt = false;        // debug: run every conv on the FP32 SIMT kernels (A/B parity tests)
 
@@ -157,8 +159,15 @@ struct Ctx {
   // streaming matcher (match_stream.cu): fp16 operand images, 20 KB per 128-row block
   void* ms_img[2] = {};           // generic A / B sets
   int ms_cap = 0;                 // rows (multiple of 256) the generic images hold
-  void* ms_fimg = nullptr;        // per-frame images of the last extract
+  void* ms_fimg = nullptr;        // (unused since the mutual matcher; kept for the grouped path's layout)
   int ms_frows = 0;
+  // mutual matcher (match_mutual.cu): fp16 operand images with both tails, 22 KB per 128-row block; per-pair column scratch
+  void* mm_img[2] = {};           // generic A / B sets
+  int mm_cap = 0;
+  void* mm_fimg = nullptr;        // per-frame images of the last extract
+  int mm_frows = 0;
+  unsigned int* mm_colg = nullptr; unsigned long long* mm_colk = nullptr; unsigned int* mm_done = nullptr;
+  int mm_col_rows = 0;            // columns per pair the scratch holds (64 pairs)
   // vocabulary tree (bow.cu): node descriptors [n][32 B], CSR children; scratch for the host-pointer entry point
   uint8_t* v_desc = nullptr; int32_t* v_start = nullptr; int32_t* v_child = nullptr; int v_nodes = 0, v_L = 0;
   int32_t* v_out = nullptr; int v_out_cap = 0;
@@ -201,6 +210,13 @@ struct MatchTcArgs {
   const float* nrm_max_B;                 // [set] largest |b|^2 of each B set (bf16 error scale)
   unsigned long long* ms_counters;        // debug: [0] queue pushes, [1] verified survivors, [2] queue overflows (or nullptr)
   int ms_mode;                            // debug timing experiments (bit flags): 1 no candidate path, 2 no epilogue arithmetic, 4 no MMAs, 8 no tcgen05.ld, 16 no bulk copies
+  // mutual matcher (match_mutual.cu)
+  const float* nrm_max_A;                 // [set] largest |a|^2 of each A set
+  int32_t* rev_idx; int32_t* rev_dist;    // column-wise best, [pair][out_stride_cols] (any may be null)
+  int out_stride_cols;
+  unsigned int* col_g;                    // [pair][rows_padded_B] running maximum of the column estimates (ordered uint; zero between launches)
+  unsigned long long* col_k;              // [pair][rows_padded_B] exact (distance << 32 | row) column keys (all-ones between launches)
+  unsigned int* pair_done;                // [pair] CTA tickets (zero between launches)
 };
 
 // profiling tags: 0..L_NUM-1 = layers, then the stages below
@@ -231,6 +247,10 @@ size_t ms_image_bytes(int rows_padded);
 cudaError_t launch_ms_prep(Ctx* c, const float* desc, size_t set_stride, int n_sets, const int32_t* n_dev, int n_host, int rows_padded,
                            void* img, size_t img_set_bytes, float* nrm, float* nrm_max);
 cudaError_t launch_match_stream(Ctx* c, const MatchTcArgs& a, int n_pairs, bool grouped);   // a.img_stride_* in BYTES
+size_t mm_image_bytes(int rows_padded);
+cudaError_t launch_mm_prep(Ctx* c, const float* desc, size_t set_stride, int n_sets, const int32_t* n_dev, int n_host, int rows_padded,
+                           void* img, size_t img_set_bytes, float* nrm, float* nrm_max);
+cudaError_t launch_match_mutual(Ctx* c, const MatchTcArgs& a, int n_pairs, bool mutual);     // a.img_stride_* in BYTES
 size_t conv_part_elems(int H, int W);
 size_t conv_tc_part_elems(int H, int W);
 size_t conv_small_part_elems(int H, int W);
