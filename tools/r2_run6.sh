@@ -1,0 +1,10 @@
+#!/bin/bash
+# round 2, GPU call 6: mutual matcher (match_mutual.cu) parity + vectorised statistics read-back in conv_tc2
+O=gpurun_out/r2f; mkdir -p $O
+timeout 300 python -m pytest tests/test_gpu_match.py -m gpu -q -x > $O/pytest_match.log 2>&1; echo "match rc=$?"; tail -12 $O/pytest_match.log | cut -c1-300
+timeout 300 python -m pytest tests/test_gpu_bench_path.py -m gpu -q -x > $O/pytest_path.log 2>&1; echo "bench-path rc=$?"; tail -12 $O/pytest_path.log | cut -c1-300
+timeout 300 python -m pytest tests/test_gpu_extract.py -m gpu -q -x -k "every_layer or dense_maps" > $O/pytest_layers.log 2>&1; echo "layers rc=$?"; tail -5 $O/pytest_layers.log | cut -c1-300
+timeout 900 python -m pytest tests -m gpu -q > $O/pytest.log 2>&1; echo "pytest rc=$?"; tail -8 $O/pytest.log | cut -c1-300
+XFB_T2_DEBUG=1 timeout 200 python bench.py --no-cpu-baseline --chunks 2 --steps 3 --contexts 1 > $O/bench_dbg.json 2> $O/bench_dbg.err; echo "bench dbg rc=$?"; grep "xfb t2" $O/bench_dbg.err | cut -c1-420 | head -12
+timeout 200 python bench.py --no-cpu-baseline --chunks 8 --steps 5 > $O/bench_v2.json 2> $O/bench_v2.err; echo "bench v2 rc=$?"; cut -c1-200 $O/bench_v2.json
+timeout 200 python bench.py --no-cpu-baseline --chunks 4 --steps 5 --height 720 --width 1280 > $O/bench_v2_hd.json 2> $O/bench_v2_hd.err; echo "bench v2 hd rc=$?"; cut -c1-200 $O/bench_v2_hd.json

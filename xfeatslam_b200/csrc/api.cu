@@ -249,6 +249,7 @@ static int tc_match_generic(Ctx* c, const float* dA, int n1, const float* dB, in
     m.best_idx = bi; m.best_dist = bd; m.second_dist = sd; m.rev_idx = ri; m.rev_dist = rd;
     m.nrm_max_A = c->tc_nmax[0]; m.nrm_max_B = c->tc_nmax[1];
     m.col_g = c->mm_colg; m.col_k = c->mm_colk; m.pair_done = c->mm_done;
+    m.ms_counters = c->ms_counters;
     XFB_CUDA_OK(c, launch_match_mutual(c, m, 1, ri || rd));
     return XFB_OK;
   }
@@ -320,6 +321,7 @@ static int tc_match_frames(Ctx* c, const int32_t* pairs, int n_pairs, int init, 
     a.init = init; a.out_stride = K; a.out_stride_cols = K;
     a.nrm_max_A = a.nrm_max_B = c->tc_fnmax;
     a.col_g = c->mm_colg; a.col_k = c->mm_colk; a.pair_done = c->mm_done;
+    a.ms_counters = c->ms_counters;
     for (int p = 0; p < np; ++p) { a.pairs[2 * p] = pairs[2 * (p0 + p)]; a.pairs[2 * p + 1] = pairs[2 * (p0 + p) + 1]; }
     auto at = [&](int i) { return o[i] ? o[i] + (size_t)p0 * K : nullptr; };
     a.best_idx = at(0); a.best_dist = at(1); a.second_dist = at(2); a.rev_idx = at(3); a.rev_dist = at(4);
@@ -471,6 +473,12 @@ void xfb_destroy(xfb_ctx* c) {
     fprintf(stderr, "[xfb] CTA(0,0) cycles per launch: total %.0f | mma thread: wait A %.0f, wait full %.0f, wait acc-empty %.0f, loop %.0f | loader wait empty %.0f | "
             "epilogue warp 2: wait acc-full (pass 1) %.0f, pass-1 end @%.0f, pass-2 end @%.0f, drain end @%.0f\n",
             h[12] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n, h[7] / n, h[8] / n, h[9] / n, h[10] / n, h[11] / n);
+    if (h[30]) {
+      const double m = (double)h[30];
+      fprintf(stderr, "[xfb] match_mutual CTA(0,0) cycles per launch: total %.0f | MMA lane loop end @%.0f | row warp: stream+bound end @%.0f, drain end @%.0f | "
+              "column warp: stream end @%.0f, drain end @%.0f || all CTAs per launch: row entries %.0f verified %.0f, column entries %.0f verified %.0f\n",
+              h[20] / m, h[25] / m, h[21] / m, h[22] / m, h[23] / m, h[24] / m, h[26] / m, h[27] / m, h[28] / m, h[29] / m);
+    }
     fprintf(stderr, "[xfb] CTA(0,0) mma thread: cycles in tcgen05.mma issue %.0f, in tcgen05.commit %.0f, in tcgen05.fence %.0f, loop tail %.0f\n", h[14] / n, h[15] / n, h[16] / n, h[17] / n);
   }
   fr(c->ms_img[0]); fr(c->ms_img[1]); fr(c->ms_fimg); fr(c->mm_img[0]); fr(c->mm_img[1]); fr(c->mm_fimg); fr(c->mm_colg); fr(c->mm_colk); fr(c->mm_done); fr(c->ms_counters); fr(c->p_idx); fr(c->p_out); fr(c->g_buf); fr(c->v_desc); fr(c->v_start); fr(c->v_child); fr(c->v_out);

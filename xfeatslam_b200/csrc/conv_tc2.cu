@@ -104,7 +104,7 @@ struct ConvTc2Args {
   float* out;               // keypoint_head.3 only (every other layer stores through the tensor map)
   const float* in_mean; const float* in_rstd;
   const float* skip_avg; const float* skip_w; const float* skip_b;
-  float* part;              // per-tile channel sums [B][tiles][2 pixel halves][COUT][2] (float)
+  float* part;              // per-tile channel sums [B][tiles][COUT][2] (float)
   unsigned int* ticket; float* out_mean; float* out_rstd;
   int B, Hin, Win, Hout, Wout;
   int full_w;               // T2IN_UNFOLD / KPSOFTMAX: width of xn / K1h
@@ -464,8 +464,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
     // the frame's last work item: fixed-order fold of all tile partials (slice-strided, then slice order), in double
     auto fold = [&](int b) {
       constexpr int NSL = C::COUT >= 128 ? 1 : (C::COUT >= 64 ? 2 : 4);
-      const float* part_b = a.part + (size_t)b * a.tiles * 2 * C::COUT * 2;
-      const int entries = a.tiles * 2;
+      const float* part_b = a.part + (size_t)b * a.tiles * C::COUT * 2;
+      const int entries = a.tiles;
       if (t < NSL * C::COUT) {
         const int c = t % C::COUT, sl = t / C::COUT;
         double d1 = 0.0, d2 = 0.0;
@@ -607,24 +607,45 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
         }
         T2_TICK(12);
         if constexpr (OUTMODE == T2OUT_STATS) {
-          // per-channel sum / sum of squares over the valid pixels: thread = (channel, pixel half), columns of the staging tile
-          const int c = t % C::NOUT, half = t / C::NOUT;
-          if (half < 2) {
-            int rows_ok, cols_ok;
-            if (C::KS == 1) { rows_ok = 16; cols_ok = 8; }
+          // per-channel sum / sum of squares over the valid pixels, read back from the staging tile with 16-byte loads: lane =
+          // (channel chunk of 4, pixel octet o: the pixels o, o + 8, ...), a warp owns 4 chunks; octets are paired (o, o + 4) inside a
+          // quarter warp so that the swizzled chunk positions never collide; 3 shuffle steps merge the 8 octets
+          {
+            constexpr int NCHUNK = C::NOUT / 4;                         // 16-byte chunks of real channels (6, 8 or 16)
+            const int o = ((lane >> 2) & 1) * 4 + (lane >> 3);          // pixel octet of this lane
+            int rows_ok = 16, cols_ok = 8, lin_ok = 128;
+            if (C::KS == 1) lin_ok = min(128, a.Hout * a.Wout - tf * 128);
             else { rows_ok = min(16, a.Hout - oy0); cols_ok = min(8, a.Wout - ox0); }
-            const int lin_ok = (C::KS == 1) ? min(128, a.Hout * a.Wout - tf * 128) : 128;
-            const unsigned char* colp = sStg + (size_t)(c >> 5) * 16384 + (size_t)(c & 3) * 4;
-            const int cc = (c & 31) >> 2;
-            float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-            for (int pp = half * 64; pp < half * 64 + 64; ++pp) {
-              const bool ok = (C::KS == 1) ? (pp < lin_ok) : ((pp >> 3) < rows_ok && (pp & 7) < cols_ok);
-              const float x = *reinterpret_cast<const float*>(colp + (size_t)pp * 128 + ((cc ^ (pp & 7)) << 4));
-              if (ok) { s1 += x; s2 = fmaf(x, x, s2); }
+            float* part_b = a.part + (size_t)b * a.tiles * C::COUT * 2;
+#pragma unroll
+            for (int rep = 0; rep < (NCHUNK + 15) / 16; ++rep) {
+              const int cc = rep * 16 + quad * 4 + (lane & 3);          // chunk of 4 channels
+              float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+              if (cc < NCHUNK) {
+                const unsigned char* base = sStg + (size_t)(cc >> 3) * 16384 + (size_t)o * 128 + (((cc & 7) ^ o) << 4);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {                          // pixel o + 8 i = tile row i, tile column o
+                  const bool ok = (C::KS == 1) ? (o + 8 * i < lin_ok) : (i < rows_ok && o < cols_ok);
+                  const float4 x = *reinterpret_cast<const float4*>(base + (size_t)i * 1024);
+                  if (ok) {
+                    s1.x += x.x; s1.y += x.y; s1.z += x.z; s1.w += x.w;
+                    s2.x = fmaf(x.x, x.x, s2.x); s2.y = fmaf(x.y, x.y, s2.y); s2.z = fmaf(x.z, x.z, s2.z); s2.w = fmaf(x.w, x.w, s2.w);
+                  }
+                }
+              }
+#pragma unroll
+              for (int off = 4; off < 32; off <<= 1) {                  // lanes differing in bits 2..4 hold the other octets of the same chunk
+                s1.x += __shfl_xor_sync(0xffffffffu, s1.x, off); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, off);
+                s1.z += __shfl_xor_sync(0xffffffffu, s1.z, off); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, off);
+                s2.x += __shfl_xor_sync(0xffffffffu, s2.x, off); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, off);
+                s2.z += __shfl_xor_sync(0xffffffffu, s2.z, off); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, off);
+              }
+              if (lane < 4 && cc < NCHUNK) {
+                float* dst = part_b + ((size_t)tf * C::COUT + cbase + cc * 4) * 2;
+                *reinterpret_cast<float4*>(dst) = make_float4(s1.x, s2.x, s1.y, s2.y);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(s1.z, s2.z, s1.w, s2.w);
+              }
             }
-            float* part_b = a.part + (size_t)b * a.tiles * 2 * C::COUT * 2;
-            *reinterpret_cast<float2*>(part_b + ((size_t)(tf * 2 + half) * C::COUT + cbase + c) * 2) = make_float2(s1, s2);
           }
           ++run_cnt;
           T2_TICK(13);
@@ -746,13 +767,13 @@ static cudaError_t run_tc2(Ctx* c, ConvTc2Args& a, int tag) {
   return cudaGetLastError();
 }
 
-// floats of partial-sum scratch per frame: [tiles][2 pixel halves][COUT][2]
+// floats of partial-sum scratch per frame: [tiles][COUT][2]
 size_t conv_tc2_part_floats(int H, int W) {
   size_t m = 0;
   auto upd = [&](int lvl, int cout, bool linear) {
     const int h = H >> lvl, w = W >> lvl;
     const size_t tiles = linear ? (size_t)(h * w + 127) / 128 : (size_t)((w + 7) / 8) * ((h + 15) / 16);
-    const size_t v = tiles * 2 * cout * 2;
+    const size_t v = tiles * cout * 2;
     if (v > m) m = v;
   };
   upd(2, 24, false); upd(3, 64, false); upd(3, 64, true); upd(4, 64, false); upd(5, 128, false); upd(5, 64, true);

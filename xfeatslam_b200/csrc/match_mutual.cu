@@ -171,6 +171,11 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = blockIdx.y;
+  // XFB_MS_DEBUG: counters [20..31] = per-launch sums over CTA (0,0): cycles (total, row warp stream end / drain end, column warp stream end /
+  // drain end, MMA lane loop) and, over ALL CTAs, queue entries / exact verifications per direction
+  unsigned long long* dbgc = a.ms_counters;
+  const bool dbg0 = dbgc != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  const long long t_start = clock64();
   const int setA = a.pairs[2 * pair], setB = a.pairs[2 * pair + 1];
   const int nA = a.nA_dev ? min(a.nA_host, a.nA_dev[setA]) : a.nA_host;
   const int nB = a.nB_dev ? min(a.nB_host, a.nB_dev[setB]) : a.nB_host;
@@ -261,6 +266,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
         }
         umma_commit(&sh->bar_empty[s]);     // the column block may be overwritten once these MMAs have read it
       }
+      if (dbg0) atomicAdd(dbgc + 25, (unsigned long long)(clock64() - t_start));
     }
     __syncwarp();
   } else {
@@ -283,9 +289,11 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
         const unsigned long long ent = q[i];
         const int r = (int)((ent >> 24) & 0x7full), j = (int)(ent & 0xffffffull);
         const float ub = __uint_as_float((unsigned int)(ent >> 32));        // upper bound of the pair's u
+        if (dbgc) atomicAdd(dbgc + (dir2 ? 28 : 26), 1ull);
         if (!dir2) {
           const float tau = final ? sTau[r] : sTau[group * MM_ROWS + r];
           if (!(ub > tau) && !wild_set) continue;
+          if (dbgc) atomicAdd(dbgc + 27, 1ull);
           const int D = mm_exact_distance(rawA + (size_t)(row0 + r) * 64, rawB + (size_t)j * 64);
           if ((unsigned int)D < init_u) {
             const unsigned long long key = ((unsigned long long)(unsigned int)D << 32) | (unsigned int)j;
@@ -295,6 +303,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
         } else {
           const float gmax = mm_unord(__ldcg(colG + j));                    // largest estimate any CTA has seen for this column
           if (!(ub >= gmax - margin_col) && !wild_set) continue;
+          if (dbgc) atomicAdd(dbgc + 29, 1ull);
           const int D = mm_exact_distance(rawA + (size_t)(row0 + r) * 64, rawB + (size_t)j * 64);
           if ((unsigned int)D < init_u) atomicMin(colK + j, ((unsigned long long)(unsigned int)D << 32) | (unsigned int)(row0 + r));
         }
@@ -390,7 +399,9 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
         sTau[ln] = bound();
       }
       asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (dbg0 && ew == 0 && lane == 0) atomicAdd(dbgc + 21, (unsigned long long)(clock64() - t_start));
       drain(true);
+      if (dbg0 && ew == 0 && lane == 0) atomicAdd(dbgc + 22, (unsigned long long)(clock64() - t_start));
     } else if (MUTUAL) {
       // ===== column direction: lane = column of the block =====
       const int rows_ok = min(MM_ROWS, nA - row0);
@@ -426,11 +437,14 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
         __syncwarp();
         if (lane == 0) mbar_arrive(&sh->bar_acce2[group]);
       }
+      if (dbg0 && ew == 8 && lane == 0) atomicAdd(dbgc + 23, (unsigned long long)(clock64() - t_start));
       drain(true);
+      if (dbg0 && ew == 8 && lane == 0) atomicAdd(dbgc + 24, (unsigned long long)(clock64() - t_start));
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (dbg0 && threadIdx.x == 0) { atomicAdd(dbgc + 20, (unsigned long long)(clock64() - t_start)); atomicAdd(dbgc + 30, 1ull); }
   if (threadIdx.x < MM_ROWS) {
     const int r = threadIdx.x, row = row0 + r;
     if (row < a.out_stride) {
