@@ -426,6 +426,9 @@ def run_b200(args):
         barrier()
         return ms
 
+    if args.diagnose_e2e:
+        return diagnose_e2e(args, dev, world, rank, Bsz, K, CH, Wm, Hf, Wf, host_pool, h_out, timed, batch_device, timed_e2e, batch_host, wait_all, barrier, ctxs)
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -501,6 +504,77 @@ def run_b200(args):
     return 0
 
 
+def diagnose_e2e(args, dev, world, rank, Bsz, K, CH, Wm, Hf, Wf, host_pool, h_out, timed, batch_device, timed_e2e, batch_host, wait_all, barrier, ctxs):
+    """Where does the end-to-end time go when N ranks share one host?  Per rank: (a) the copies alone (the H2D / D2H traffic of
+    xfb_submit replayed with torch on two streams, no kernels), (b) the kernels alone (device-resident), (c) the real xfb_submit
+    path, (d) host time spent inside the xfb_submit calls.  Rank 0 prints every rank's numbers (one JSON line)."""
+    import torch
+    import torch.distributed as dist
+    n_groups = K * CH
+    # (a) copies only
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    d_in = torch.empty_like(host_pool[0], device=dev)
+    o0 = h_out[0]
+    d_o = {k: (torch.empty_like(v, device=dev) if not isinstance(v, list) else [torch.empty_like(x, device=dev) for x in v]) for k, v in o0.items()}
+    def copies(i):
+        o = h_out[i % len(h_out)]
+        with torch.cuda.stream(s_in):
+            d_in.copy_(host_pool[i % len(host_pool)], non_blocking=True)
+        with torch.cuda.stream(s_out):
+            for k in ("nv", "xy", "sc", "ds"):
+                o[k].copy_(d_o[k], non_blocking=True)
+            for a_, b_ in zip(o["m"], d_o["m"]):
+                a_.copy_(b_, non_blocking=True)
+    for i in range(8):
+        copies(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(n_groups):
+        copies(i)
+    torch.cuda.synchronize(dev)
+    ms_copy = (time.perf_counter() - t0) * 1e3
+    barrier()
+    # (b) kernels only, (c) the real path, (d) host time inside xfb_submit
+    ms_dev, _ = timed(batch_device)
+    ms_e2e = timed_e2e()
+    for i in range(4):
+        batch_host(i)
+    wait_all()
+    barrier()
+    cpu = 0.0
+    t_all = time.perf_counter()
+    for i in range(n_groups):
+        t1 = time.perf_counter()
+        batch_host(Wm * CH + i)
+        cpu += time.perf_counter() - t1
+    wait_all()
+    torch.cuda.synchronize(dev)
+    ms_e2e2 = (time.perf_counter() - t_all) * 1e3
+    barrier()
+    frame_bytes = Hf * Wf
+    out_bytes = TOPK * (8 + 4 + 256) + 4 + 5 * TOPK * 4
+    mine = torch.tensor([ms_copy / n_groups, ms_dev / n_groups, ms_e2e / n_groups, ms_e2e2 / n_groups, cpu * 1e3 / n_groups], dtype=torch.float64, device=dev)
+    if world > 1:
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+    else:
+        allv = [mine]
+    if rank == 0:
+        rows = [[round(float(x), 4) for x in v.cpu()] for v in allv]
+        gb = Bsz * (frame_bytes + out_bytes) / 1e9
+        print(json.dumps({"diagnose_e2e": True, "n_gpus": world, "workload": workload_name(Hf, Wf), "frames_per_launch_group": Bsz,
+                          "bytes_per_group": {"h2d": Bsz * frame_bytes, "d2h": Bsz * out_bytes},
+                          "per_rank_ms_per_group": {"columns": ["copies_only", "kernels_only", "e2e_submit", "e2e_submit_again", "host_time_in_submit"], "rows": rows},
+                          "copy_GBps_per_rank": [round(gb / (r[0] * 1e-3), 2) for r in rows],
+                          "copy_GBps_aggregate": round(sum(gb / (r[0] * 1e-3) for r in rows), 2), "host_cpus": os.cpu_count()}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    for c_ in ctxs:
+        c_.close()
+    return 0
+
+
 def PAIRS_FN(bsz):
     """Frame i of a launch group is matched against frame i - 1 of the group; frame 0 against the group's LAST frame (the
     groups of the synthetic stream are independent draws, so 'the previous frame' of frame 0 is simply another frame:
@@ -521,6 +595,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="frames per launch group (one xfb_extract_batch + one xfb_match_frame_pairs call)")
     ap.add_argument("--chunks", type=int, default=64, help="launch groups per step: a step processes chunks x batch frames per GPU")
+    ap.add_argument("--diagnose-e2e", action="store_true", help="per-rank split of the end-to-end time: copies only / kernels only / xfb_submit / host time")
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--no-cpu-baseline", action="store_true")

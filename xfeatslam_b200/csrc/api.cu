@@ -156,9 +156,9 @@ static int alloc_buffers(Ctx* c) {
   XFB_ALLOC(c, c->ticket, B * XFB_TICKET_STRIDE * 4);
   XFB_CUDA_OK(c, cudaMemset(c->ticket, 0, B * XFB_TICKET_STRIDE * 4));
   XFB_ALLOC(c, c->cand, B * HW * 8);
-  XFB_ALLOC(c, c->cand_count, B * 4);
+  XFB_ALLOC(c, c->cand_count, B * XFB_TICKET_STRIDE * 4);   // one 128-byte line per frame: the CTAs of a batch would otherwise serialise their atomics on ONE L2 line
   XFB_ALLOC(c, c->cand_count_last, B * 4);
-  XFB_CUDA_OK(c, cudaMemset(c->cand_count, 0, B * 4));
+  XFB_CUDA_OK(c, cudaMemset(c->cand_count, 0, B * XFB_TICKET_STRIDE * 4));
   XFB_CUDA_OK(c, cudaMemset(c->cand_count_last, 0, B * 4));
   const size_t K = c->max_topk;
   XFB_ALLOC(c, c->o_nvalid, B * 4);
@@ -414,6 +414,7 @@ int xfb_create(xfb_ctx** out, const void* weights_blob, size_t n, int device, in
       break;
     }
     c->num_sms = prop.multiProcessorCount;
+    if (const char* bf = getenv("XFB_B1_FUSE")) c->b1_fuse = atoi(bf) != 0;
     if (const char* cv = getenv("XFB_CONV_TC")) c->conv_tc_version = (atoi(cv) == 1) ? 1 : 2;   // A/B: 1 = the round-1 one-tile-per-CTA 3xTF32 kernels
     if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { c->err = cudaGetErrorString(e); r = XFB_ERR_CUDA; break; }
     c->stream = c->own_stream;

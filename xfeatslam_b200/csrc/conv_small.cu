@@ -34,7 +34,10 @@ struct SCfg {
   static_assert(COUT % 4 == 0 && (CIN == 1 || CIN % 4 == 0), "channel vectors");
 };
 
-template <class C, bool IN_BN, bool DIRECT>
+// STORE = false: statistics only (block1.0 when its output is never materialised).  FUSE0 = true (block1.1): the input tile is
+// block1.0's output RECOMPUTED from the normalised image xn (1 -> 4 channels, 3x3; a.w0 = its weights, a.in = xn), with
+// block1.0's BatchNorm + ReLU applied in flight -- the 4.9 MB / frame intermediate is neither written nor read.
+template <class C, bool IN_BN, bool DIRECT, bool STORE = true, bool FUSE0 = false>
 __global__ void __launch_bounds__(C::NT) conv_small_kernel(const ConvArgs a) {
   constexpr int CIN = C::CIN, COUT = C::COUT, S = C::S, PY = C::PY, NT = C::NT, TIW = C::TIW, TIH = C::TIH, NYIN = C::NYIN, Q = C::Q;
   extern __shared__ __align__(16) float smem[];
@@ -44,11 +47,43 @@ __global__ void __launch_bounds__(C::NT) conv_small_kernel(const ConvArgs a) {
   const int b = blockIdx.z;
   const int oy0 = blockIdx.y * C::TH, ox0 = blockIdx.x * C::TW;
   const int iy_org = oy0 * S - 1, ix_org = ox0 * S - 1;
-  const float* in_b = a.in + (size_t)b * a.Hin * a.Win * CIN;
+  const float* in_b = a.in + (size_t)b * a.Hin * a.Win * (FUSE0 ? 1 : CIN);
 
   // ---- stage weights and the input tile -----------------------------------------------------------------
   for (int i = t; i < C::W_FLOATS / 4; i += NT) reinterpret_cast<float4*>(sW)[i] = reinterpret_cast<const float4*>(a.w)[i];
-  if (DIRECT) {
+  if (FUSE0) {
+    // xn tile with one more ring of halo, then block1.0 on the fly: y0 = conv3x3(xn) (zero padding), relu(bn(y0)) -> sIn[ty][tx][0..3];
+    // positions outside block1.0's output map are block1.1's zero padding
+    float* sX = sW + C::W_FLOATS;                                   // [TIH + 2][TIW + 2]
+    float* sW0 = sX + ((TIH + 2) * (TIW + 2) + 3) / 4 * 4;          // [9][4] (16-byte aligned)
+    if (t < 36) sW0[t] = a.w0[t];
+    for (int i = t; i < (TIH + 2) * (TIW + 2); i += NT) {
+      const int ty = i / (TIW + 2), tx = i - ty * (TIW + 2);
+      const int iy = iy_org - 1 + ty, ix = ix_org - 1 + tx;
+      sX[i] = (iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win) ? in_b[(size_t)iy * a.Win + ix] : 0.f;
+    }
+    __syncthreads();
+    const float4 m = *reinterpret_cast<const float4*>(a.in_mean + b * 4), r = *reinterpret_cast<const float4*>(a.in_rstd + b * 4);
+    for (int i = t; i < TIH * TIW; i += NT) {
+      const int ty = i / TIW, tx = i - ty * TIW;
+      const int iy = iy_org + ty, ix = ix_org + tx;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win) {
+        // same accumulation order as the statistics pass (kx outer, ky inner; fmaf chain from 0)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const float x = sX[(ty + ky) * (TIW + 2) + tx + kx];
+            const float4 w4 = *reinterpret_cast<const float4*>(sW0 + (ky * 3 + kx) * 4);
+            v.x = fmaf(x, w4.x, v.x); v.y = fmaf(x, w4.y, v.y); v.z = fmaf(x, w4.z, v.z); v.w = fmaf(x, w4.w, v.w);
+          }
+        v.x = fmaxf((v.x - m.x) * r.x, 0.f); v.y = fmaxf((v.y - m.y) * r.y, 0.f);
+        v.z = fmaxf((v.z - m.z) * r.z, 0.f); v.w = fmaxf((v.w - m.w) * r.w, 0.f);
+      }
+      reinterpret_cast<float4*>(sIn)[i] = v;
+    }
+  } else if (DIRECT) {
     // no tile: every thread pulls its input pixels through L1 (neighbouring lanes / rows share the lines)
   } else if (CIN == 1) {
     for (int i = t; i < TIH * TIW; i += NT) {
@@ -170,9 +205,11 @@ __global__ void __launch_bounds__(C::NT) conv_small_kernel(const ConvArgs a) {
   for (int p = 0; p < PY; ++p) {
     const int oy = oy0 + warp * PY + p;
     if (oy < a.Hout && ox < a.Wout) {
-      float4* dst = reinterpret_cast<float4*>(out_b + ((size_t)oy * a.Wout + ox) * COUT);
+      if (STORE) {
+        float4* dst = reinterpret_cast<float4*>(out_b + ((size_t)oy * a.Wout + ox) * COUT);
 #pragma unroll
-      for (int c4 = 0; c4 < COUT / 4; ++c4) dst[c4] = make_float4(acc[p][4 * c4], acc[p][4 * c4 + 1], acc[p][4 * c4 + 2], acc[p][4 * c4 + 3]);
+        for (int c4 = 0; c4 < COUT / 4; ++c4) dst[c4] = make_float4(acc[p][4 * c4], acc[p][4 * c4 + 1], acc[p][4 * c4 + 2], acc[p][4 * c4 + 3]);
+      }
 #pragma unroll
       for (int c = 0; c < COUT; ++c) { s1[c] += acc[p][c]; s2[c] = fmaf(acc[p][c], acc[p][c], s2[c]); }
     }
@@ -247,11 +284,12 @@ using SB11 = SCfg<4, 8, 2, 4, 8>;     // block1.1  -> 240x320         tile 32 x 
 using SB12 = SCfg<8, 8, 1, 4, 8>;     // block1.2  240x320            tile 32 x 32
 using SB13 = SCfg<8, 24, 2, 2, 8>;    // block1.3  -> 120x160         tile 32 x 16 (input 33 x 65 x 8)
 
-template <class C, bool IN_BN, bool DIRECT>
+template <class C, bool IN_BN, bool DIRECT, bool STORE = true, bool FUSE0 = false>
 static cudaError_t run_small(Ctx* c, const ConvArgs& a, int tag) {
-  auto kern = conv_small_kernel<C, IN_BN, DIRECT>;
-  // DIRECT needs no input tile: reduction scratch + weights only (more CTAs per SM)
-  const size_t smem = DIRECT ? sizeof(float) * (C::RED_FLOATS + C::W_FLOATS) : C::SMEM_BYTES;
+  auto kern = conv_small_kernel<C, IN_BN, DIRECT, STORE, FUSE0>;
+  // DIRECT needs no input tile: reduction scratch + weights only (more CTAs per SM); FUSE0 adds the xn tile and block1.0's weights
+  const size_t smem = DIRECT ? sizeof(float) * (C::RED_FLOATS + C::W_FLOATS)
+                             : (FUSE0 ? C::SMEM_BYTES + sizeof(float) * ((C::TIH + 2) * (C::TIW + 2) + 36 + 8) : C::SMEM_BYTES);
   static unsigned long long attr_mask = 0;
   if (!((attr_mask >> c->device) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 49152 ? smem : 49152));
@@ -291,8 +329,17 @@ cudaError_t launch_conv_small_layer(Ctx* c, int L) {
   switch (L) {
     // DIRECT (inputs through L1, no staged tile) measured faster except for the 8->8 stride-1 layer
     // (18 two-vector pixel loads per thread): 0.070 / 0.133 / 0.128 / 0.110 ms per 32-frame batch
-    case L_B1_0: a.in = c->xn; return run_small<SB10, false, true>(c, a, L);
-    case L_B1_1: from(L_B1_0); return run_small<SB11, true, true>(c, a, L);
+    // block1.0 -> block1.1 fused by recomputation (default): block1.0 only produces its BatchNorm statistics, block1.1 rebuilds
+    // block1.0's output tile from xn in shared memory.  XFB_B1_FUSE=0 (or the layer-parity debug reads) keeps the two-kernel form.
+    case L_B1_0: a.in = c->xn; return c->b1_fuse ? run_small<SB10, false, true, false>(c, a, L) : run_small<SB10, false, true>(c, a, L);
+    case L_B1_1:
+      if (c->b1_fuse) {
+        a.in = c->xn; a.in_mean = c->bn[L_B1_0].mean; a.in_rstd = c->bn[L_B1_0].rstd; a.w0 = c->w[L_B1_0];
+        a.Hin = c->H; a.Win = c->W;
+        return run_small<SB11, true, false, true, true>(c, a, L);
+      }
+      from(L_B1_0);
+      return run_small<SB11, true, true>(c, a, L);
     case L_B1_2: from(L_B1_1); return run_small<SB12, true, false>(c, a, L);
     case L_B1_3: from(L_B1_2); return run_small<SB13, true, true>(c, a, L);
     default: return cudaErrorInvalidValue;

@@ -623,14 +623,15 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
               float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
               if (cc < NCHUNK) {
                 const unsigned char* base = sStg + (size_t)(cc >> 3) * 16384 + (size_t)o * 128 + (((cc & 7) ^ o) << 4);
+                float4 x[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {                          // pixel o + 8 i = tile row i, tile column o
+                for (int i = 0; i < 16; ++i) x[i] = *reinterpret_cast<const float4*>(base + (size_t)i * 1024);   // pixel o + 8 i = tile row i, column o
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
                   const bool ok = (C::KS == 1) ? (o + 8 * i < lin_ok) : (i < rows_ok && o < cols_ok);
-                  const float4 x = *reinterpret_cast<const float4*>(base + (size_t)i * 1024);
-                  if (ok) {
-                    s1.x += x.x; s1.y += x.y; s1.z += x.z; s1.w += x.w;
-                    s2.x = fmaf(x.x, x.x, s2.x); s2.y = fmaf(x.y, x.y, s2.y); s2.z = fmaf(x.z, x.z, s2.z); s2.w = fmaf(x.w, x.w, s2.w);
-                  }
+                  const float4 y = ok ? x[i] : make_float4(0.f, 0.f, 0.f, 0.f);                                  // (a zero adds nothing to either sum)
+                  s1.x += y.x; s1.y += y.y; s1.z += y.z; s1.w += y.w;
+                  s2.x = fmaf(y.x, y.x, s2.x); s2.y = fmaf(y.y, y.y, s2.y); s2.z = fmaf(y.z, y.z, s2.z); s2.w = fmaf(y.w, y.w, s2.w);
                 }
               }
 #pragma unroll

@@ -282,30 +282,43 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
     const float e_col = 1.05f * sqrtf(nam * nbm) + 0.02f * (nam + nbm + 1.0f);
     const float margin_col = wild_set ? CUDART_INF_F : (2.0f * e_col + 1.0f) * (1.0f / 1024.0f);
 
-    // exact verification of queued (row, column) pairs, 32 at a time; `final` = the stream is over (tight filters)
+    // Exact verification of the queued (row, column) pairs; `final` = the stream is over (tight filters).  Two phases: (1) filter
+    // every entry against the current bound (rows: the row's candidate bound; columns: the largest estimate ANY CTA has seen for
+    // the column) and compact the survivors in place (ballot-based, warp-uniform), (2) verify the survivors 32 at a time, one per
+    // lane -- dense batches: the 64-step fp64 chain costs the same whether 3 or 32 lanes run it.
     auto drain = [&](bool final) {
       __syncwarp();
-      for (int i = lane; i < qn; i += 32) {
+      int nw = 0;
+      for (int base = 0; base < qn; base += 32) {
+        const int i = base + lane;
+        unsigned long long ent = 0;
+        bool keep = false;
+        if (i < qn) {
+          ent = q[i];
+          const int r = (int)((ent >> 24) & 0x7full), j = (int)(ent & 0xffffffull);
+          const float ub = __uint_as_float((unsigned int)(ent >> 32));        // upper bound of the pair's u
+          if (dbgc) atomicAdd(dbgc + (dir2 ? 28 : 26), 1ull);
+          if (!dir2) keep = wild_set || ub > (final ? sTau[r] : sTau[group * MM_ROWS + r]);
+          else keep = wild_set || ub >= mm_unord(__ldcg(colG + j)) - margin_col;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) q[nw + __popc(bal & ((1u << lane) - 1u))] = ent;            // nw <= base: never ahead of the entries still to be read
+        nw += __popc(bal);
+        __syncwarp();
+      }
+      for (int i = lane; i < nw; i += 32) {
         const unsigned long long ent = q[i];
         const int r = (int)((ent >> 24) & 0x7full), j = (int)(ent & 0xffffffull);
-        const float ub = __uint_as_float((unsigned int)(ent >> 32));        // upper bound of the pair's u
-        if (dbgc) atomicAdd(dbgc + (dir2 ? 28 : 26), 1ull);
-        if (!dir2) {
-          const float tau = final ? sTau[r] : sTau[group * MM_ROWS + r];
-          if (!(ub > tau) && !wild_set) continue;
-          if (dbgc) atomicAdd(dbgc + 27, 1ull);
-          const int D = mm_exact_distance(rawA + (size_t)(row0 + r) * 64, rawB + (size_t)j * 64);
-          if ((unsigned int)D < init_u) {
+        if (dbgc) atomicAdd(dbgc + (dir2 ? 29 : 27), 1ull);
+        const int D = mm_exact_distance(rawA + (size_t)(row0 + r) * 64, rawB + (size_t)j * 64);
+        if ((unsigned int)D < init_u) {
+          if (!dir2) {
             const unsigned long long key = ((unsigned long long)(unsigned int)D << 32) | (unsigned int)j;
             const unsigned long long old = atomicMin(&sK1[r], key);
             atomicMin(&sK2[r], max(old, key));
+          } else {
+            atomicMin(colK + j, ((unsigned long long)(unsigned int)D << 32) | (unsigned int)(row0 + r));
           }
-        } else {
-          const float gmax = mm_unord(__ldcg(colG + j));                    // largest estimate any CTA has seen for this column
-          if (!(ub >= gmax - margin_col) && !wild_set) continue;
-          if (dbgc) atomicAdd(dbgc + 29, 1ull);
-          const int D = mm_exact_distance(rawA + (size_t)(row0 + r) * 64, rawB + (size_t)j * 64);
-          if ((unsigned int)D < init_u) atomicMin(colK + j, ((unsigned long long)(unsigned int)D << 32) | (unsigned int)(row0 + r));
         }
       }
       qn = 0;

@@ -2,7 +2,7 @@
 //   nms_score : 5x5 max-pool NMS (XFextractor::NMS, :219-248: x == local_max && x > thr) fused with the
 //               reliability score nearest(K1h)(kp) * bilinear(H1)(kp) (:280) and the (0,0) mask (:281-282);
 //               every surviving candidate is appended as one sortable 64-bit key
-//   topk      : per-frame exact top-k by an 8-pass MSB radix select + bitonic sort (:285-295).  The
+//   topk      : per-frame exact top-k: bitonic sort of all candidates when they fit shared memory, else MSB radix passes first (:285-295).  The
 //               reference's argsort is unstable; this build's order is score descending, then row-major
 //               pixel index ascending (SURVEY.md hard part (c)) -- the key encodes exactly that.
 //   describe  : InterpolateSparse2d bilinear on the channel-normalised feature map, then L2-normalise
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(NMS_T * NMS_T) nms_score_kernel(const float* k
   if (tid == 0) {
     int total = 0;
     for (int i = 0; i < NMS_NX * 8; ++i) { const int n = s_cnt[i]; s_cnt[i] = total; total += n; }
-    s_base = total ? atomicAdd(cand_count + b, total) : 0;
+    s_base = total ? atomicAdd(cand_count + b * XFB_TICKET_STRIDE, total) : 0;
   }
   __syncthreads();
 #pragma unroll
@@ -116,31 +116,43 @@ __global__ void __launch_bounds__(NMS_T * NMS_T) nms_score_kernel(const float* k
 
 // ------------------------------------------------------------------------------------------------
 constexpr int TOPK_NT = 1024;
+constexpr int TOPK_CAP = 8192;     // keys the shared-memory sorter holds
+// Exact per-frame top-k of the candidate keys (score bits << 32 | ~pixel index: unique, so "the k largest keys" is the reference's
+// order with this build's tie-break).  If the frame has at most TOPK_CAP candidates they are all sorted (bitonic, shared memory)
+// and the first k taken.  Otherwise MSB-first radix passes (one private 256-bin histogram per warp: no inter-warp contention on
+// the few hot exponent bins) narrow the selection until the keys >= the running prefix fit the sorter -- usually two passes.
 __global__ void __launch_bounds__(TOPK_NT) topk_kernel(const u64* cand, int* cand_count, int* cand_count_last, int HW, int W,
-                                                       int topk, int sort_n /*pow2 >= topk*/, int32_t* n_valid, float* kpt_xy,
-                                                       float* score) {
+                                                       int topk, int32_t* n_valid, float* kpt_xy, float* score) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  u64* skeys = reinterpret_cast<u64*>(smem_raw);  // [sort_n]
+  u64* skeys = reinterpret_cast<u64*>(smem_raw);                                  // [TOPK_CAP]
+  unsigned int* whist = reinterpret_cast<unsigned int*>(skeys + TOPK_CAP);        // [32 warps][256]
   __shared__ unsigned int hist[256];
   __shared__ u64 s_prefix;
-  __shared__ int s_remaining;
-  __shared__ int s_fill;
-  const int b = blockIdx.x, t = threadIdx.x;
+  __shared__ int s_remaining, s_take, s_done, s_fill;
+  const int b = blockIdx.x, t = threadIdx.x, wrp = t >> 5;
   const u64* keys = cand + (size_t)b * HW;
-  const int N = cand_count[b];
+  const int N = cand_count[b * XFB_TICKET_STRIDE];
   const int K = N < topk ? N : topk;
-  u64 thresh = 0;  // select keys >= thresh
-  if (N > K) {
-    if (t == 0) { s_prefix = 0; s_remaining = K; }
+  u64 thresh = 0;      // select keys >= thresh
+  int take = N;        // how many keys that is
+  if (N > TOPK_CAP) {
+    if (t == 0) { s_prefix = 0; s_remaining = K; s_done = 0; }
     u64 mask = 0;
     for (int pass = 7; pass >= 0; --pass) {
-      for (int i = t; i < 256; i += TOPK_NT) hist[i] = 0;
+      for (int i = t; i < 32 * 256; i += TOPK_NT) whist[i] = 0;
       __syncthreads();
       const u64 prefix = s_prefix;
       const int shift = pass * 8;
       for (int i = t; i < N; i += TOPK_NT) {
         const u64 k = keys[i];
-        if ((k & mask) == prefix) atomicAdd(&hist[(unsigned int)(k >> shift) & 255u], 1u);
+        if ((k & mask) == prefix) atomicAdd(&whist[wrp * 256 + ((unsigned int)(k >> shift) & 255u)], 1u);
+      }
+      __syncthreads();
+      if (t < 256) {
+        unsigned int h = 0;
+#pragma unroll 8
+        for (int w = 0; w < 32; ++w) h += whist[w * 256 + t];
+        hist[t] = h;
       }
       __syncthreads();
       if (t == 0) {
@@ -153,19 +165,32 @@ __global__ void __launch_bounds__(TOPK_NT) topk_kernel(const u64* cand, int* can
         }
         s_prefix = prefix | ((u64)d << shift);
         s_remaining = rem;
+        s_take = K - rem + (int)hist[d];            // keys >= the new prefix: everything already selected + the whole boundary bin
+        s_done = (s_take <= TOPK_CAP) ? 1 : 0;
       }
       mask |= (u64)255 << shift;
       __syncthreads();
+      if (s_done) break;
     }
-    thresh = s_prefix;  // the K-th largest key (keys are unique)
+    thresh = s_prefix;   // (after 8 passes: the K-th largest key itself, take == K)
+    take = s_take;
   }
+  int sort_n = 2;
+  while (sort_n < take) sort_n <<= 1;
   if (t == 0) s_fill = 0;
   for (int i = t; i < sort_n; i += TOPK_NT) skeys[i] = 0;
   __syncthreads();
-  for (int i = t; i < N; i += TOPK_NT) {
-    const u64 k = keys[i];
-    if (k >= thresh) {
-      const int pos = atomicAdd(&s_fill, 1);
+  // compaction, warp-aggregated: ONE shared-memory atomic per warp and round (a per-key atomic on one address serialises the CTA)
+  for (int i0 = 0; i0 < N; i0 += TOPK_NT) {
+    const int i = i0 + t;
+    const u64 k = (i < N) ? keys[i] : 0;
+    const bool sel = i < N && k >= thresh;
+    const unsigned int bal = __ballot_sync(0xffffffffu, sel);
+    int base = 0;
+    if ((t & 31) == 0 && bal) base = atomicAdd(&s_fill, __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (sel) {
+      const int pos = base + __popc(bal & ((1u << (t & 31)) - 1u));
       if (pos < sort_n) skeys[pos] = k;
     }
   }
@@ -199,7 +224,7 @@ __global__ void __launch_bounds__(TOPK_NT) topk_kernel(const u64* cand, int* can
   if (t == 0) {
     n_valid[b] = K;
     cand_count_last[b] = N;
-    cand_count[b] = 0;  // re-arm for the next call
+    cand_count[b * XFB_TICKET_STRIDE] = 0;  // re-arm for the next call
   }
 }
 
@@ -248,8 +273,6 @@ __global__ void __launch_bounds__(256) describe_kernel(const float* feats, int H
   *reinterpret_cast<float2*>(desc + ((size_t)b * topk + i) * 64 + lane * 2) = o;
 }
 
-static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
-
 cudaError_t launch_post(Ctx* c, int topk, float nms_thr, int32_t* d_nvalid, float* d_xy, float* d_score, float* d_desc) {
   const int H = c->H, W = c->W;
   dim3 g1((W + NMS_T * NMS_NX - 1) / (NMS_T * NMS_NX), (H + NMS_T - 1) / NMS_T, c->B);
@@ -259,17 +282,15 @@ cudaError_t launch_post(Ctx* c, int topk, float nms_thr, int32_t* d_nvalid, floa
   c->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const int sort_n = next_pow2(topk < 2 ? 2 : topk);
-  const size_t smem = sizeof(u64) * (size_t)sort_n;
+  const size_t smem = sizeof(u64) * (size_t)TOPK_CAP + 32 * 256 * 4;
   static unsigned long long attr_mask = 0;
   if (!((attr_mask >> c->device) & 1ull)) {
-    e = cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * 8192));
+    e = cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_mask |= 1ull << c->device;
   }
   prof_begin(c, P_TOPK);
-  topk_kernel<<<c->B, TOPK_NT, smem, c->stream>>>(c->cand, c->cand_count, c->cand_count_last, H * W, W, topk, sort_n, d_nvalid, d_xy,
-                                                  d_score);
+  topk_kernel<<<c->B, TOPK_NT, smem, c->stream>>>(c->cand, c->cand_count, c->cand_count_last, H * W, W, topk, d_nvalid, d_xy, d_score);
   prof_end(c);
   c->launches++;
   e = cudaGetLastError();

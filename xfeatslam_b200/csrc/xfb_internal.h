@@ -63,6 +63,7 @@ struct ConvArgs {
   float* out_rstd;
   int Hin, Win, Hout, Wout;
   int full_w;             // IN_UNFOLD: width of xn
+  const float* w0;        // conv_small FUSE0: block1.0's packed weights [9][1][4]
 };
 
 struct Ctx {
@@ -81,6 +82,7 @@ struct Ctx {
   float wscale2[L_NUM] = {};      // its epilogue factor 1 / (activation scale * weight scale)
   int conv_tc_version = 2;        // 2 = conv_tc2.cu (default), 1 = conv_tc.cu (XFB_CONV_TC=1: A/B reference)
   int num_sms = 148;
+  bool b1_fuse = true;            // block1.0 recomputed inside block1.1 (XFB_B1_FUSE=0: materialise block1.0 like round 1)
   struct TmapSlot { alignas(64) unsigned char blob[128]; const void* ptr; int B, H, W; };   // CUtensorMap of a layer's output + what it was encoded for
   TmapSlot tmap[L_NUM] = {};
   unsigned long long* t2_counters = nullptr;   // XFB_T2_DEBUG: [L_NUM][32] cycle counters of CTA 0 (conv_tc2.cu), printed at xfb_destroy
@@ -106,7 +108,7 @@ struct Ctx {
 
   // post-processing
   unsigned long long* cand = nullptr;  // [B][H*W] candidate keys
-  int* cand_count = nullptr;           // [B]
+  int* cand_count = nullptr;           // [B * XFB_TICKET_STRIDE] (one cache line per frame)
   int* cand_count_last = nullptr;      // [B] copy kept for xfb_debug_candidates
   // device outputs used by the host-pointer entry points
   int32_t* o_nvalid = nullptr;
