@@ -290,8 +290,8 @@ def kernel_roofline(name, ms_per_batch, launches_per_batch, h, w, batch, peaks, 
 
 
 # the tensor-core convolutions compute an fp32-accurate product from split operands: cost in plain bf16/fp16 MMA passes
-CONV_SPLIT_COST = 6.0
-CONV_SPLIT_NAME = "tcgen05 kind::tf32, 3xTF32 split (hi*hi + hi*lo + lo*hi; TF32 = half the bf16 rate)"
+CONV_SPLIT_COST = 3.0
+CONV_SPLIT_NAME = "tcgen05 kind::f16, fp16 two-piece split (A_hi x [W_hi ; W_lo] + A_lo x W_hi = three fp16 products per output, fp32 TMEM accumulators)"
 
 
 def kernel_bytes(name, h, w, batch):

@@ -329,8 +329,9 @@ cudaError_t launch_conv_small_layer(Ctx* c, int L) {
   switch (L) {
     // DIRECT (inputs through L1, no staged tile) measured faster except for the 8->8 stride-1 layer
     // (18 two-vector pixel loads per thread): 0.070 / 0.133 / 0.128 / 0.110 ms per 32-frame batch
-    // block1.0 -> block1.1 fused by recomputation (default): block1.0 only produces its BatchNorm statistics, block1.1 rebuilds
-    // block1.0's output tile from xn in shared memory.  XFB_B1_FUSE=0 (or the layer-parity debug reads) keeps the two-kernel form.
+    // XFB_B1_FUSE=1: block1.0 -> block1.1 fused by recomputation (block1.0 only produces its BatchNorm statistics, block1.1 rebuilds
+    // block1.0's output tile from xn in shared memory).  Measured on the B200: 0.060 + 0.152 ms against 0.068 + 0.133 ms for the two
+    // kernels -- the recomputation costs more than the 9.8 MB / frame of traffic it saves, so the two-kernel form stays the default.
     case L_B1_0: a.in = c->xn; return c->b1_fuse ? run_small<SB10, false, true, false>(c, a, L) : run_small<SB10, false, true>(c, a, L);
     case L_B1_1:
       if (c->b1_fuse) {

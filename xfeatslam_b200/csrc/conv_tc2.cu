@@ -79,20 +79,26 @@ struct T2Cfg {
   static constexpr int W_BYTES = NPHASE * TAPS * W_UNIT_BYTES;                    // resident weight image of one output group
   static constexpr uint32_t LBO_A = PS, SBO_A = WT * 16;
   static constexpr uint32_t LBO_B = (2 * NP / 8) * 128, SBO_B = 128;
-  static constexpr int ITEMS = NSUB * NPIX * KCS;                                 // (pixel, 8-channel chunk) items per staged buffer
-  static constexpr int ROUNDS = (ITEMS + T2_PROD * UNR - 1) / (T2_PROD * UNR);    // units per staged buffer
+  // A single-phase layer with padded input channels (block2: 24 -> 32) zeroes the padding chunk of every ring buffer ONCE: only the
+  // KCR real chunks are staged per tile, by the first PT producer threads (a multiple of KCR, so a thread keeps its chunk).
+  static constexpr int KCR = (NPHASE == 1 && CINP != CIN) ? CIN / 8 : KCS;
+  static constexpr int PT = T2_PROD - T2_PROD % KCR;
+  static constexpr int ITEMS = NSUB * NPIX * KCR;                                 // (pixel, 8-channel chunk) items per staged buffer
+  static constexpr int ROUNDS = (ITEMS + PT * UNR - 1) / (PT * UNR);              // units per staged buffer
+  static constexpr int NSLOT = ROUNDS * UNR;                                      // items per thread and staged buffer
   static constexpr bool HAS_STG = COUT != 65;                                     // keypoint_head.3 writes its own folded output
   static constexpr int NHALF = HAS_STG ? (NOUT + 31) / 32 : 0;                    // 32-channel TMA boxes per tile
   static constexpr int STG_BYTES = NHALF * 16384;                                 // staging tile(s): [128 px][32 ch] fp32, 128B-swizzled
   static constexpr int FOLD_BYTES = 128 * 2 * 8;
-  static constexpr size_t SMEM_BYTES = (size_t)STG_BYTES + W_BYTES + (size_t)NBUF * BUF_BYTES + FOLD_BYTES + 256;
+  static constexpr int BN_BYTES = CINP * 2 * 4;                                   // the current frame's (16 rstd, -16 mean rstd) per input channel
+  static constexpr size_t SMEM_BYTES = (size_t)STG_BYTES + W_BYTES + (size_t)NBUF * BUF_BYTES + FOLD_BYTES + BN_BYTES + 256;
   // kind::f16, F16 x F16 -> F32, both K-major, M = 128
   static constexpr uint32_t IDESC_2N = (1u << 4) | ((uint32_t)(2 * NP >> 3) << 17) | ((128u >> 4) << 24);
   static constexpr uint32_t IDESC_1N = (1u << 4) | ((uint32_t)(NP >> 3) << 17) | ((128u >> 4) << 24);
   static_assert(CSTAGE % 16 == 0 && CINP % CSTAGE == 0 && COUT % NSPLIT == 0 && (NOUT % 8 == 0 || NOUT == 65) && NOUT <= 80, "shape");
   static_assert(2 * NP <= 256 && (2 * NP) % 16 == 0, "UMMA N");
   static_assert(S == 1 || KS == 3, "stride 2 is implemented for 3x3 only");
-  static_assert(T2_PROD % KCS == 0, "a producer thread keeps one channel chunk");
+  static_assert(T2_PROD % KCS == 0 && PT % KCR == 0 && ROUNDS <= 2, "a producer thread keeps one channel chunk; at most two units per buffer");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(PS % 16 == 0 && W_UNIT_BYTES % 16 == 0 && W_BYTES % 1024 == 0, "descriptor alignment");
 };
@@ -201,7 +207,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
   unsigned char* sW = smem_raw + C::STG_BYTES;                    // resident weights of this CTA's output group
   unsigned char* sA = sW + C::W_BYTES;                            // NBUF x [hi | lo] staged tiles
   double* sFold = reinterpret_cast<double*>(sA + (size_t)NBUF * C::BUF_BYTES);   // [128][2]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sFold + 128 * 2);
+  float* sBN = reinterpret_cast<float*>(sFold + 128 * 2);                        // [2][CINP]: scale, shift of the producers' current frame
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBN + 2 * C::CINP);
   uint64_t* bar_in = bars + 0;          // [NBUF] tile staged (T2_PROD arrivals)
   uint64_t* bar_free = bars + 4;        // [NBUF] tensor core finished reading the staged buffer
   uint64_t* bar_accf = bars + 8;        // [2] accumulator complete
@@ -234,7 +241,34 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
   if (warp >= 5) {
     // ===================== producers: stage (tile, channel phase) buffers, global loads one unit ahead =====================
     const int pt = t - (T2_EPI + 32);
-    const int kc = pt % KCS;                         // this thread's 8-channel chunk inside a phase (constant)
+    const int kc = pt % C::KCR;                      // this thread's 8-channel chunk inside a phase (constant)
+    // Per-thread item table, computed ONCE: the (pixel, chunk) slots a thread stages are the same for every tile -- only the tile
+    // origin moves.  slot_off = byte offset in the staged buffer (-1: no item), slot_yx = input pixel relative to the tile origin
+    // ((dy << 16) | (dx & 0xffff); 1x1 layers: the pixel index inside the 128-pixel tile).
+    int slot_off[C::NSLOT], slot_yx[C::NSLOT];
+#pragma unroll
+    for (int sl = 0; sl < C::NSLOT; ++sl) {
+      const int idx = sl * C::PT + pt;
+      slot_off[sl] = -1; slot_yx[sl] = 0;
+      if (pt < C::PT && idx < ITEMS) {
+        const int rest = idx / C::KCR;               // idx % KCR == kc
+        const int pix = rest % NPIX, sub = rest / NPIX;
+        slot_off[sl] = sub * C::SUB_BYTES + kc * PS + pix * 16;
+        int dy, dx;
+        if (C::KS == 1) { dy = 0; dx = pix; }
+        else if (C::S == 1) { dy = pix / WT - C::PAD; dx = pix % WT - C::PAD; }
+        else { dy = 2 * (pix / WT - 1) + (sub >> 1); dx = 2 * (pix % WT - 1) + (sub & 1); }
+        slot_yx[sl] = (int)(((unsigned int)dy << 16) | ((unsigned int)dx & 0xffffu));
+      }
+    }
+    if (C::KCR != KCS) {
+      // zero the padding chunk planes of every ring buffer once (hi and lo)
+      for (int i = pt; i < NBUF * 2 * C::NSUB * (KCS - C::KCR) * (PS / 16); i += T2_PROD) {
+        const int per = (KCS - C::KCR) * (PS / 16);
+        const int plane = i / per, w = i - plane * per;        // plane = (buffer, hi|lo, sub)
+        *reinterpret_cast<uint4*>(sA + (size_t)plane * C::SUB_BYTES + (size_t)C::KCR * PS + (size_t)w * 16) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
     const bool dbg_me = a.dbg != nullptr && blockIdx.x == 0 && pt == 0;
     long long t0 = dbg_me ? clock64() : 0;
 
@@ -277,53 +311,97 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
       const int ch = u.ph * C::CSTAGE + kc * 8;      // first of this thread's 8 channels
       const bool ch_ok = ch < C::CIN;                // padded chunks (Cin 24 -> 32) are zero
       R.inside = 0u;
+      int uy0 = 0, ux0 = 0;                          // T2IN_UNFOLD: cell of the tile's first pixel
+      if (INMODE == T2IN_UNFOLD) { uy0 = (tf * 128) / a.Win; ux0 = tf * 128 - uy0 * a.Win; }
+      const int lin_ok = (C::KS == 1) ? a.Hin * a.Win - tf * 128 : 0;          // 1x1: pixels of the frame left from this tile on
+      const int oyi = (C::S == 1) ? oy0 : 2 * oy0, oxi = (C::S == 1) ? ox0 : 2 * ox0;
 #pragma unroll
       for (int q = 0; q < UNR; ++q) {
-        const int idx = (u.rnd * UNR + q) * T2_PROD + pt;
+        const int off = (ROUNDS == 1 || u.rnd == 0) ? slot_off[q] : slot_off[(ROUNDS - 1) * UNR + q];
+        const int yx = (ROUNDS == 1 || u.rnd == 0) ? slot_yx[q] : slot_yx[(ROUNDS - 1) * UNR + q];
         R.v[q].a = make_float4(0.f, 0.f, 0.f, 0.f); R.v[q].b = R.v[q].a;
-        R.av[q] = 0.f; R.off[q] = -1;
-        if (idx < ITEMS) {
-          const int rest = idx / KCS;                // idx % KCS == kc
-          const int pix = rest % NPIX, sub = rest / NPIX;
-          int iy, ix;
-          if (C::KS == 1) { const int lin = tf * 128 + pix; iy = lin / a.Win; ix = lin - iy * a.Win; }
-          else if (C::S == 1) { iy = oy0 - C::PAD + pix / WT; ix = ox0 - C::PAD + pix % WT; }
-          else { iy = 2 * (oy0 - 1 + pix / WT) + (sub >> 1); ix = 2 * (ox0 - 1 + pix % WT) + (sub & 1); }
-          R.off[q] = sub * C::SUB_BYTES + kc * PS + pix * 16;
-          if (ch_ok && iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win) {
-            R.inside |= 1u << q;
+        R.av[q] = 0.f; R.off[q] = off;
+        if (off >= 0 && ch_ok) {
+          const int dy = yx >> 16, dx = (int)(short)(yx & 0xffff);
+          if (C::KS == 1 && INMODE != T2IN_UNFOLD) {
+            if (dx < lin_ok) {                       // the tile is 128 consecutive pixels of the frame
+              R.inside |= 1u << q;
+              R.v[q] = ldg256(in_b + ((size_t)tf * 128 + dx) * C::CIN + ch);
+            }
+          } else {
+            int iy, ix;
             if (INMODE == T2IN_UNFOLD) {
-              // XFeatModel::unfold2d(x, 8), src/XFeat.cc:124-133: channel c = (y % 8) * 8 + x % 8 -> chunk kc = row iy * 8 + kc of xn
-              R.v[q] = ldg256(in_b + (size_t)(iy * 8 + (ch >> 3)) * a.full_w + ix * 8);
-            } else {
-              R.v[q] = ldg256(in_b + ((size_t)iy * a.Win + ix) * C::CIN + ch);
-              if (INMODE == T2IN_BN_SKIP) R.av[q] = a.skip_avg[((size_t)b * a.Hin + iy) * a.Win + ix];
+              ix = ux0 + dx; iy = uy0;
+              if (a.Win >= 128) { if (ix >= a.Win) { ix -= a.Win; ++iy; } }
+              else { const int wr = ix / a.Win; iy += wr; ix -= wr * a.Win; }
+            } else { iy = oyi + dy; ix = oxi + dx; }
+            if (iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win) {
+              R.inside |= 1u << q;
+              if (INMODE == T2IN_UNFOLD) {
+                // XFeatModel::unfold2d(x, 8), src/XFeat.cc:124-133: channel c = (y % 8) * 8 + x % 8 -> chunk kc = row iy * 8 + kc of xn
+                R.v[q] = ldg256(in_b + (size_t)(iy * 8 + (ch >> 3)) * a.full_w + ix * 8);
+              } else {
+                R.v[q] = ldg256(in_b + ((size_t)iy * a.Win + ix) * C::CIN + ch);
+                if (INMODE == T2IN_BN_SKIP) R.av[q] = a.skip_avg[((size_t)b * a.Hin + iy) * a.Win + ix];
+              }
             }
           }
         }
+      }
+    };
+    // BatchNorm parameters of a unit's 8 channels, from shared memory.  The producers keep the CURRENT frame's parameters of all
+    // input channels there in fused form (scale = 16 rstd, shift = -16 mean rstd: relu((x - mean) rstd) * 16 = max(fma(x, scale,
+    // shift), 0), the scale / shift form ATen's batch_norm uses, with the exact activation scale folded in) and reload them -- two
+    // named barriers among the 224 producer threads -- only when their tile range enters another frame: no global load, no
+    // dependent latency per staged buffer.
+    float m[8], r[8], sw[8], sb[8];
+    int cur_b = -1, sw_loaded = 0;
+    auto load_params = [&](const ProdPos& u) {
+      if (!(INMODE == T2IN_BN || INMODE == T2IN_BN_SKIP)) return;
+      const int b = u.tile / a.tiles;
+      if (C::KCR != KCS) {
+        // block2 (single phase, 24 channels): measured faster with the parameters straight from global memory / L1, loaded BEFORE the
+        // next unit's data loads are issued (the L1 returns a warp's loads in order: behind them they would wait for DRAM latency)
+        const int ch = kc * 8;
+        const f8 mm = ldg256(a.in_mean + b * C::CIN + ch), rr = ldg256(a.in_rstd + b * C::CIN + ch);
+        m[0] = mm.a.x; m[1] = mm.a.y; m[2] = mm.a.z; m[3] = mm.a.w; m[4] = mm.b.x; m[5] = mm.b.y; m[6] = mm.b.z; m[7] = mm.b.w;
+        r[0] = rr.a.x; r[1] = rr.a.y; r[2] = rr.a.z; r[3] = rr.a.w; r[4] = rr.b.x; r[5] = rr.b.y; r[6] = rr.b.z; r[7] = rr.b.w;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { r[e] *= T2_ACT_SCALE; m[e] = -m[e] * r[e]; }
+        if (INMODE == T2IN_BN_SKIP && sw_loaded == 0) {
+          const f8 ww = ldg256(a.skip_w + ch), bb = ldg256(a.skip_b + ch);
+          sw[0] = ww.a.x; sw[1] = ww.a.y; sw[2] = ww.a.z; sw[3] = ww.a.w; sw[4] = ww.b.x; sw[5] = ww.b.y; sw[6] = ww.b.z; sw[7] = ww.b.w;
+          sb[0] = bb.a.x; sb[1] = bb.a.y; sb[2] = bb.a.z; sb[3] = bb.a.w; sb[4] = bb.b.x; sb[5] = bb.b.y; sb[6] = bb.b.z; sb[7] = bb.b.w;
+          sw_loaded = 1;
+        }
+        return;
+      }
+      if (b != cur_b) {                             // (uniform over the producer threads: they walk the same unit sequence)
+        asm volatile("bar.sync 2, %0;" ::"n"(T2_PROD) : "memory");      // everybody is done reading the previous frame's parameters
+        for (int c = pt; c < C::CINP; c += T2_PROD) {
+          float sc = 0.f, sh = 0.f;
+          if (c < C::CIN) { sc = a.in_rstd[b * C::CIN + c] * T2_ACT_SCALE; sh = -a.in_mean[b * C::CIN + c] * sc; }
+          sBN[c] = sc; sBN[C::CINP + c] = sh;
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(T2_PROD) : "memory");
+        cur_b = b;
+      }
+      const int ch = u.ph * C::CSTAGE + kc * 8;
+      const float4 r0 = *reinterpret_cast<const float4*>(sBN + ch), r1 = *reinterpret_cast<const float4*>(sBN + ch + 4);
+      const float4 m0 = *reinterpret_cast<const float4*>(sBN + C::CINP + ch), m1 = *reinterpret_cast<const float4*>(sBN + C::CINP + ch + 4);
+      r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w; r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
+      m[0] = m0.x; m[1] = m0.y; m[2] = m0.z; m[3] = m0.w; m[4] = m1.x; m[5] = m1.y; m[6] = m1.z; m[7] = m1.w;
+      if (INMODE == T2IN_BN_SKIP && cur_b >= 0 && sw_loaded == 0 && ch < C::CIN) {
+        const f8 ww = ldg256(a.skip_w + ch), bb = ldg256(a.skip_b + ch);     // (single-phase layer: the chunk, hence these, never change)
+        sw[0] = ww.a.x; sw[1] = ww.a.y; sw[2] = ww.a.z; sw[3] = ww.a.w; sw[4] = ww.b.x; sw[5] = ww.b.y; sw[6] = ww.b.z; sw[7] = ww.b.w;
+        sb[0] = bb.a.x; sb[1] = bb.a.y; sb[2] = bb.a.z; sb[3] = bb.a.w; sb[4] = bb.b.x; sb[5] = bb.b.y; sb[6] = bb.b.z; sb[7] = bb.b.w;
+        sw_loaded = 1;
       }
     };
     // transform the loaded unit and store it into its staged buffer
     auto consume = [&](const ProdPos& u, const ProdRegs<UNR>& R) {
       const int buf = u.it % NBUF;
       unsigned char* dst_hi = sA + (size_t)buf * C::BUF_BYTES;
-      const int b = u.tile / a.tiles;
-      const int ch = u.ph * C::CSTAGE + kc * 8;
-      float m[8], r[8], sw[8], sb[8];
-      if ((INMODE == T2IN_BN || INMODE == T2IN_BN_SKIP) && ch < C::CIN) {      // (L1-resident: neighbouring tiles belong to the same frame)
-        const f8 mm = ldg256(a.in_mean + b * C::CIN + ch), rr = ldg256(a.in_rstd + b * C::CIN + ch);
-        m[0] = mm.a.x; m[1] = mm.a.y; m[2] = mm.a.z; m[3] = mm.a.w; m[4] = mm.b.x; m[5] = mm.b.y; m[6] = mm.b.z; m[7] = mm.b.w;
-        r[0] = rr.a.x; r[1] = rr.a.y; r[2] = rr.a.z; r[3] = rr.a.w; r[4] = rr.b.x; r[5] = rr.b.y; r[6] = rr.b.z; r[7] = rr.b.w;
-        // relu((x - mean) * rstd) * 16 = max(fma(x, 16 rstd, -16 mean rstd), 0): the scale / shift form ATen's batch_norm uses
-        // (alpha = invstd, beta = -mean * invstd), with the exact activation scale folded in
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { r[e] *= T2_ACT_SCALE; m[e] = -m[e] * r[e]; }
-        if (INMODE == T2IN_BN_SKIP) {
-          const f8 ww = ldg256(a.skip_w + ch), bb = ldg256(a.skip_b + ch);
-          sw[0] = ww.a.x; sw[1] = ww.a.y; sw[2] = ww.a.z; sw[3] = ww.a.w; sw[4] = ww.b.x; sw[5] = ww.b.y; sw[6] = ww.b.z; sw[7] = ww.b.w;
-          sb[0] = bb.a.x; sb[1] = bb.a.y; sb[2] = bb.a.z; sb[3] = bb.a.w; sb[4] = bb.b.x; sb[5] = bb.b.y; sb[6] = bb.b.z; sb[7] = bb.b.w;
-        }
-      }
       if (u.rnd == 0) {
         if (u.ph == 0 && u.tile + 2 < tile_end) prefetch_tile(u.tile + 2);
         T2_TICK(3);
@@ -374,12 +452,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
         ProdPos un = u;
         advance(un);
         bool more = un.tile < tile_end;
+        load_params(u);
         if (more) issue(un, rb);           // the next unit's loads fly while this one is transformed
         consume(u, ra);
         if (!more) break;
         u = un;
         advance(un);
         more = un.tile < tile_end;
+        load_params(u);
         if (more) issue(un, ra);
         consume(u, rb);
         if (!more) break;
@@ -669,7 +749,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
 
 // ---------------------------------------------------------------------------------------------------
 //                        CIN COUT KS S CSTAGE NBUF NSPLIT UNR
-using T2B2x = T2Cfg<24, 24, 3, 1, 32, 3, 1, 4>;      // block2.0/.1                   120x160         (Cin padded 24 -> 32)
+using T2B2x = T2Cfg<24, 24, 3, 1, 32, 3, 1, 3>;      // block2.0/.1                   120x160         (Cin padded 24 -> 32)
 using T2B30 = T2Cfg<24, 64, 3, 2, 16, 3, 1, 3>;      // block3.0                      -> 60x80
 using T2C33 = T2Cfg<64, 64, 3, 1, 32, 2, 1, 4>;      // block3.1, block4.1/.2, block_fusion.0/.1   (147 KB of weights resident)
 using T2C11 = T2Cfg<64, 64, 1, 1, 64, 3, 1, 3>;      // block3.2, block_fusion.2, heatmap_head.0/.1, keypoint_head.0/.1/.2

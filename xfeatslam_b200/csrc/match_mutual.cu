@@ -135,8 +135,9 @@ __device__ __forceinline__ float mm_unord(unsigned int o) {
   if (o == 0u) return -CUDART_INF_F;
   return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
 }
-// exact ORBmatcher::DescriptorDistance of two fp32 rows (same op order as oracle/matcher_oracle.c)
-__device__ __forceinline__ int mm_exact_distance(const float* arow, const float* brow) {
+// exact ORBmatcher::DescriptorDistance of two fp32 rows, in the reference's op order (oracle/matcher_oracle.c): fp32 subtract,
+// fp64 accumulate in index order, round to float, * 512, truncate
+__device__ __noinline__ int mm_exact_distance_seq(const float* arow, const float* brow) {
   double s = 0.0;
 #pragma unroll 4
   for (int kq = 0; kq < 16; ++kq) {
@@ -149,6 +150,76 @@ __device__ __forceinline__ int mm_exact_distance(const float* arow, const float*
     d = x.w - b.w; s = fma((double)d, (double)d, s);
   }
   return (int)(__double2float_rn(s) * 512.0f);
+}
+// The same integer, usually 4x sooner: every square of an fp32 difference is EXACT in fp64, so any summation order differs from
+// the reference's by less than 2^-45 relative (<= 67 roundings of 2^-53).  Four interleaved chains (a 16-step instead of a 64-step
+// dependency chain); if rounding to float gives the same value at both ends of a 2^-40 band around the sum, that float -- hence
+// the integer -- IS the reference's; otherwise (probability ~ 2^-15) the sequential order decides.
+__device__ __forceinline__ int mm_exact_distance(const float* arow, const float* brow) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 4
+  for (int kq = 0; kq < 16; ++kq) {
+    const float4 x = *reinterpret_cast<const float4*>(arow + kq * 4);
+    const float4 b = *reinterpret_cast<const float4*>(brow + kq * 4);
+    float d;
+    d = x.x - b.x; s0 = fma((double)d, (double)d, s0);
+    d = x.y - b.y; s1 = fma((double)d, (double)d, s1);
+    d = x.z - b.z; s2 = fma((double)d, (double)d, s2);
+    d = x.w - b.w; s3 = fma((double)d, (double)d, s3);
+  }
+  const double s = (s0 + s1) + (s2 + s3);
+  const float f = __double2float_rn(s);
+  const float flo = __double2float_rn(s * (1.0 - 0x1p-40)), fhi = __double2float_rn(s * (1.0 + 0x1p-40));
+  if (flo == fhi) return (int)(f * 512.0f);
+  return mm_exact_distance_seq(arow, brow);
+}
+
+// Exact verification of a warp's queued (row, column) pairs, OUT OF LINE (the streaming loops stay small: this code runs a few
+// times per CTA).  Two phases: (1) filter every entry against the current bound (rows: the row's candidate bound; columns: the
+// largest estimate ANY CTA has seen for the column) and compact the survivors in place (ballot-based, warp-uniform), (2) verify
+// the survivors 32 at a time, one per lane -- dense batches: the fp64 chain costs the same whether 3 or 32 lanes run it.
+struct MmDrain {
+  unsigned long long* q; const float* sTau; const float* rawA; const float* rawB; unsigned long long* sK1; unsigned long long* sK2;
+  const unsigned int* colG; unsigned long long* colK; unsigned long long* dbgc;
+  float margin_col; unsigned int init_u; int row0, group; bool dir2, wild;
+};
+__device__ __noinline__ void mm_drain(const MmDrain& c, int qn, bool final, int lane) {
+  __syncwarp();
+  unsigned long long* q = c.q;
+  int nw = 0;
+  for (int base = 0; base < qn; base += 32) {
+    const int i = base + lane;
+    unsigned long long ent = 0;
+    bool keep = false;
+    if (i < qn) {
+      ent = q[i];
+      const int r = (int)((ent >> 24) & 0x7full), j = (int)(ent & 0xffffffull);
+      const float ub = __uint_as_float((unsigned int)(ent >> 32));        // upper bound of the pair's u
+      if (c.dbgc) atomicAdd(c.dbgc + (c.dir2 ? 28 : 26), 1ull);
+      if (!c.dir2) keep = c.wild || ub > (final ? c.sTau[r] : c.sTau[c.group * MM_ROWS + r]);
+      else keep = c.wild || ub >= mm_unord(__ldcg(c.colG + j)) - c.margin_col;
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+    if (keep) q[nw + __popc(bal & ((1u << lane) - 1u))] = ent;            // nw <= base: never ahead of the entries still to be read
+    nw += __popc(bal);
+    __syncwarp();
+  }
+  for (int i = lane; i < nw; i += 32) {
+    const unsigned long long ent = q[i];
+    const int r = (int)((ent >> 24) & 0x7full), j = (int)(ent & 0xffffffull);
+    if (c.dbgc) atomicAdd(c.dbgc + (c.dir2 ? 29 : 27), 1ull);
+    const int D = mm_exact_distance(c.rawA + (size_t)(c.row0 + r) * 64, c.rawB + (size_t)j * 64);
+    if ((unsigned int)D < c.init_u) {
+      if (!c.dir2) {
+        const unsigned long long key = ((unsigned long long)(unsigned int)D << 32) | (unsigned int)j;
+        const unsigned long long old = atomicMin(&c.sK1[r], key);
+        atomicMin(&c.sK2[r], max(old, key));
+      } else {
+        atomicMin(c.colK + j, ((unsigned long long)(unsigned int)D << 32) | (unsigned int)(c.row0 + r));
+      }
+    }
+  }
+  __syncwarp();
 }
 
 struct MmShared {
@@ -282,48 +353,10 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
     const float e_col = 1.05f * sqrtf(nam * nbm) + 0.02f * (nam + nbm + 1.0f);
     const float margin_col = wild_set ? CUDART_INF_F : (2.0f * e_col + 1.0f) * (1.0f / 1024.0f);
 
-    // Exact verification of the queued (row, column) pairs; `final` = the stream is over (tight filters).  Two phases: (1) filter
-    // every entry against the current bound (rows: the row's candidate bound; columns: the largest estimate ANY CTA has seen for
-    // the column) and compact the survivors in place (ballot-based, warp-uniform), (2) verify the survivors 32 at a time, one per
-    // lane -- dense batches: the 64-step fp64 chain costs the same whether 3 or 32 lanes run it.
-    auto drain = [&](bool final) {
-      __syncwarp();
-      int nw = 0;
-      for (int base = 0; base < qn; base += 32) {
-        const int i = base + lane;
-        unsigned long long ent = 0;
-        bool keep = false;
-        if (i < qn) {
-          ent = q[i];
-          const int r = (int)((ent >> 24) & 0x7full), j = (int)(ent & 0xffffffull);
-          const float ub = __uint_as_float((unsigned int)(ent >> 32));        // upper bound of the pair's u
-          if (dbgc) atomicAdd(dbgc + (dir2 ? 28 : 26), 1ull);
-          if (!dir2) keep = wild_set || ub > (final ? sTau[r] : sTau[group * MM_ROWS + r]);
-          else keep = wild_set || ub >= mm_unord(__ldcg(colG + j)) - margin_col;
-        }
-        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-        if (keep) q[nw + __popc(bal & ((1u << lane) - 1u))] = ent;            // nw <= base: never ahead of the entries still to be read
-        nw += __popc(bal);
-        __syncwarp();
-      }
-      for (int i = lane; i < nw; i += 32) {
-        const unsigned long long ent = q[i];
-        const int r = (int)((ent >> 24) & 0x7full), j = (int)(ent & 0xffffffull);
-        if (dbgc) atomicAdd(dbgc + (dir2 ? 29 : 27), 1ull);
-        const int D = mm_exact_distance(rawA + (size_t)(row0 + r) * 64, rawB + (size_t)j * 64);
-        if ((unsigned int)D < init_u) {
-          if (!dir2) {
-            const unsigned long long key = ((unsigned long long)(unsigned int)D << 32) | (unsigned int)j;
-            const unsigned long long old = atomicMin(&sK1[r], key);
-            atomicMin(&sK2[r], max(old, key));
-          } else {
-            atomicMin(colK + j, ((unsigned long long)(unsigned int)D << 32) | (unsigned int)(row0 + r));
-          }
-        }
-      }
-      qn = 0;
-      __syncwarp();
-    };
+    MmDrain dc;
+    dc.q = q; dc.sTau = sTau; dc.rawA = rawA; dc.rawB = rawB; dc.sK1 = sK1; dc.sK2 = sK2; dc.colG = colG; dc.colK = colK; dc.dbgc = dbgc;
+    dc.margin_col = margin_col; dc.init_u = init_u; dc.row0 = row0; dc.group = group; dc.dir2 = dir2; dc.wild = wild_set;
+    auto drain = [&](bool final) { mm_drain(dc, qn, final, lane); qn = 0; };
     // warp-uniform append (no atomics): every round, each lane with candidates left contributes its lowest one
     // entry e of the mask is the pair (row_base + e * row_step, col_base + e * col_step)
     auto append = [&](uint32_t mask, int row_base, int row_step, int col_base, int col_step, float ub) {
@@ -384,9 +417,10 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
           const float tau = bound();
           mm_ld32(tq + (uint32_t)part * 32u, v);
           const float m = mm_max32(v);
-          uint32_t mask = 0;
+          uint32_t mk[4] = {0u, 0u, 0u, 0u};                     // four independent chains instead of one 32-step dependency
 #pragma unroll
-          for (int e = 0; e < 32; ++e) mask |= (v[e] > tau) ? (1u << e) : 0u;
+          for (int e = 0; e < 32; ++e) mk[e & 3] |= (v[e] > tau) ? (1u << e) : 0u;
+          uint32_t mask = (mk[0] | mk[1]) | (mk[2] | mk[3]);
           if (wild && ok) mask = 0xffffffffu;
           const int j0 = k * MM_ROWS + part * 32;
           if (j0 + 32 > nB) mask &= (nB > j0) ? (0xffffffffu >> (32 - (nB - j0))) : 0u;     // padded columns
@@ -437,9 +471,10 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
 #pragma unroll 1
         for (int part = 0; part < 4; ++part) {
           mm_ld32(tq + (uint32_t)part * 32u, v);
-          uint32_t mask = 0;
+          uint32_t mk[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-          for (int e = 0; e < 32; ++e) mask |= (v[e] > thr) ? (1u << e) : 0u;
+          for (int e = 0; e < 32; ++e) mk[e & 3] |= (v[e] > thr) ? (1u << e) : 0u;
+          uint32_t mask = (mk[0] | mk[1]) | (mk[2] | mk[3]);
           if (wild_set) mask = 0xffffffffu;
           const int r0 = part * 32;
           if (r0 + 32 > rows_ok) mask &= (rows_ok > r0) ? (0xffffffffu >> (32 - (rows_ok - r0))) : 0u;   // padded rows

@@ -82,7 +82,7 @@ struct Ctx {
   float wscale2[L_NUM] = {};      // its epilogue factor 1 / (activation scale * weight scale)
   int conv_tc_version = 2;        // 2 = conv_tc2.cu (default), 1 = conv_tc.cu (XFB_CONV_TC=1: A/B reference)
   int num_sms = 148;
-  bool b1_fuse = true;            // block1.0 recomputed inside block1.1 (XFB_B1_FUSE=0: materialise block1.0 like round 1)
+  bool b1_fuse = false;           // XFB_B1_FUSE=1: block1.0 recomputed inside block1.1 (measured: 0.212 ms vs 0.201 ms for the two kernels -- a loss, kept as an A/B option)
   struct TmapSlot { alignas(64) unsigned char blob[128]; const void* ptr; int B, H, W; };   // CUtensorMap of a layer's output + what it was encoded for
   TmapSlot tmap[L_NUM] = {};
   unsigned long long* t2_counters = nullptr;   // XFB_T2_DEBUG: [L_NUM][32] cycle counters of CTA 0 (conv_tc2.cu), printed at xfb_destroy
