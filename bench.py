@@ -460,10 +460,10 @@ def run_b200(args):
         traffic = None
         for tp in sorted((REPO / "profiles").glob("r*_dram_traffic_per_launch.json"), reverse=True):
             tj = json.loads(tp.read_text())
-            key = {"match_tile": "ms_kernel"}.get(name, name)
-            hits = [v for k, v in tj.items() if key in k]
+            keys = {"match_tile": ("mm_kernel<1>", "ms_kernel")}.get(name, (name,))
+            hits = [v for key in keys for k, v in tj.items() if key in k]
             if hits:
-                traffic = hits[0]
+                traffic = hits[0]["dram_bytes_per_launch"] if isinstance(hits[0], dict) else hits[0]
                 break
         shares = {k: round(v[0] / tot, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:8]}
         all_ms = {k: round(v[0] / PROF_BATCHES, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}

@@ -64,6 +64,11 @@ def test_real_orbvoc_shape():
     d = z["out_descriptors"][:200]
     leaf, nid = mo.bow_transform(d, v["node_desc"], v["child_start"], v["child_index"], v["L"], 4)
     assert np.all(v["is_leaf"][leaf] == 1) and np.all(nid > 0)
+    # the pin on the real vocabulary: word / node ids the reference's own DBoW2 returned for these descriptors (tools/pin_orbvoc.py)
+    g = np.load(Path(__file__).resolve().parent / "golden" / "dbow2_orbvoc_vga1000.npz")
+    d = np.ascontiguousarray(z["out_descriptors"][:1000], np.float32)
+    leaf, nid = mo.bow_transform(d, v["node_desc"], v["child_start"], v["child_index"], v["L"], int(g["meta"][4]))
+    assert np.array_equal(v["word_id"][leaf], g["leaf"][:, 0]) and np.array_equal(nid, g["leaf"][:, 1])
 
 
 # ---- the pin: the reference's OWN DBoW2 (thirdparty/DBoW2 compiled unchanged -> oracle/_ref/ref_dbow2) -------------------------

@@ -1,13 +1,13 @@
 #!/bin/bash
-# Round-end measurement on one B200 (run under gpurun): tests, smoke, bench, ncu launch list, ncu full captures, microbenchmarks.
-O=gpurun_out/final; mkdir -p $O
-timeout 200 python -m pytest tests -m gpu -q > $O/pytest.log 2>&1; echo "pytest rc=$?"; tail -2 $O/pytest.log
+# Round-end measurement on one B200 (run under gpurun): tests, smoke, both bench arms, HD config, ncu launch list, ncu full capture.
+O=gpurun_out/final2; mkdir -p $O
+timeout 900 python -m pytest tests -m gpu -q > $O/pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest.log | cut -c1-300
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $O/smoke.log
-timeout 300 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; echo "bench rc=$?"; cut -c1-600 $O/bench_n1.json
-timeout 100 python bench.py --contexts 1 --no-cpu-baseline > $O/bench_n1_ctx1.json 2> $O/bench_n1_ctx1.err; echo "bench ctx1 rc=$?"
-XFB_MS_DEBUG=0 timeout 60 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --contexts 1 2> $O/ms_debug.err > /dev/null; grep xfb $O/ms_debug.err
-timeout 60 tools/tmem_bench > $O/tmem_bench.txt 2>&1
-timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -s 111 -c 37 --csv --log-file $O/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --contexts 1 > $O/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:ms_kernel -s 2 -c 2 -o $O/ms_full python bench.py --steps 1 --warmup 1 --no-cpu-baseline --contexts 1 > $O/ncu_ms.log 2>&1; echo "ncu ms rc=$?"
-timeout 240 ncu --set full --clock-control none -k regex:"conv_tc_kernel|conv_small_kernel" -s 25 -c 25 -o $O/conv_full python bench.py --steps 1 --warmup 1 --no-cpu-baseline --contexts 1 > $O/ncu_conv.log 2>&1; echo "ncu conv rc=$?"
+timeout 400 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; echo "bench rc=$?"; cut -c1-400 $O/bench_n1.json
+timeout 400 python bench.py --impl reference > $O/bench_ref.json 2> $O/bench_ref.err; echo "bench ref rc=$?"; cut -c1-300 $O/bench_ref.json
+timeout 300 python bench.py --height 720 --width 1280 --chunks 32 --no-cpu-baseline > $O/bench_n1_hd.json 2> $O/bench_n1_hd.err; echo "bench hd rc=$?"; cut -c1-300 $O/bench_n1_hd.json
+timeout 200 python bench.py --contexts 1 --no-cpu-baseline --chunks 16 > $O/bench_n1_ctx1.json 2> $O/bench_n1_ctx1.err; echo "bench ctx1 rc=$?"; cut -c1-200 $O/bench_n1_ctx1.json
+timeout 200 python bench.py --contexts 3 --no-cpu-baseline --chunks 16 > $O/bench_n1_ctx3.json 2> $O/bench_n1_ctx3.err; echo "bench ctx3 rc=$?"; cut -c1-200 $O/bench_n1_ctx3.json
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --chunks 1 --steps 2 --warmup 3 --no-cpu-baseline --contexts 1 > $O/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+timeout 500 ncu --set full --clock-control none --import-source on -s 160 -c 40 -o $O/step_full python bench.py --chunks 1 --steps 1 --warmup 3 --no-cpu-baseline --contexts 1 > $O/ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la $O

@@ -44,8 +44,9 @@ def main():
     for (name, c), d in zip(kernels.items(), dem):
         if not any(c[w] for w in ("UTCHMMA", "LDTM", "UBLKCP", "UTMASTG", "STTM")):
             continue
-        short = re.sub(r"\(.*", "", d).replace("void xfb::", "").replace("xfb::", "")
-        print("| `%s` | %d | " % (short[:110], c["_n"]) + " | ".join(str(c[w]) if c[w] else "" for w in cols) + " |")
+        short = re.sub(r"\((?:int|bool)\)", "", d)
+        short = re.sub(r"\((?:xfb::|const |CUtensorMap).*$", "", short).replace("void xfb::", "").replace("xfb::", "")
+        print("| `%s` | %d | " % (short[:120], c["_n"]) + " | ".join(str(c[w]) if c[w] else "" for w in cols) + " |")
     tot = Counter()
     for c in kernels.values():
         tot.update(c)

@@ -127,6 +127,35 @@ __device__ __forceinline__ float mm_max32(const float* v) {
   return fmaxf(fmaxf(fmaxf(mg[0], mg[1]), fmaxf(mg[2], mg[3])), fmaxf(fmaxf(mg[4], mg[5]), fmaxf(mg[6], mg[7])));
 }
 // order-preserving float -> unsigned (0 is below every value)
+// Candidate mask of one 32-value slice: bit e = (v[e] > tau), possibly MORE bits than that (never fewer) when |tau| < 2^-60.
+// The slice maximum costs 16 alu-pipe instructions; a compare + bit insert costs 2.5 more per value on the same pipe
+// (FSETP, SEL, half an IADD3) while the fma pipe idles.  So MM_FMA_BITS of the 32 values take the fma pipe instead:
+//   s = saturate(fma(v, 2^100, -tau * 2^100))     1.0 when v > tau, 0.0 otherwise   (FFMA.SAT)
+//   acc = fma(s, 2^e, acc)                         acc starts at 2^23: integer sums < 2^23 are exact in the mantissa
+// fma(v, 2^100, -tau 2^100) is (v - tau) * 2^100 with ONE rounding, so its sign is exact; it is >= 1 whenever v > tau because
+// |tau| >= 2^-60 puts distinct values at least 2^-84 apart (tau closer to zero than that is replaced by -2^-60: a looser
+// bound, a superset of candidates, all of which are verified exactly later); |v|, |tau| < 2^18 here, no overflow.
+#ifndef XFB_MM_FMA_BITS
+#define XFB_MM_FMA_BITS 21
+#endif
+constexpr int MM_FMA_BITS = XFB_MM_FMA_BITS;      // 0: every compare on the alu pipe
+__device__ __forceinline__ uint32_t mm_mask32(const float* v, float tau) {
+  constexpr float BIG = 0x1p100f;
+  const float te = (fabsf(tau) < 0x1p-60f) ? -0x1p-60f : tau;
+  const float nt = -te * BIG;                              // -inf / +inf pass through: everything / nothing is a candidate
+  constexpr int H = (MM_FMA_BITS + 1) / 2;
+  float acc0 = 8388608.0f, acc1 = 8388608.0f;
+#pragma unroll
+  for (int e = 0; e < H; ++e) acc0 = fmaf(__saturatef(fmaf(v[e], BIG, nt)), (float)(1u << e), acc0);
+#pragma unroll
+  for (int e = H; e < MM_FMA_BITS; ++e) acc1 = fmaf(__saturatef(fmaf(v[e], BIG, nt)), (float)(1u << (e - H)), acc1);
+  uint32_t mk0 = 0u, mk1 = 0u;
+#pragma unroll
+  for (int e = MM_FMA_BITS; e < 32; e += 2) mk0 |= (v[e] > tau) ? (1u << e) : 0u;
+#pragma unroll
+  for (int e = MM_FMA_BITS + 1; e < 32; e += 2) mk1 |= (v[e] > tau) ? (1u << e) : 0u;
+  return (__float_as_uint(acc0) & 0x007fffffu) | ((__float_as_uint(acc1) & 0x007fffffu) << H) | (mk0 | mk1);
+}
 __device__ __forceinline__ unsigned int mm_ord(float u) {
   const unsigned int b = __float_as_uint(u);
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
@@ -417,10 +446,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
           const float tau = bound();
           mm_ld32(tq + (uint32_t)part * 32u, v);
           const float m = mm_max32(v);
-          uint32_t mk[4] = {0u, 0u, 0u, 0u};                     // four independent chains instead of one 32-step dependency
-#pragma unroll
-          for (int e = 0; e < 32; ++e) mk[e & 3] |= (v[e] > tau) ? (1u << e) : 0u;
-          uint32_t mask = (mk[0] | mk[1]) | (mk[2] | mk[3]);
+          uint32_t mask = mm_mask32(v, tau);
           if (wild && ok) mask = 0xffffffffu;
           const int j0 = k * MM_ROWS + part * 32;
           if (j0 + 32 > nB) mask &= (nB > j0) ? (0xffffffffu >> (32 - (nB - j0))) : 0u;     // padded columns
@@ -471,10 +497,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
 #pragma unroll 1
         for (int part = 0; part < 4; ++part) {
           mm_ld32(tq + (uint32_t)part * 32u, v);
-          uint32_t mk[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-          for (int e = 0; e < 32; ++e) mk[e & 3] |= (v[e] > thr) ? (1u << e) : 0u;
-          uint32_t mask = (mk[0] | mk[1]) | (mk[2] | mk[3]);
+          uint32_t mask = mm_mask32(v, thr);
           if (wild_set) mask = 0xffffffffu;
           const int r0 = part * 32;
           if (r0 + 32 > rows_ok) mask &= (rows_ok > r0) ? (0xffffffffu >> (32 - (rows_ok - r0))) : 0u;   // padded rows
