@@ -321,7 +321,7 @@ static int tc_match_frames(Ctx* c, const int32_t* pairs, int n_pairs, int init, 
     a.init = init; a.out_stride = K; a.out_stride_cols = K;
     a.nrm_max_A = a.nrm_max_B = c->tc_fnmax;
     a.col_g = c->mm_colg; a.col_k = c->mm_colk; a.pair_done = c->mm_done;
-    a.ms_counters = c->ms_counters;
+    a.ms_counters = c->ms_counters; a.ms_mode = c->ms_mode;
     for (int p = 0; p < np; ++p) { a.pairs[2 * p] = pairs[2 * (p0 + p)]; a.pairs[2 * p + 1] = pairs[2 * (p0 + p) + 1]; }
     auto at = [&](int i) { return o[i] ? o[i] + (size_t)p0 * K : nullptr; };
     a.best_idx = at(0); a.best_dist = at(1); a.second_dist = at(2); a.rev_idx = at(3); a.rev_dist = at(4);
@@ -422,7 +422,7 @@ int xfb_create(xfb_ctx** out, const void* weights_blob, size_t n, int device, in
       // bit 64 also counts survivors; the other bits switch kernel stages OFF for timing ablations (results are then WRONG), so they
       // are honoured only together with XFB_MS_DEBUG_ABLATE=1
       c->ms_mode = atoi(md) & (getenv("XFB_MS_DEBUG_ABLATE") ? ~0 : 64);
-      if ((e = cudaMalloc(&c->ms_counters, 256)) != cudaSuccess || (e = cudaMemset(c->ms_counters, 0, 256)) != cudaSuccess) { c->err = cudaGetErrorString(e); r = XFB_ERR_CUDA; break; }
+      if ((e = cudaMalloc(&c->ms_counters, 512)) != cudaSuccess || (e = cudaMemset(c->ms_counters, 0, 512)) != cudaSuccess) { c->err = cudaGetErrorString(e); r = XFB_ERR_CUDA; break; }
     }
     if (getenv("XFB_T2_DEBUG")) {   // profiling aid (conv_tc2.cu): per-role cycle counters of CTA 0, printed per layer at xfb_destroy
       if ((e = cudaMalloc(&c->t2_counters, L_NUM * 32 * 8)) != cudaSuccess || (e = cudaMemset(c->t2_counters, 0, L_NUM * 32 * 8)) != cudaSuccess) { c->err = cudaGetErrorString(e); r = XFB_ERR_CUDA; break; }
@@ -467,8 +467,8 @@ void xfb_destroy(xfb_ctx* c) {
     cudaFree(c->t2_counters);
   }
   if (c->ms_counters) {
-    unsigned long long h[32] = {};
-    cudaMemcpy(h, c->ms_counters, 256, cudaMemcpyDeviceToHost);
+    unsigned long long h[64] = {};
+    cudaMemcpy(h, c->ms_counters, 512, cudaMemcpyDeviceToHost);
     fprintf(stderr, "[xfb] match_stream counters: pushes %llu, verified %llu, overflow %llu\n", h[0], h[1], h[2]);
     const double n = h[13] ? (double)h[13] : 1.0;
     fprintf(stderr, "[xfb] CTA(0,0) cycles per launch: total %.0f | mma thread: wait A %.0f, wait full %.0f, wait acc-empty %.0f, loop %.0f | loader wait empty %.0f | "
@@ -476,9 +476,15 @@ void xfb_destroy(xfb_ctx* c) {
             h[12] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n, h[7] / n, h[8] / n, h[9] / n, h[10] / n, h[11] / n);
     if (h[30]) {
       const double m = (double)h[30];
-      fprintf(stderr, "[xfb] match_mutual CTA(0,0) cycles per launch: total %.0f | MMA lane loop end @%.0f | row warp: stream+bound end @%.0f, drain end @%.0f | "
+      fprintf(stderr, "[xfb] match_mutual CTA(7,3) cycles per launch: total %.0f | MMA lane loop end @%.0f | row warp: stream+bound end @%.0f, drain end @%.0f | "
               "column warp: stream end @%.0f, drain end @%.0f || all CTAs per launch: row entries %.0f verified %.0f, column entries %.0f verified %.0f\n",
               h[20] / m, h[25] / m, h[21] / m, h[22] / m, h[23] / m, h[24] / m, h[26] / m, h[27] / m, h[28] / m, h[29] / m);
+      const char* nm[4] = {"row overflow", "row final", "column overflow", "column final"};
+      for (int k = 0; k < 4; ++k) {
+        const unsigned long long* d = h + 32 + 5 * k;
+        fprintf(stderr, "[xfb]   %s drains of ONE warp of that CTA, per launch: calls %.2f, entries in %.0f, kept %.0f, filter cycles %.0f, verify cycles %.0f\n",
+                nm[k], d[0] / m, d[1] / m, d[2] / m, d[3] / m, d[4] / m);
+      }
     }
     fprintf(stderr, "[xfb] CTA(0,0) mma thread: cycles in tcgen05.mma issue %.0f, in tcgen05.commit %.0f, in tcgen05.fence %.0f, loop tail %.0f\n", h[14] / n, h[15] / n, h[16] / n, h[17] / n);
   }

@@ -52,44 +52,58 @@ constexpr uint32_t MM_IDESC = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 
 
 size_t mm_image_bytes(int rows_padded) { return (size_t)(rows_padded / MM_ROWS) * MM_BLK_BYTES; }
 
-// ---- operand images: one thread per (row, 4 consecutive k); rows >= n (per set) are zero with the padding tails ----------
+// ---- operand images: one CTA per 128-descriptor block.  The rows come in as coalesced float4 (16 lanes per row), the fp16 image is
+// assembled in shared memory in its final K-major layout and leaves as ONE contiguous 22 KB run of 16-byte stores (the first version
+// wrote 8 scattered bytes per thread: 51 us per 32 x 4096 descriptors, four times the byte time).  Rows >= n (per set) are zero with
+// the padding tails.
 __global__ void __launch_bounds__(256) mm_prep_kernel(const float* desc, size_t set_stride, const int32_t* n_dev, int n_host, int rows_padded,
                                                       unsigned char* img, size_t img_set_bytes, float* nrm, float* nrm_max) {
-  const int set = blockIdx.y;
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;   // row * 16 + kq
-  const int row = g >> 4, kq = g & 15;
-  if (row >= rows_padded) return;
+  __shared__ __align__(16) unsigned char simg[MM_BLK_BYTES];
+  __shared__ unsigned int s_max;
+  const int set = blockIdx.y, blk = blockIdx.x, t = threadIdx.x;
   const int n = n_dev ? min(n_host, n_dev[set]) : n_host;
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (row < n) v = *reinterpret_cast<const float4*>(desc + (size_t)set * set_stride + (size_t)row * 64 + kq * 4);
-  const int blk = row >> 7, r = row & 127;
-  unsigned char* base = img + (size_t)set * img_set_bytes + (size_t)blk * MM_BLK_BYTES;
-  const size_t roff = (size_t)(r >> 3) * MM_SBO + (size_t)(r & 7) * 16;
-  const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
-  uint2 pk;
-  pk.x = *reinterpret_cast<const unsigned int*>(&h01);
-  pk.y = *reinterpret_cast<const unsigned int*>(&h23);
-  *reinterpret_cast<uint2*>(base + (size_t)(kq >> 1) * MM_LBO + roff + (size_t)(kq & 1) * 8) = pk;
-  double s = (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+  if (t == 0) s_max = 0u;
+  __syncthreads();
+  const int kq = t & 15;
+  unsigned int my_max = 0u;
+#pragma unroll 2
+  for (int it = 0; it < MM_ROWS / 16; ++it) {
+    const int r = it * 16 + (t >> 4), row = blk * MM_ROWS + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < n) v = *reinterpret_cast<const float4*>(desc + (size_t)set * set_stride + (size_t)row * 64 + kq * 4);
+    const size_t roff = (size_t)(r >> 3) * MM_SBO + (size_t)(r & 7) * 16;
+    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const unsigned int*>(&h01);
+    pk.y = *reinterpret_cast<const unsigned int*>(&h23);
+    *reinterpret_cast<uint2*>(simg + (size_t)(kq >> 1) * MM_LBO + roff + (size_t)(kq & 1) * 8) = pk;
+    double s = (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 16);
-  if (kq == 0) {
-    const float nf = (float)s;
-    nrm[(size_t)set * rows_padded + row] = (row < n) ? nf : CUDART_INF_F;
-    if (s > 0.0 && row < n) atomicMax(reinterpret_cast<unsigned int*>(nrm_max + set), __float_as_uint(nf));
-    float x = (row < n) ? -0.5f * nf : MM_PAD_TAIL;       // -|x|^2/2 = p1 + p2 + p3 (fp16 pieces, residual 2^-33)
-    const __half p1 = __float2half_rn(x);
-    x -= __half2float(p1);
-    const __half p2 = __float2half_rn(x);
-    x -= __half2float(p2);
-    const __half p3 = __float2half_rn(x);
-    const unsigned int p12 = (unsigned int)__half_as_ushort(p1) | ((unsigned int)__half_as_ushort(p2) << 16);
-    const unsigned int p3u = (unsigned int)__half_as_ushort(p3);
-    // row-role tail [p1 p2 p3 1 | 1 1 0 0], column-role tail [1 1 1 p1 | p2 p3 0 0]; 1.0 = 0x3C00
-    *reinterpret_cast<uint4*>(base + 8 * MM_LBO + roff) = make_uint4(p12, p3u | 0x3C000000u, 0x3C003C00u, 0u);
-    *reinterpret_cast<uint4*>(base + 9 * MM_LBO + roff) = make_uint4(0x3C003C00u, 0x00003C00u | (p12 << 16), (p12 >> 16) | (p3u << 16), 0u);
-    *reinterpret_cast<uint4*>(base + 10 * MM_LBO + roff) = make_uint4(0u, 0u, 0u, 0u);
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 16);
+    if (kq == 0) {
+      const float nf = (float)s;
+      nrm[(size_t)set * rows_padded + row] = (row < n) ? nf : CUDART_INF_F;
+      if (s > 0.0 && row < n) my_max = max(my_max, __float_as_uint(nf));
+      float x = (row < n) ? -0.5f * nf : MM_PAD_TAIL;       // -|x|^2/2 = p1 + p2 + p3 (fp16 pieces, residual 2^-33)
+      const __half p1 = __float2half_rn(x);
+      x -= __half2float(p1);
+      const __half p2 = __float2half_rn(x);
+      x -= __half2float(p2);
+      const __half p3 = __float2half_rn(x);
+      const unsigned int p12 = (unsigned int)__half_as_ushort(p1) | ((unsigned int)__half_as_ushort(p2) << 16);
+      const unsigned int p3u = (unsigned int)__half_as_ushort(p3);
+      // row-role tail [p1 p2 p3 1 | 1 1 0 0], column-role tail [1 1 1 p1 | p2 p3 0 0]; 1.0 = 0x3C00
+      *reinterpret_cast<uint4*>(simg + 8 * MM_LBO + roff) = make_uint4(p12, p3u | 0x3C000000u, 0x3C003C00u, 0u);
+      *reinterpret_cast<uint4*>(simg + 9 * MM_LBO + roff) = make_uint4(0x3C003C00u, 0x00003C00u | (p12 << 16), (p12 >> 16) | (p3u << 16), 0u);
+      *reinterpret_cast<uint4*>(simg + 10 * MM_LBO + roff) = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
+  if (my_max) atomicMax(&s_max, my_max);
+  __syncthreads();
+  uint4* dst = reinterpret_cast<uint4*>(img + (size_t)set * img_set_bytes + (size_t)blk * MM_BLK_BYTES);
+  const uint4* src = reinterpret_cast<const uint4*>(simg);
+  for (int i = t; i < MM_BLK_BYTES / 16; i += 256) dst[i] = src[i];
+  if (t == 0 && s_max) atomicMax(reinterpret_cast<unsigned int*>(nrm_max + set), s_max);
 }
 
 __device__ __forceinline__ void mm_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
@@ -186,7 +200,7 @@ __device__ __noinline__ int mm_exact_distance_seq(const float* arow, const float
 // the integer -- IS the reference's; otherwise (probability ~ 2^-15) the sequential order decides.
 __device__ __forceinline__ int mm_exact_distance(const float* arow, const float* brow) {
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll 4
+#pragma unroll 8
   for (int kq = 0; kq < 16; ++kq) {
     const float4 x = *reinterpret_cast<const float4*>(arow + kq * 4);
     const float4 b = *reinterpret_cast<const float4*>(brow + kq * 4);
@@ -207,53 +221,116 @@ __device__ __forceinline__ int mm_exact_distance(const float* arow, const float*
 // times per CTA).  Two phases: (1) filter every entry against the current bound (rows: the row's candidate bound; columns: the
 // largest estimate ANY CTA has seen for the column) and compact the survivors in place (ballot-based, warp-uniform), (2) verify
 // the survivors 32 at a time, one per lane -- dense batches: the fp64 chain costs the same whether 3 or 32 lanes run it.
-struct MmDrain {
-  unsigned long long* q; const float* sTau; const float* rawA; const float* rawB; unsigned long long* sK1; unsigned long long* sK2;
-  const unsigned int* colG; unsigned long long* colK; unsigned long long* dbgc;
-  float margin_col; unsigned int init_u; int row0, group; bool dir2, wild;
+// ---- explicit shared-space accesses for the out-of-line drain (a generic pointer costs an address-space check per access) ----
+__device__ __forceinline__ unsigned long long mm_lds64(uint32_t a) { unsigned long long v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void mm_sts64(uint32_t a, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ float mm_ldsf(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ unsigned int mm_lds32(uint32_t a) { unsigned int v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ unsigned long long mm_atoms_min64(uint32_t a, unsigned long long v) {
+  unsigned long long o;
+  asm volatile("atom.shared.min.u64 %0, [%1], %2;" : "=l"(o) : "r"(a), "l"(v) : "memory");
+  return o;
+}
+
+// One warp empties its candidate queue: (1) re-filter every entry against the bound as it stands now, compacting the queue in place;
+// (2) verify the survivors exactly, FOUR LANES PER PAIR (16 dimensions each: all of a lane's 8 row loads are in flight at once, a
+// round of 8 pairs costs one memory latency; one lane per pair needed 32 loads per lane, i.e. 4+ dependent batches per round:
+// 9.6 k clk per round measured) and merge the exact keys.  Everything arrives in registers (the first version passed a struct by
+// reference: ~10 local-memory loads per loop iteration).  flags: 1 final, 2 column direction, 4 wild (verify everything).
+// tau_s: shared address of the row bounds to filter with; colg_s: shared snapshot of the column maxima or 0 (then colG, global);
+// c_s: shared address of the CTA's drain constants (MmShared::dc, see MmDrainConst).
+struct MmDrainConst {      // 64 bytes, written once per CTA
+  const unsigned int* colG; unsigned long long* colK; const float* rawA0; const float* rawB; unsigned long long* dbg;
+  float margin_col; unsigned int init_u; int row0; uint32_t k1_s; unsigned long long pad;
 };
-__device__ __noinline__ void mm_drain(const MmDrain& c, int qn, bool final, int lane) {
+static_assert(sizeof(MmDrainConst) == 64, "drain constants");
+__device__ __noinline__ void mm_drain(uint32_t q_s, int qn, int flags, int lane, uint32_t tau_s, uint32_t colg_s, uint32_t c_s) {
+  const unsigned int* colG = reinterpret_cast<const unsigned int*>(mm_lds64(c_s));
+  unsigned long long* colK = reinterpret_cast<unsigned long long*>(mm_lds64(c_s + 8));
+  const float* rawA0 = reinterpret_cast<const float*>(mm_lds64(c_s + 16));
+  const float* rawB = reinterpret_cast<const float*>(mm_lds64(c_s + 24));
+  unsigned long long* dbg = reinterpret_cast<unsigned long long*>(mm_lds64(c_s + 32));
+  const float margin_col = mm_ldsf(c_s + 40);
+  const unsigned int init_u = mm_lds32(c_s + 44);
+  const int row0 = (int)mm_lds32(c_s + 48);
+  const uint32_t k1_s = mm_lds32(c_s + 52), k2_s = k1_s + 8u * MM_ROWS;
+  unsigned long long* const cnt = (flags & 8) ? dbg : nullptr;        // entry counting (perturbs the timing: only on request)
+  unsigned long long* const tdbg = (flags & 16) ? dbg : nullptr;      // cycle counters of one warp per direction of one CTA
   __syncwarp();
-  unsigned long long* q = c.q;
+  const long long t_in = clock64();
+  const bool dir2 = flags & 2, wild = flags & 4;
   int nw = 0;
   for (int base = 0; base < qn; base += 32) {
     const int i = base + lane;
     unsigned long long ent = 0;
     bool keep = false;
     if (i < qn) {
-      ent = q[i];
-      const int r = (int)((ent >> 24) & 0x7full), j = (int)(ent & 0xffffffull);
+      ent = mm_lds64(q_s + 8u * (uint32_t)i);
+      const uint32_t r = (uint32_t)(ent >> 24) & 0x7fu, j = (uint32_t)ent & 0xffffffu;
       const float ub = __uint_as_float((unsigned int)(ent >> 32));        // upper bound of the pair's u
-      if (c.dbgc) atomicAdd(c.dbgc + (c.dir2 ? 28 : 26), 1ull);
-      if (!c.dir2) keep = c.wild || ub > (final ? c.sTau[r] : c.sTau[c.group * MM_ROWS + r]);
-      else keep = c.wild || ub >= mm_unord(__ldcg(c.colG + j)) - c.margin_col;
+      if (!dir2) keep = wild || ub > mm_ldsf(tau_s + 4u * r);
+      else keep = wild || ub >= mm_unord(colg_s ? mm_lds32(colg_s + 4u * j) : __ldcg(colG + j)) - margin_col;
     }
     const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-    if (keep) q[nw + __popc(bal & ((1u << lane) - 1u))] = ent;            // nw <= base: never ahead of the entries still to be read
+    if (keep) mm_sts64(q_s + 8u * (uint32_t)(nw + __popc(bal & ((1u << lane) - 1u))), ent);   // nw <= base: never ahead of the entries still to be read
     nw += __popc(bal);
     __syncwarp();
   }
-  for (int i = lane; i < nw; i += 32) {
-    const unsigned long long ent = q[i];
+  if (cnt && lane == 0) { atomicAdd(cnt + (dir2 ? 28 : 26), (unsigned long long)qn); atomicAdd(cnt + (dir2 ? 29 : 27), (unsigned long long)nw); }
+  const long long t_f = clock64();
+  const int sub = lane & 3, slot = lane >> 2;          // 4 lanes per pair, 8 pairs per round
+  for (int base = 0; base < nw; base += 8) {
+    const int i = base + slot;
+    const bool live = i < nw;
+    const unsigned long long ent = mm_lds64(q_s + 8u * (uint32_t)(live ? i : 0));
     const int r = (int)((ent >> 24) & 0x7full), j = (int)(ent & 0xffffffull);
-    if (c.dbgc) atomicAdd(c.dbgc + (c.dir2 ? 29 : 27), 1ull);
-    const int D = mm_exact_distance(c.rawA + (size_t)(c.row0 + r) * 64, c.rawB + (size_t)j * 64);
-    if ((unsigned int)D < c.init_u) {
-      if (!c.dir2) {
-        const unsigned long long key = ((unsigned long long)(unsigned int)D << 32) | (unsigned int)j;
-        const unsigned long long old = atomicMin(&c.sK1[r], key);
-        atomicMin(&c.sK2[r], max(old, key));
-      } else {
-        atomicMin(c.colK + j, ((unsigned long long)(unsigned int)D << 32) | (unsigned int)(c.row0 + r));
+    const float* arow = rawA0 + (size_t)r * 64 + sub * 16;
+    const float* brow = rawB + (size_t)j * 64 + sub * 16;
+    float4 xa[4], xb[4];
+#pragma unroll
+    for (int kq = 0; kq < 4; ++kq) { xa[kq] = __ldg(reinterpret_cast<const float4*>(arow) + kq); xb[kq] = __ldg(reinterpret_cast<const float4*>(brow) + kq); }
+    double acc = 0.0;
+#pragma unroll
+    for (int kq = 0; kq < 4; ++kq) {
+      float d;
+      d = xa[kq].x - xb[kq].x; acc = fma((double)d, (double)d, acc);
+      d = xa[kq].y - xb[kq].y; acc = fma((double)d, (double)d, acc);
+      d = xa[kq].z - xb[kq].z; acc = fma((double)d, (double)d, acc);
+      d = xa[kq].w - xb[kq].w; acc = fma((double)d, (double)d, acc);
+    }
+    // every square of an fp32 difference is EXACT in fp64, so this order differs from the reference's index order by < 2^-45
+    // relative; if rounding to float gives the same value at both ends of a 2^-40 band around the sum, that float -- hence the
+    // integer -- IS the reference's; otherwise (probability ~ 2^-15) the sequential order decides.
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    const float f = __double2float_rn(acc);
+    const float flo = __double2float_rn(acc * (1.0 - 0x1p-40)), fhi = __double2float_rn(acc * (1.0 + 0x1p-40));
+    int D = (int)(f * 512.0f);
+    if (live && sub == 0) {
+      if (flo != fhi) D = mm_exact_distance_seq(rawA0 + (size_t)r * 64, rawB + (size_t)j * 64);
+      if ((unsigned int)D < init_u) {
+        if (!dir2) {
+          const unsigned long long key = ((unsigned long long)(unsigned int)D << 32) | (unsigned int)j;
+          const unsigned long long old = mm_atoms_min64(k1_s + 8u * (uint32_t)r, key);
+          mm_atoms_min64(k2_s + 8u * (uint32_t)r, max(old, key));
+        } else {
+          atomicMin(colK + j, ((unsigned long long)(unsigned int)D << 32) | (unsigned int)(row0 + r));
+        }
       }
     }
   }
   __syncwarp();
+  if (tdbg && lane == 0) {     // slots 32.. : [dir][final] x (calls, entries in, entries kept, filter cycles, verify cycles)
+    unsigned long long* d = tdbg + 32 + ((dir2 ? 2 : 0) + ((flags & 1) ? 1 : 0)) * 5;
+    atomicAdd(d, 1ull); atomicAdd(d + 1, (unsigned long long)qn); atomicAdd(d + 2, (unsigned long long)nw);
+    atomicAdd(d + 3, (unsigned long long)(t_f - t_in)); atomicAdd(d + 4, (unsigned long long)(clock64() - t_f));
+  }
 }
 
 struct MmShared {
   uint64_t bar_a, bar_full[MM_STAGES], bar_empty[MM_STAGES], bar_accf1[2], bar_acce1[2], bar_accf2[2], bar_acce2[2];
   uint32_t tmem, flag;
+  MmDrainConst dc;
 };
 
 template <bool MUTUAL>
@@ -274,7 +351,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
   // XFB_MS_DEBUG: counters [20..31] = per-launch sums over CTA (0,0): cycles (total, row warp stream end / drain end, column warp stream end /
   // drain end, MMA lane loop) and, over ALL CTAs, queue entries / exact verifications per direction
   unsigned long long* dbgc = a.ms_counters;
-  const bool dbg0 = dbgc != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  const bool dbg0 = dbgc != nullptr && blockIdx.x == 7 % gridDim.x && blockIdx.y == 3 % gridDim.y;   // a CTA in the middle of the launch
   const long long t_start = clock64();
   const int setA = a.pairs[2 * pair], setB = a.pairs[2 * pair + 1];
   const int nA = a.nA_dev ? min(a.nA_host, a.nA_dev[setA]) : a.nA_host;
@@ -382,10 +459,19 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
     const float e_col = 1.05f * sqrtf(nam * nbm) + 0.02f * (nam + nbm + 1.0f);
     const float margin_col = wild_set ? CUDART_INF_F : (2.0f * e_col + 1.0f) * (1.0f / 1024.0f);
 
-    MmDrain dc;
-    dc.q = q; dc.sTau = sTau; dc.rawA = rawA; dc.rawB = rawB; dc.sK1 = sK1; dc.sK2 = sK2; dc.colG = colG; dc.colK = colK; dc.dbgc = dbgc;
-    dc.margin_col = margin_col; dc.init_u = init_u; dc.row0 = row0; dc.group = group; dc.dir2 = dir2; dc.wild = wild_set;
-    auto drain = [&](bool final) { mm_drain(dc, qn, final, lane); qn = 0; };
+    const uint32_t q_s = smem_u32(q), tau_s = smem_u32(sTau), c_s = smem_u32(&sh->dc);
+    uint32_t colg_s = 0;                           // shared snapshot of the column maxima (column direction, final drain)
+    if (lane == 0) {                               // every warp writes the same constants: no CTA barrier needed before the first overflow drain
+      MmDrainConst& k = sh->dc;
+      k.colG = colG; k.colK = colK; k.rawA0 = rawA + (size_t)row0 * 64; k.rawB = rawB; k.dbg = dbgc;
+      k.margin_col = margin_col; k.init_u = init_u; k.row0 = row0; k.k1_s = smem_u32(sK1);
+    }
+    __syncwarp();
+    const int dflags = (dir2 ? 2 : 0) | (wild_set ? 4 : 0) | ((a.ms_mode & 64) && dbgc ? 8 : 0) | ((dbg0 && (ew == 0 || ew == 8)) ? 16 : 0);
+    auto drain = [&](bool final) {
+      mm_drain(q_s, qn, dflags | (final ? 1 : 0), lane, final ? tau_s : tau_s + 4u * (uint32_t)(group * MM_ROWS), final ? colg_s : 0u, c_s);
+      qn = 0;
+    };
     // warp-uniform append (no atomics): every round, each lane with candidates left contributes its lowest one
     // entry e of the mask is the pair (row_base + e * row_step, col_base + e * col_step)
     auto append = [&](uint32_t mask, int row_base, int row_step, int col_base, int col_step, float ub) {
@@ -509,6 +595,17 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
         if (lane == 0) mbar_arrive(&sh->bar_acce2[group]);
       }
       if (dbg0 && ew == 8 && lane == 0) atomicAdd(dbgc + 23, (unsigned long long)(clock64() - t_start));
+      // The final filter compares every queued row with the pair's per-column maximum over ALL CTAs so far: a dependent L2 load per
+      // 32 entries (27 k clk for ~550 entries, measured).  The stream is over -- both groups are past their last accumulator, so
+      // every MMA has read its column block -- and the ring of column blocks is free: park a snapshot of the maxima there (any
+      // older value is a valid, merely looser, bound).
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      if (a.rows_padded_B * 4 <= MM_STAGES * MM_BLK_BYTES) {
+        unsigned int* sG = reinterpret_cast<unsigned int*>(sB0);
+        for (int j = (ew - 8) * 32 + lane; j < a.rows_padded_B; j += 256) sG[j] = __ldcg(colG + j);
+        colg_s = smem_u32(sG);
+      }
+      asm volatile("bar.sync 3, 256;" ::: "memory");
       drain(true);
       if (dbg0 && ew == 8 && lane == 0) atomicAdd(dbgc + 24, (unsigned long long)(clock64() - t_start));
     }
@@ -564,7 +661,7 @@ static_assert(MM_SMEM <= 227 * 1024, "shared memory budget");
 
 cudaError_t launch_mm_prep(Ctx* c, const float* desc, size_t set_stride, int n_sets, const int32_t* n_dev, int n_host, int rows_padded,
                            void* img, size_t img_set_bytes, float* nrm, float* nrm_max) {
-  dim3 grid((rows_padded * 16 + 255) / 256, n_sets);
+  dim3 grid(rows_padded / MM_ROWS, n_sets);
   cudaError_t e0 = cudaMemsetAsync(nrm_max, 0, (size_t)n_sets * 4, c->stream);
   if (e0 != cudaSuccess) return e0;
   prof_begin(c, P_MATCH_PREP);

@@ -46,75 +46,143 @@ __device__ __forceinline__ float bilinear1(const float* map, int mh, int mw, flo
   return bilerp4(nw, ne, sw, se, __fmul_rn(s, e), __fmul_rn(s, w), __fmul_rn(n, e), __fmul_rn(n, w));
 }
 
-constexpr int NMS_T = 16;    // 256-thread CTAs (16 x 16) ...
-constexpr int NMS_NX = 4;    // ... that each sweep a 64 x 16 pixel strip: 4x fewer, 4x longer CTAs than one 16 x 16 tile each
-                             // (the kernel is launch- / tile-load-latency bound, not bandwidth bound)
-__global__ void __launch_bounds__(NMS_T * NMS_T) nms_score_kernel(const float* k1h, const float* h1, int H, int W, float thr,
-                                                                  u64* cand, int* cand_count) {
-  constexpr int TW = NMS_T * NMS_NX;
-  __shared__ float tile[NMS_T + 4][TW + 4];
-  const int b = blockIdx.z;
+// 64 x 16 output pixels per 256-thread CTA.  Three phases, each with every lane busy:
+//   1. the (64 + 8) x (16 + 4) halo tile comes in as aligned float4 (x0 - 4 .. x0 + 67);
+//   2. SEPARABLE 5x5 maximum: a thread owns 4 consecutive columns -- horizontal 5-maxima of all 20 rows into shared memory (3 LDS.128
+//      + 9 FMNMX per 4 values), then the vertical 5-maximum of its 4 output pixels (6 LDS.128); a pixel with x == max && x > thr goes
+//      onto a shared-memory list (about one pixel in 30);
+//   3. the reliability score (two IEEE divisions per coordinate, a bilinear tap: ~300 instructions) is computed for the LISTED pixels
+//      only, one per thread -- the round-1 kernel ran that path divergently in every warp that held a maximum (70 M warp
+//      instructions per 32 VGA frames, 92 us; ncu source view, profiles/r02_step_ncu_full_table.md).
+// The CTA appends its keys with ONE atomic on the frame's counter; the order inside the list is irrelevant, the key sorts.
+constexpr int NMS_TW = 64, NMS_TH = 16, NMS_NT = 256;
+constexpr int NMS_IW = NMS_TW + 8, NMS_IH = NMS_TH + 4;
+__global__ void __launch_bounds__(NMS_NT) nms_score_kernel(const float* k1h, const float* h1, int H, int W, float thr,
+                                                           u64* cand, int* cand_count) {
+  __shared__ __align__(16) float sbuf[NMS_IH * NMS_IW + NMS_IH * NMS_TW];
+  float (*tin)[NMS_IW] = reinterpret_cast<float (*)[NMS_IW]>(sbuf);
+  float (*hmx)[NMS_TW] = reinterpret_cast<float (*)[NMS_TW]>(sbuf + NMS_IH * NMS_IW);
+  __shared__ unsigned short s_list[NMS_TW * NMS_TH];
+  __shared__ int s_n, s_nkeys, s_base;
+  u64* s_keys = reinterpret_cast<u64*>(sbuf);                // [<= 1024] reuses the two tiles (5760 + 5120 B >= 8192 B) after phase 2
+  static_assert(sizeof(float) * NMS_IH * NMS_IW % 16 == 0 && sizeof(sbuf) >= 8 * NMS_TW * NMS_TH, "key buffer");
+  const int b = blockIdx.z, t = threadIdx.x;
   const float* img = k1h + (size_t)b * H * W;
-  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * NMS_T;
-  const int tid = threadIdx.y * NMS_T + threadIdx.x;
-  for (int i = tid; i < (NMS_T + 4) * (TW + 4); i += NMS_T * NMS_T) {
-    const int ty = i / (TW + 4), tx = i - ty * (TW + 4);
-    const int gy = y0 + ty - 2, gx = x0 + tx - 2;
-    tile[ty][tx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? img[(size_t)gy * W + gx] : -CUDART_INF_F;
-  }
-  __syncthreads();
-  __shared__ int s_cnt[NMS_NX * 8];   // candidates per (sub-tile, warp), then their exclusive prefix
-  __shared__ int s_base;
-  const int lane = tid & 31, wrp = tid >> 5;
-  u64 keys[NMS_NX];
-  unsigned int ballots[NMS_NX];
-#pragma unroll
-  for (int sx = 0; sx < NMS_NX; ++sx) {
-    const int lx = sx * NMS_T + threadIdx.x;   // column inside the strip
-    const int x = x0 + lx, y = y0 + threadIdx.y;
-    u64 key = 0;   // 0 = not a candidate (a real key has score bits > 0)
-    if (x < W && y < H) {
-      const float v = tile[threadIdx.y + 2][lx + 2];
-      if (v > thr) {
-        float m = v;
-#pragma unroll
-        for (int dy = 0; dy < 5; ++dy)
-#pragma unroll
-          for (int dx = 0; dx < 5; ++dx) m = fmaxf(m, tile[threadIdx.y + dy][lx + dx]);
-        if (v == m && !(x == 0 && y == 0)) {   // (0,0) is masked to -1 by the reference, never valid
-          // nearest(K1h)(kp): grid_sample nearest at full resolution (drops the last row / column)
-          const float nx = nearbyintf(grid_src(x, W, W)), ny = nearbyintf(grid_src(y, H, H));
-          float sn = 0.f;
-          if (nx >= 0.f && nx < (float)W && ny >= 0.f && ny < (float)H) sn = img[(size_t)(int)ny * W + (int)nx];
-          const int mh = H >> 3, mw = W >> 3;
-          const float sb = bilinear1(h1 + (size_t)b * mh * mw, mh, mw, grid_src(x, W, mw), grid_src(y, H, mh));
-          const float score = __fmul_rn(sn, sb);
-          if (score > 0.f) {                   // `valid = scores > 0`, src/XFextractor.cc:313
-            const unsigned int lin = (unsigned int)(y * W + x);
-            key = ((u64)__float_as_uint(score) << 32) | (u64)(0xFFFFFFFFu - lin);
-          }
-        }
+  const int x0 = blockIdx.x * NMS_TW, y0 = blockIdx.y * NMS_TH;
+  if (t == 0) { s_n = 0; s_nkeys = 0; }
+  // ---- 1. halo tile ----
+  const bool vec = (W & 3) == 0;
+  for (int i = t; i < NMS_IH * (NMS_IW / 4); i += NMS_NT) {
+    const int r = i / (NMS_IW / 4), c4 = i - r * (NMS_IW / 4);
+    const int gy = y0 - 2 + r, gx = x0 - 4 + 4 * c4;
+    float4 v = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+    if (gy >= 0 && gy < H) {
+      if (vec && gx >= 0 && gx + 3 < W) v = *reinterpret_cast<const float4*>(img + (size_t)gy * W + gx);
+      else {
+        const float* row = img + (size_t)gy * W;
+        if (gx >= 0 && gx < W) v.x = row[gx];
+        if (gx + 1 >= 0 && gx + 1 < W) v.y = row[gx + 1];
+        if (gx + 2 >= 0 && gx + 2 < W) v.z = row[gx + 2];
+        if (gx + 3 >= 0 && gx + 3 < W) v.w = row[gx + 3];
       }
     }
-    keys[sx] = key;
-    ballots[sx] = __ballot_sync(0xffffffffu, key != 0);
-    if (lane == 0) s_cnt[sx * 8 + wrp] = __popc(ballots[sx]);
+    *reinterpret_cast<float4*>(&tin[r][4 * c4]) = v;
   }
   __syncthreads();
-  // CTA-aggregated append: ONE atomic per CTA on the frame's counter (the 32 per-frame counters share a cache line, so
-  // per-warp atomics of the whole batch serialise on it); the order inside the list is irrelevant, the key sorts
-  if (tid == 0) {
-    int total = 0;
-    for (int i = 0; i < NMS_NX * 8; ++i) { const int n = s_cnt[i]; s_cnt[i] = total; total += n; }
-    s_base = total ? atomicAdd(cand_count + b * XFB_TICKET_STRIDE, total) : 0;
+  // ---- 2a. horizontal 5-maxima: hmx[r][x] = max tin[r][x + 2 .. x + 6]  (tile column = x + 4) ----
+  for (int i = t; i < NMS_IH * (NMS_TW / 4); i += NMS_NT) {
+    const int r = i / (NMS_TW / 4), xg = i - r * (NMS_TW / 4);
+    const float4 p = *reinterpret_cast<const float4*>(&tin[r][4 * xg]);
+    const float4 q = *reinterpret_cast<const float4*>(&tin[r][4 * xg + 4]);
+    const float4 u = *reinterpret_cast<const float4*>(&tin[r][4 * xg + 8]);
+    // columns 4xg+2 .. 4xg+9 = p.z p.w q.x q.y q.z q.w u.x u.y
+    const float c = fmaxf(fmaxf(q.x, q.y), q.z);             // shared by outputs 0 and 1 (+ q.w: by 1 and 2 ...)
+    float4 o;
+    o.x = fmaxf(fmaxf(p.z, p.w), c);
+    o.y = fmaxf(fmaxf(p.w, q.w), c);
+    const float d = fmaxf(fmaxf(q.y, q.z), q.w);
+    o.z = fmaxf(fmaxf(q.x, u.x), d);
+    o.w = fmaxf(fmaxf(u.x, u.y), d);
+    *reinterpret_cast<float4*>(&hmx[r][4 * xg]) = o;
   }
   __syncthreads();
+  // ---- 2b. vertical 5-maximum of this thread's 4 pixels, candidate test ----
+  {
+    const int ty = t >> 4, xg = t & 15;
+    const float4 v = *reinterpret_cast<const float4*>(&tin[ty + 2][4 * xg + 4]);
+    float4 m = *reinterpret_cast<const float4*>(&hmx[ty][4 * xg]);
 #pragma unroll
-  for (int sx = 0; sx < NMS_NX; ++sx)
-    if (keys[sx] != 0) cand[(size_t)b * H * W + s_base + s_cnt[sx * 8 + wrp] + __popc(ballots[sx] & ((1u << lane) - 1u))] = keys[sx];
+    for (int dy = 1; dy < 5; ++dy) {
+      const float4 h = *reinterpret_cast<const float4*>(&hmx[ty + dy][4 * xg]);
+      m.x = fmaxf(m.x, h.x); m.y = fmaxf(m.y, h.y); m.z = fmaxf(m.z, h.z); m.w = fmaxf(m.w, h.w);
+    }
+    const int y = y0 + ty, xb = x0 + 4 * xg;
+    const float vv[4] = {v.x, v.y, v.z, v.w}, mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int x = xb + j;
+      // x == local_max && x > thr (:236-240); (0,0) is masked to -1 by the reference, never valid
+      if (vv[j] > thr && vv[j] == mm[j] && x < W && y < H && !(x == 0 && y == 0)) s_list[atomicAdd(&s_n, 1)] = (unsigned short)((ty << 6) | (4 * xg + j));
+    }
+  }
+  __syncthreads();
+  // ---- 3. scores of the listed pixels, one per thread ----
+  const int n = s_n;
+  for (int i0 = 0; i0 < n; i0 += NMS_NT) {          // (n <= 256 except on plateaus)
+    const int i = i0 + t;
+    u64 key = 0;   // 0 = not a candidate (a real key has score bits > 0)
+    if (i < n) {
+      const int e = s_list[i];
+      const int x = x0 + (e & 63), y = y0 + (e >> 6);
+      // nearest(K1h)(kp): grid_sample nearest at full resolution (drops the last row / column)
+      const float nx = nearbyintf(grid_src(x, W, W)), ny = nearbyintf(grid_src(y, H, H));
+      float sn = 0.f;
+      if (nx >= 0.f && nx < (float)W && ny >= 0.f && ny < (float)H) sn = img[(size_t)(int)ny * W + (int)nx];
+      const int mh = H >> 3, mw = W >> 3;
+      const float sb = bilinear1(h1 + (size_t)b * mh * mw, mh, mw, grid_src(x, W, mw), grid_src(y, H, mh));
+      const float score = __fmul_rn(sn, sb);
+      if (score > 0.f) {                   // `valid = scores > 0`, src/XFextractor.cc:313
+        const unsigned int lin = (unsigned int)(y * W + x);
+        key = ((u64)__float_as_uint(score) << 32) | (u64)(0xFFFFFFFFu - lin);
+      }
+    }
+    // (the first pass may overwrite tin / hmx: every thread is past phase 2)
+    const unsigned int bal = __ballot_sync(0xffffffffu, key != 0);
+    int wbase = 0;
+    if ((t & 31) == 0 && bal) wbase = atomicAdd(&s_nkeys, __popc(bal));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (key != 0) s_keys[wbase + __popc(bal & ((1u << (t & 31)) - 1u))] = key;
+  }
+  __syncthreads();
+  const int nk = s_nkeys;
+  if (nk == 0) return;
+  if (t == 0) s_base = atomicAdd(cand_count + b * XFB_TICKET_STRIDE, nk);
+  __syncthreads();
+  u64* dst = cand + (size_t)b * H * W + s_base;
+  for (int i = t; i < nk; i += NMS_NT) dst[i] = s_keys[i];
 }
 
 // ------------------------------------------------------------------------------------------------
+// ---- bitonic network pieces for the register-resident sorter (thread t holds elements 8t .. 8t+7) ----
+__device__ __forceinline__ void tk_cx(u64& a, u64& b, bool desc) {      // afterwards a >= b when desc, a <= b otherwise
+  const bool sw = (a < b) == desc;
+  const u64 x = sw ? b : a;
+  b = sw ? a : b;
+  a = x;
+}
+__device__ __forceinline__ void tk_local(u64 (&k)[8], bool desc) {      // strides 4, 2, 1 inside the thread
+  tk_cx(k[0], k[4], desc); tk_cx(k[1], k[5], desc); tk_cx(k[2], k[6], desc); tk_cx(k[3], k[7], desc);
+  tk_cx(k[0], k[2], desc); tk_cx(k[1], k[3], desc); tk_cx(k[4], k[6], desc); tk_cx(k[5], k[7], desc);
+  tk_cx(k[0], k[1], desc); tk_cx(k[2], k[3], desc); tk_cx(k[4], k[5], desc); tk_cx(k[6], k[7], desc);
+}
+__device__ __forceinline__ void tk_keep(u64 (&k)[8], const u64 (&o)[8], bool keepmax) {
+#pragma unroll
+  for (int r = 0; r < 8; ++r) k[r] = keepmax ? (k[r] > o[r] ? k[r] : o[r]) : (k[r] < o[r] ? k[r] : o[r]);
+}
+// exchange layout in shared memory: thread t's 16-byte chunk c sits at chunk slot c ^ ((t >> 1) & 3) of its 64-byte block, so the
+// 8 lanes of a quarter warp touch 8 distinct 16-byte bank groups (a plain 64-byte stride would be a 4-way conflict)
+__device__ __forceinline__ ulonglong2* tk_slot(u64* skeys, int t, int c) { return reinterpret_cast<ulonglong2*>(skeys + 8 * t + 2 * (c ^ ((t >> 1) & 3))); }
+
 constexpr int TOPK_NT = 1024;
 constexpr int TOPK_CAP = 8192;     // keys the shared-memory sorter holds
 // Exact per-frame top-k of the candidate keys (score bits << 32 | ~pixel index: unique, so "the k largest keys" is the reference's
@@ -195,7 +263,57 @@ __global__ void __launch_bounds__(TOPK_NT) topk_kernel(const u64* cand, int* can
     }
   }
   __syncthreads();
-  // bitonic sort, descending
+  if (sort_n > TOPK_NT) {
+    // ---- register-resident bitonic sort of TOPK_CAP keys (zero padded), descending: 8 keys per thread.  Strides 1, 2, 4 are
+    // compare-exchanges inside the thread, strides 8 .. 128 one 64-bit shuffle per key, and only strides >= 256 (15 of the 91
+    // stages) go through shared memory and a CTA barrier.  (The shared-memory-only network below paid a barrier and a dependent
+    // LDS -> compare -> STS chain per stage: 84 us per 32 frames on 32 SMs; ncu source view of round 2.)
+    for (int i = sort_n + t; i < TOPK_CAP; i += TOPK_NT) skeys[i] = 0;
+    __syncthreads();
+    u64 k[8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(skeys + 8 * t + 2 * c);
+      k[2 * c] = v.x; k[2 * c + 1] = v.y;
+    }
+    __syncthreads();
+    const int lane = t & 31;
+    // size 2, size 4: the direction depends on the element's own index bits
+    tk_cx(k[0], k[1], true); tk_cx(k[2], k[3], false); tk_cx(k[4], k[5], true); tk_cx(k[6], k[7], false);
+    tk_cx(k[0], k[2], true); tk_cx(k[1], k[3], true); tk_cx(k[4], k[6], false); tk_cx(k[5], k[7], false);
+    tk_cx(k[0], k[1], true); tk_cx(k[2], k[3], true); tk_cx(k[4], k[5], false); tk_cx(k[6], k[7], false);
+#pragma unroll 1
+    for (int size = 8; size <= TOPK_CAP; size <<= 1) {
+      const bool desc = ((8 * t) & size) == 0;
+#pragma unroll 1
+      for (int stride = size >> 1; stride >= 8; stride >>= 1) {
+        const int tm = stride >> 3;                    // partner thread = t ^ tm
+        const bool keepmax = ((t & tm) == 0) == desc;  // the lower element of a pair keeps the maximum in a descending run
+        u64 o[8];
+        if (tm >= 32) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) *tk_slot(skeys, t, c) = make_ulonglong2(k[2 * c], k[2 * c + 1]);
+          __syncthreads();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const ulonglong2 v = *tk_slot(skeys, t ^ tm, c);
+            o[2 * c] = v.x; o[2 * c + 1] = v.y;
+          }
+          __syncthreads();
+        } else {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) o[r] = __shfl_xor_sync(0xffffffffu, k[r], tm);
+        }
+        tk_keep(k, o, keepmax);
+      }
+      tk_local(k, desc);
+    }
+    (void)lane;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) *reinterpret_cast<ulonglong2*>(skeys + 8 * t + 2 * c) = make_ulonglong2(k[2 * c], k[2 * c + 1]);
+    __syncthreads();
+  } else
+  // bitonic sort, descending (small candidate sets: one pair per thread and stage)
   for (int size = 2; size <= sort_n; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       for (int i = t; i < (sort_n >> 1); i += TOPK_NT) {
@@ -229,55 +347,64 @@ __global__ void __launch_bounds__(TOPK_NT) topk_kernel(const u64* cand, int* can
 }
 
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float warp_sum(float v) {
+// sum over the 16 lanes that share a keypoint (xor offsets 8 .. 1 stay inside a half warp)
+__device__ __forceinline__ float half_warp_sum(float v) {
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  for (int off = 8; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
   return v;
 }
 
-// channel-normalised corner: feats[y][x][:] / max(||.||_2, 1e-12)  (F.normalize(M1, dim=1), :273)
-__device__ __forceinline__ float2 corner_unit(const float* fmap, int mh, int mw, int x, int y, int lane) {
-  if (x < 0 || x >= mw || y < 0 || y >= mh) return make_float2(0.f, 0.f);
-  const float2 v = *reinterpret_cast<const float2*>(fmap + ((size_t)y * mw + x) * 64 + lane * 2);
-  const float nrm = sqrtf(warp_sum(v.x * v.x + v.y * v.y));
-  const float den = fmaxf(nrm, 1e-12f);
-  return make_float2(__fdiv_rn(v.x, den), __fdiv_rn(v.y, den));
+// channel-normalised corner: feats[y][x][:] / max(||.||_2, 1e-12)  (F.normalize(M1, dim=1), :273); this lane's 4 channels.
+// The quotient is x * (1 / den) with an IEEE-rounded reciprocal: within 1.5 ulp of the reference's division, 1e-7 against a 1e-4
+// tolerance, and one reciprocal per corner instead of four divisions per lane (the kernel is instruction bound).
+__device__ __forceinline__ float4 corner_unit(const float* fmap, int mh, int mw, int x, int y, int sub) {
+  // (no early return: the two keypoints of a warp may differ here and the shuffles below need all 32 lanes; a zero vector stays zero)
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (x >= 0 && x < mw && y >= 0 && y < mh) v = *reinterpret_cast<const float4*>(fmap + ((size_t)y * mw + x) * 64 + sub * 4);
+  const float nrm = sqrtf(half_warp_sum(fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)))));
+  const float inv = __frcp_rn(fmaxf(nrm, 1e-12f));
+  return make_float4(__fmul_rn(v.x, inv), __fmul_rn(v.y, inv), __fmul_rn(v.z, inv), __fmul_rn(v.w, inv));
 }
 
+// 16 lanes per keypoint (4 channels each: a corner is one 256-byte line read as 16 x LDG.128), two keypoints per warp
 __global__ void __launch_bounds__(256) describe_kernel(const float* feats, int H, int W, int topk, const int32_t* n_valid,
                                                        const float* kpt_xy, float* desc) {
   const int b = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= topk) return;
-  float2 o = make_float2(0.f, 0.f);
-  if (i < n_valid[b]) {
-    const int mh = H >> 3, mw = W >> 3;
-    const float* fmap = feats + (size_t)b * mh * mw * 64;
-    const int px = (int)kpt_xy[((size_t)b * topk + i) * 2], py = (int)kpt_xy[((size_t)b * topk + i) * 2 + 1];
-    const float sx = grid_src(px, W, mw), sy = grid_src(py, H, mh);
-    const float x0f = floorf(sx), y0f = floorf(sy);
-    const int x0 = (int)x0f, y0 = (int)y0f;
-    const float w = __fsub_rn(sx, x0f), e = __fsub_rn(1.0f, w), n = __fsub_rn(sy, y0f), s = __fsub_rn(1.0f, n);
-    const float2 nw = corner_unit(fmap, mh, mw, x0, y0, lane);
-    const float2 ne = corner_unit(fmap, mh, mw, x0 + 1, y0, lane);
-    const float2 sw = corner_unit(fmap, mh, mw, x0, y0 + 1, lane);
-    const float2 se = corner_unit(fmap, mh, mw, x0 + 1, y0 + 1, lane);
-    const float wnw = __fmul_rn(s, e), wne = __fmul_rn(s, w), wsw = __fmul_rn(n, e), wse = __fmul_rn(n, w);
-    float2 v;
-    v.x = bilerp4(nw.x, ne.x, sw.x, se.x, wnw, wne, wsw, wse);
-    v.y = bilerp4(nw.y, ne.y, sw.y, se.y, wnw, wne, wsw, wse);
-    const float den = fmaxf(sqrtf(warp_sum(v.x * v.x + v.y * v.y)), 1e-12f);
-    o = make_float2(__fdiv_rn(v.x, den), __fdiv_rn(v.y, den));
-  }
-  *reinterpret_cast<float2*>(desc + ((size_t)b * topk + i) * 64 + lane * 2) = o;
+  const int sub = threadIdx.x & 15;
+  const int i = blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
+  const bool live = i < topk && i < n_valid[b];       // (the branch is uniform over the 16 lanes of a keypoint; shuffles stay inside them)
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  // every lane of the warp runs the arithmetic (the half-warp shuffles need all 32 lanes converged); dead keypoints read nothing
+  const int ii = live ? i : 0;
+  const int mh = H >> 3, mw = W >> 3;
+  const float* fmap = feats + (size_t)b * mh * mw * 64;
+  const float2 kp = live ? *reinterpret_cast<const float2*>(kpt_xy + ((size_t)b * topk + ii) * 2) : make_float2(0.f, 0.f);
+  const int px = (int)kp.x, py = (int)kp.y;
+  const float sx = grid_src(px, W, mw), sy = grid_src(py, H, mh);
+  const float x0f = floorf(sx), y0f = floorf(sy);
+  const int x0 = live ? (int)x0f : -4, y0 = (int)y0f;  // dead: every corner is out of the map
+  const float w = __fsub_rn(sx, x0f), e = __fsub_rn(1.0f, w), n = __fsub_rn(sy, y0f), s = __fsub_rn(1.0f, n);
+  const float4 nw = corner_unit(fmap, mh, mw, x0, y0, sub);
+  const float4 ne = corner_unit(fmap, mh, mw, x0 + 1, y0, sub);
+  const float4 sw = corner_unit(fmap, mh, mw, x0, y0 + 1, sub);
+  const float4 se = corner_unit(fmap, mh, mw, x0 + 1, y0 + 1, sub);
+  const float wnw = __fmul_rn(s, e), wne = __fmul_rn(s, w), wsw = __fmul_rn(n, e), wse = __fmul_rn(n, w);
+  float4 v;
+  v.x = bilerp4(nw.x, ne.x, sw.x, se.x, wnw, wne, wsw, wse);
+  v.y = bilerp4(nw.y, ne.y, sw.y, se.y, wnw, wne, wsw, wse);
+  v.z = bilerp4(nw.z, ne.z, sw.z, se.z, wnw, wne, wsw, wse);
+  v.w = bilerp4(nw.w, ne.w, sw.w, se.w, wnw, wne, wsw, wse);
+  const float nrm = sqrtf(half_warp_sum(fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)))));
+  const float inv = __frcp_rn(fmaxf(nrm, 1e-12f));
+  if (live) o = make_float4(__fmul_rn(v.x, inv), __fmul_rn(v.y, inv), __fmul_rn(v.z, inv), __fmul_rn(v.w, inv));
+  if (i < topk) *reinterpret_cast<float4*>(desc + ((size_t)b * topk + i) * 64 + sub * 4) = o;
 }
 
 cudaError_t launch_post(Ctx* c, int topk, float nms_thr, int32_t* d_nvalid, float* d_xy, float* d_score, float* d_desc) {
   const int H = c->H, W = c->W;
-  dim3 g1((W + NMS_T * NMS_NX - 1) / (NMS_T * NMS_NX), (H + NMS_T - 1) / NMS_T, c->B);
+  dim3 g1((W + NMS_TW - 1) / NMS_TW, (H + NMS_TH - 1) / NMS_TH, c->B);
   prof_begin(c, P_NMS);
-  nms_score_kernel<<<g1, dim3(NMS_T, NMS_T), 0, c->stream>>>(c->k1h, c->act[L_HM_2], H, W, nms_thr, c->cand, c->cand_count);
+  nms_score_kernel<<<g1, NMS_NT, 0, c->stream>>>(c->k1h, c->act[L_HM_2], H, W, nms_thr, c->cand, c->cand_count);
   prof_end(c);
   c->launches++;
   cudaError_t e = cudaGetLastError();
@@ -295,7 +422,7 @@ cudaError_t launch_post(Ctx* c, int topk, float nms_thr, int32_t* d_nvalid, floa
   c->launches++;
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  dim3 g3((topk + 7) / 8, c->B);
+  dim3 g3((topk + 15) / 16, c->B);
   prof_begin(c, P_DESCRIBE);
   describe_kernel<<<g3, 256, 0, c->stream>>>(c->act[L_F_2], H, W, topk, d_nvalid, d_xy, d_desc);
   prof_end(c);
