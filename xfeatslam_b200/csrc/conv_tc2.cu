@@ -52,9 +52,9 @@ constexpr int T2_THREADS = T2_EPI + 32 + T2_PROD;   // warps 0-3 epilogue, warp 
 // CIN: real input channels; CINP: padded to a multiple of 16 (zero chunks); COUT: real outputs; NSPLIT: output-channel
 // groups processed by different CTAs; CSTAGE: input channels per staged buffer (channel phase); NBUF: ring depth;
 // UNR: 32-byte global loads in flight per producer thread and unit.
-template <int CIN_, int COUT_, int KS_, int S_, int CSTAGE_, int NBUF_, int NSPLIT_, int UNR_>
+template <int CIN_, int COUT_, int KS_, int S_, int CSTAGE_, int NBUF_, int NSPLIT_, int UNR_, int RAW_ = 0>
 struct T2Cfg {
-  static constexpr int CIN = CIN_, COUT = COUT_, KS = KS_, S = S_, CSTAGE = CSTAGE_, NBUF = NBUF_, NSPLIT = NSPLIT_, UNR = UNR_;
+  static constexpr int CIN = CIN_, COUT = COUT_, KS = KS_, S = S_, CSTAGE = CSTAGE_, NBUF = NBUF_, NSPLIT = NSPLIT_, UNR = UNR_, RAW = RAW_;
   static constexpr int CINP = (CIN + 15) / 16 * 16;
   static constexpr int NOUT = COUT / NSPLIT;                                      // real output channels per CTA
   static constexpr int NP = NOUT <= 32 ? 32 : (NOUT + 15) / 16 * 16;              // padded outputs; UMMA N = 2 * NP (hi rows | lo rows) and NP
@@ -91,7 +91,15 @@ struct T2Cfg {
   static constexpr int STG_BYTES = NHALF * 16384;                                 // staging tile(s): [128 px][32 ch] fp32, 128B-swizzled
   static constexpr int FOLD_BYTES = 128 * 2 * 8;
   static constexpr int BN_BYTES = CINP * 2 * 4;                                   // the current frame's (16 rstd, -16 mean rstd) per input channel
-  static constexpr size_t SMEM_BYTES = (size_t)STG_BYTES + W_BYTES + (size_t)NBUF * BUF_BYTES + FOLD_BYTES + BN_BYTES + 256;
+  // RAW > 0: the raw fp32 input of a (tile, channel phase) arrives by ONE TMA tensor load (cp.async.bulk.tensor, zero-filled outside the
+  // image and beyond CIN) into a ring of RAW shared-memory stages, issued RAW buffers ahead of the tensor core -- the bytes in flight
+  // no longer depend on producer registers (one unit ahead = 3 MB in flight chip-wide = 1 TB/s at 2.5 us latency, measured on block2).
+  static constexpr int CB = CIN < CSTAGE ? CIN : CSTAGE;                          // channels per raw box
+  static constexpr int RAW_W = KS == 1 ? 128 : (S == 1 ? WT : 2 * WT);
+  static constexpr int RAW_H = KS == 1 ? 1 : (S == 1 ? HT : 2 * HT);
+  static constexpr int RAW_TX = RAW_W * RAW_H * CB * 4;                            // bytes one load delivers
+  static constexpr int RAW_BYTES = RAW > 0 ? (RAW_TX + 127) / 128 * 128 : 0;
+  static constexpr size_t SMEM_BYTES = (size_t)STG_BYTES + W_BYTES + (size_t)RAW * RAW_BYTES + (size_t)NBUF * BUF_BYTES + FOLD_BYTES + BN_BYTES + 320;
   // kind::f16, F16 x F16 -> F32, both K-major, M = 128
   static constexpr uint32_t IDESC_2N = (1u << 4) | ((uint32_t)(2 * NP >> 3) << 17) | ((128u >> 4) << 24);
   static constexpr uint32_t IDESC_1N = (1u << 4) | ((uint32_t)(NP >> 3) << 17) | ((128u >> 4) << 24);
@@ -100,6 +108,7 @@ struct T2Cfg {
   static_assert(S == 1 || KS == 3, "stride 2 is implemented for 3x3 only");
   static_assert(T2_PROD % KCS == 0 && PT % KCR == 0 && ROUNDS <= 2, "a producer thread keeps one channel chunk; at most two units per buffer");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  static_assert(RAW <= 8 && CB % 8 == 0 && RAW_W <= 256 && RAW_H <= 256, "raw input ring");
   static_assert(PS % 16 == 0 && W_UNIT_BYTES % 16 == 0 && W_BYTES % 1024 == 0, "descriptor alignment");
 };
 
@@ -184,6 +193,17 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sm
                "r"(c1), "r"(c2), "r"(c3), "r"(smem)
                : "memory");
 }
+// TMA tensor loads (global -> shared, completion on an mbarrier; parts of the box outside the tensor arrive as zeros)
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t smem, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t smem, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(smem),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -199,13 +219,16 @@ struct ProdRegs {
 struct ProdPos { int tile, ph, rnd, it; };   // it = staged-buffer counter of this CTA
 
 template <class C, int INMODE, int OUTMODE>
-__global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Args a, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Args a, const __grid_constant__ CUtensorMap tmap,
+                                                                 const __grid_constant__ CUtensorMap tmap_in) {
+  constexpr bool USE_RAW = C::RAW > 0 && INMODE != T2IN_UNFOLD;
   constexpr int KCS = C::KCS, PS = C::PS, WT = C::WT, NPIX = C::NPIX, TAPS = C::TAPS, NBUF = C::NBUF, NPHASE = C::NPHASE, UNR = C::UNR,
                 ROUNDS = C::ROUNDS, ITEMS = C::ITEMS;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* sStg = smem_raw;                                 // staging tile(s) for the TMA store (1024-byte aligned: 128B swizzle)
   unsigned char* sW = smem_raw + C::STG_BYTES;                    // resident weights of this CTA's output group
-  unsigned char* sA = sW + C::W_BYTES;                            // NBUF x [hi | lo] staged tiles
+  unsigned char* sRaw = sW + C::W_BYTES;                          // RAW x raw fp32 input boxes (TMA destinations, 128-byte aligned)
+  unsigned char* sA = sRaw + (size_t)C::RAW * C::RAW_BYTES;       // NBUF x [hi | lo] staged tiles
   double* sFold = reinterpret_cast<double*>(sA + (size_t)NBUF * C::BUF_BYTES);   // [128][2]
   float* sBN = reinterpret_cast<float*>(sFold + 128 * 2);                        // [2][CINP]: scale, shift of the producers' current frame
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBN + 2 * C::CINP);
@@ -214,7 +237,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
   uint64_t* bar_accf = bars + 8;        // [2] accumulator complete
   uint64_t* bar_acce = bars + 10;       // [2] accumulator drained (4 arrivals)
   uint64_t* bar_w = bars + 12;          // [NPHASE <= 8] weights of a channel phase landed
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* bar_raw = bars + 20;        // [RAW <= 8] raw input box landed
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 28);
   uint32_t* s_flag = s_tmem + 1;
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -230,6 +254,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
     for (int s = 0; s < NBUF; ++s) { mbar_init(bar_in + s, T2_PROD); mbar_init(bar_free + s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(bar_accf + s, 1); mbar_init(bar_acce + s, 4); }
     for (int s = 0; s < NPHASE; ++s) mbar_init(bar_w + s, 1);
+    for (int s = 0; s < C::RAW; ++s) mbar_init(bar_raw + s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) tmem_alloc(s_tmem, C::TMEM_COLS);
@@ -246,6 +271,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
     // origin moves.  slot_off = byte offset in the staged buffer (-1: no item), slot_yx = input pixel relative to the tile origin
     // ((dy << 16) | (dx & 0xffff); 1x1 layers: the pixel index inside the 128-pixel tile).
     int slot_off[C::NSLOT], slot_yx[C::NSLOT];
+    int slot_raw[USE_RAW ? C::NSLOT : 1];            // byte offset of the item's 8 channels inside the raw box
 #pragma unroll
     for (int sl = 0; sl < C::NSLOT; ++sl) {
       const int idx = sl * C::PT + pt;
@@ -259,7 +285,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
         else if (C::S == 1) { dy = pix / WT - C::PAD; dx = pix % WT - C::PAD; }
         else { dy = 2 * (pix / WT - 1) + (sub >> 1); dx = 2 * (pix % WT - 1) + (sub & 1); }
         slot_yx[sl] = (int)(((unsigned int)dy << 16) | ((unsigned int)dx & 0xffffu));
-      }
+        if (USE_RAW) {
+          const int brow = (C::KS == 1) ? 0 : (C::S == 1 ? dy + C::PAD : dy + 2), bcol = (C::KS == 1) ? pix : (C::S == 1 ? dx + C::PAD : dx + 2);
+          slot_raw[sl] = ((brow * C::RAW_W + bcol) * C::CB + kc * 8) * 4;
+        }
+      } else if (USE_RAW) slot_raw[sl] = 0;
     }
     if (C::KCR != KCS) {
       // zero the padding chunk planes of every ring buffer once (hi and lo)
@@ -326,7 +356,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
           if (C::KS == 1 && INMODE != T2IN_UNFOLD) {
             if (dx < lin_ok) {                       // the tile is 128 consecutive pixels of the frame
               R.inside |= 1u << q;
-              R.v[q] = ldg256(in_b + ((size_t)tf * 128 + dx) * C::CIN + ch);
+              if (!USE_RAW) R.v[q] = ldg256(in_b + ((size_t)tf * 128 + dx) * C::CIN + ch);
             }
           } else {
             int iy, ix;
@@ -341,7 +371,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
                 // XFeatModel::unfold2d(x, 8), src/XFeat.cc:124-133: channel c = (y % 8) * 8 + x % 8 -> chunk kc = row iy * 8 + kc of xn
                 R.v[q] = ldg256(in_b + (size_t)(iy * 8 + (ch >> 3)) * a.full_w + ix * 8);
               } else {
-                R.v[q] = ldg256(in_b + ((size_t)iy * a.Win + ix) * C::CIN + ch);
+                if (!USE_RAW) R.v[q] = ldg256(in_b + ((size_t)iy * a.Win + ix) * C::CIN + ch);
                 if (INMODE == T2IN_BN_SKIP) R.av[q] = a.skip_avg[((size_t)b * a.Hin + iy) * a.Win + ix];
               }
             }
@@ -402,16 +432,24 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
     auto consume = [&](const ProdPos& u, const ProdRegs<UNR>& R) {
       const int buf = u.it % NBUF;
       unsigned char* dst_hi = sA + (size_t)buf * C::BUF_BYTES;
+      const unsigned char* raw = sRaw + (size_t)(USE_RAW ? u.it % (C::RAW > 0 ? C::RAW : 1) : 0) * C::RAW_BYTES;
       if (u.rnd == 0) {
-        if (u.ph == 0 && u.tile + 2 < tile_end) prefetch_tile(u.tile + 2);
+        if (!USE_RAW && u.ph == 0 && u.tile + 2 < tile_end) prefetch_tile(u.tile + 2);
         T2_TICK(3);
         if (u.it >= NBUF) mbar_wait(bar_free + buf, ((u.it / NBUF) - 1) & 1);   // the MMAs that read this buffer are done
+        if (USE_RAW) mbar_wait(bar_raw + u.it % (C::RAW > 0 ? C::RAW : 1), (u.it / (C::RAW > 0 ? C::RAW : 1)) & 1);   // the raw box has landed
         T2_TICK(2);
       }
 #pragma unroll
       for (int q = 0; q < UNR; ++q) {
         if (R.off[q] < 0) continue;
         float x[8] = {R.v[q].a.x, R.v[q].a.y, R.v[q].a.z, R.v[q].a.w, R.v[q].b.x, R.v[q].b.y, R.v[q].b.z, R.v[q].b.w};
+        if (USE_RAW) {
+          const int ro = (ROUNDS == 1 || u.rnd == 0) ? slot_raw[USE_RAW ? q : 0] : slot_raw[USE_RAW ? (ROUNDS - 1) * UNR + q : 0];
+          float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+          if ((R.inside >> q) & 1u) { x0 = *reinterpret_cast<const float4*>(raw + ro); x1 = *reinterpret_cast<const float4*>(raw + ro + 16); }
+          x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+        }
         if ((R.inside >> q) & 1u) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -469,6 +507,23 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
   } else if (warp == 4) {
     // ===================== weights (once) + MMA issue: the whole warp runs the uniform loop, ONE elected lane issues ===========
     const bool leader = elect_one_sync();
+    // raw input boxes: buffer it2 = (tile, channel phase) of this CTA's walk goes to ring stage it2 % RAW
+    const int total_its = (tile_end - tile_begin) * NPHASE;
+    auto raw_load = [&](int it2) {
+      const int tile = tile_begin + it2 / NPHASE, ph = it2 % NPHASE;
+      const int b = tile / a.tiles, tf = tile - b * a.tiles;
+      const int stage = it2 % (C::RAW > 0 ? C::RAW : 1);
+      mbar_expect_tx(bar_raw + stage, C::RAW_TX);
+      const uint32_t dst = smem_u32(sRaw + (size_t)stage * C::RAW_BYTES);
+      if (C::KS == 1) tma_load_3d(&tmap_in, dst, bar_raw + stage, ph * C::CSTAGE, tf * 128, b);
+      else {
+        const int oy0 = (tf / a.tiles_x) * C::TH, ox0 = (tf % a.tiles_x) * C::TW;
+        if (C::S == 1) tma_load_4d(&tmap_in, dst, bar_raw + stage, ph * C::CSTAGE, ox0 - C::PAD, oy0 - C::PAD, b);
+        else tma_load_4d(&tmap_in, dst, bar_raw + stage, ph * C::CSTAGE, 2 * ox0 - 2, 2 * oy0 - 2, b);
+      }
+    };
+    if (USE_RAW && leader)
+      for (int i = 0; i < C::RAW && i < total_its; ++i) raw_load(i);
     if (leader && tile_begin < tile_end) {
       const unsigned char* wsrc = a.wimg + (size_t)split * C::W_BYTES;
       constexpr uint32_t PH_BYTES = (uint32_t)TAPS * C::W_UNIT_BYTES;
@@ -503,6 +558,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
         mbar_wait(bar_in + buf, (it / NBUF) & 1);
         T2_TICK(6);
         tc_fence_after();
+        // every producer has read raw stage it % RAW (they arrived on bar_in after their last read): refill it, RAW buffers ahead
+        if (USE_RAW && leader && it + C::RAW < total_its) raw_load(it + C::RAW);
         if (leader) {
           const uint64_t dah = da0 + (uint64_t)buf * A_BUF, dal = dah + A_LO;
 #pragma unroll
@@ -749,10 +806,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
 
 // ---------------------------------------------------------------------------------------------------
 //                        CIN COUT KS S CSTAGE NBUF NSPLIT UNR
-using T2B2x = T2Cfg<24, 24, 3, 1, 32, 3, 1, 3>;      // block2.0/.1                   120x160         (Cin padded 24 -> 32)
+using T2B2x = T2Cfg<24, 24, 3, 1, 32, 3, 1, 3, 4>;   // block2.0/.1                   120x160         (Cin padded 24 -> 32; raw ring of 4)
 using T2B30 = T2Cfg<24, 64, 3, 2, 16, 3, 1, 3>;      // block3.0                      -> 60x80
 using T2C33 = T2Cfg<64, 64, 3, 1, 32, 2, 1, 4>;      // block3.1, block4.1/.2, block_fusion.0/.1   (147 KB of weights resident)
-using T2C11 = T2Cfg<64, 64, 1, 1, 64, 3, 1, 3>;      // block3.2, block_fusion.2, heatmap_head.0/.1, keypoint_head.0/.1/.2
+using T2C11 = T2Cfg<64, 64, 1, 1, 64, 2, 1, 3, 3>;   // block3.2, block_fusion.2, heatmap_head.0/.1, keypoint_head.0/.1/.2   (raw ring of 3)
 using T2B40 = T2Cfg<64, 64, 3, 2, 16, 2, 2, 3>;      // block4.0                      -> 30x40        (two output groups of 32)
 using T2B50 = T2Cfg<64, 128, 3, 2, 16, 2, 4, 3>;     // block5.0                      -> 15x20        (four output groups of 32)
 using T2B5x = T2Cfg<128, 128, 3, 1, 32, 2, 4, 4>;    // block5.1/.2                                   (four output groups of 32)
@@ -821,6 +878,38 @@ static cudaError_t output_tmap(Ctx* c, int L, float* out, int B, int H, int W, i
   return cudaSuccess;
 }
 
+// NHWC fp32 input [B][H][W][C] of a layer with a raw ring: box = the halo tile (3x3: {CB, RAW_W, RAW_H, 1} at any, also negative,
+// origin) or 128 consecutive pixels (1x1: 3-D map {C, H*W, B}); no swizzle (the producers read 32-byte pieces); what lies outside
+// the tensor -- image border, channels beyond C -- arrives as zeros.
+static cudaError_t input_tmap(Ctx* c, int L, const float* in, int B, int H, int W, int C, bool linear, int cb, int bw, int bh, const CUtensorMap** map) {
+  Ctx::TmapSlot& s = c->tmap_in[L];
+  if (s.ptr != in || s.B != B || s.H != H || s.W != W) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return cudaErrorNotSupported;
+    CUtensorMap m;
+    CUresult r;
+    void* base = const_cast<float*>(in);
+    if (linear) {
+      const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)H * W, (cuuint64_t)B};
+      const cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)H * W * C * 4};
+      const cuuint32_t box[3] = {(cuuint32_t)cb, (cuuint32_t)bw, 1}, es[3] = {1, 1, 1};
+      r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+      const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+      const cuuint32_t box[4] = {(cuuint32_t)cb, (cuuint32_t)bw, (cuuint32_t)bh, 1}, es[4] = {1, 1, 1, 1};
+      r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    std::memcpy(s.blob, &m, sizeof(m));
+    s.ptr = in; s.B = B; s.H = H; s.W = W;
+  }
+  *map = reinterpret_cast<const CUtensorMap*>(s.blob);
+  return cudaSuccess;
+}
+
 template <class C, int INMODE, int OUTMODE>
 static cudaError_t run_tc2(Ctx* c, ConvTc2Args& a, int tag) {
   auto kern = conv_tc2_kernel<C, INMODE, OUTMODE>;
@@ -838,11 +927,16 @@ static cudaError_t run_tc2(Ctx* c, ConvTc2Args& a, int tag) {
     cudaError_t e = output_tmap(c, tag, a.out, a.B, a.Hout, a.Wout, C::COUT, C::KS == 1, &map);
     if (e != cudaSuccess) return e;
   }
+  const CUtensorMap* map_in = map;                                                      // (unused without a raw ring)
+  if (C::RAW > 0 && INMODE != T2IN_UNFOLD) {
+    cudaError_t e = input_tmap(c, tag, a.in, a.B, a.Hin, a.Win, C::CIN, C::KS == 1, C::CB, C::RAW_W, C::RAW_H, &map_in);
+    if (e != cudaSuccess) return e;
+  }
   const int items = a.B * a.tiles * C::NSPLIT;
   int grid = c->num_sms - c->num_sms % C::NSPLIT;            // persistent: one CTA per SM, a multiple of the output groups
   if (grid > items) grid = items;                            // (items is a multiple of NSPLIT)
   prof_begin(c, tag);
-  kern<<<grid, T2_THREADS, C::SMEM_BYTES, c->stream>>>(a, *map);
+  kern<<<grid, T2_THREADS, C::SMEM_BYTES, c->stream>>>(a, *map, *map_in);
   prof_end(c);
   c->launches++;
   return cudaGetLastError();

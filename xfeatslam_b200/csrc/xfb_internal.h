@@ -85,6 +85,7 @@ struct Ctx {
   bool b1_fuse = false;           // XFB_B1_FUSE=1: block1.0 recomputed inside block1.1 (measured: 0.212 ms vs 0.201 ms for the two kernels -- a loss, kept as an A/B option)
   struct TmapSlot { alignas(64) unsigned char blob[128]; const void* ptr; int B, H, W; };   // CUtensorMap of a layer's output + what it was encoded for
   TmapSlot tmap[L_NUM] = {};
+  TmapSlot tmap_in[L_NUM] = {};   // CUtensorMap of a layer's INPUT (conv_tc2.cu raw ring: one TMA box per tile and channel phase)
   unsigned long long* t2_counters = nullptr;   // XFB_T2_DEBUG: [L_NUM][32] cycle counters of CTA 0 (conv_tc2.cu), printed at xfb_destroy
   bool force_simt = false;        // debug: run every conv on the FP32 SIMT kernels (A/B parity tests)
 
