@@ -415,6 +415,7 @@ int xfb_create(xfb_ctx** out, const void* weights_blob, size_t n, int device, in
     }
     c->num_sms = prop.multiProcessorCount;
     if (const char* bf = getenv("XFB_B1_FUSE")) c->b1_fuse = atoi(bf) != 0;
+    if (const char* pd = getenv("XFB_PDL")) c->pdl = atoi(pd) != 0;
     if (const char* cv = getenv("XFB_CONV_TC")) c->conv_tc_version = (atoi(cv) == 1) ? 1 : 2;   // A/B: 1 = the round-1 one-tile-per-CTA 3xTF32 kernels
     if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { c->err = cudaGetErrorString(e); r = XFB_ERR_CUDA; break; }
     c->stream = c->own_stream;

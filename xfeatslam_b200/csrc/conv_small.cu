@@ -122,11 +122,13 @@ __global__ void __launch_bounds__(C::NT) conv_small_kernel(const ConvArgs a) {
   __syncthreads();
 
   // ---- compute: PY output rows x COUT channels per thread -----------------------------------------------
-  float acc[PY][COUT];
+  // accumulators as channel PAIRS: FFMA2 (fma.rn.f32x2, sm_100) does two of the fp32 FMAs per issue slot -- same rounding, same order
+  // per channel as the scalar form, half the instructions of the issue-bound inner loop
+  float2 acc2[PY][COUT / 2];
 #pragma unroll
   for (int p = 0; p < PY; ++p)
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) acc[p][c] = 0.f;
+    for (int c = 0; c < COUT / 2; ++c) acc2[p][c] = make_float2(0.f, 0.f);
   const int row0 = warp * PY * S;                             // first input row of this thread inside the tile
   float4 bm[Q], br[Q];                                        // BN parameters of the producer (DIRECT path)
   if (DIRECT && IN_BN && CIN > 1) {
@@ -180,22 +182,30 @@ __global__ void __launch_bounds__(C::NT) conv_small_kernel(const ConvArgs a) {
     for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
       for (int ci = 0; ci < CIN; ++ci) {
-        float wv[COUT];
+        float2 wv[COUT / 2];
         const float4* wp = reinterpret_cast<const float4*>(sW + ((ky * 3 + kx) * CIN + ci) * COUT);
 #pragma unroll
         for (int c4 = 0; c4 < COUT / 4; ++c4) {
           const float4 w4 = wp[c4];
-          wv[4 * c4] = w4.x; wv[4 * c4 + 1] = w4.y; wv[4 * c4 + 2] = w4.z; wv[4 * c4 + 3] = w4.w;
+          wv[2 * c4] = make_float2(w4.x, w4.y); wv[2 * c4 + 1] = make_float2(w4.z, w4.w);
         }
 #pragma unroll
-        for (int p = 0; p < PY; ++p)
+        for (int p = 0; p < PY; ++p) {
+          const float x = xin[p * S + ky][ci];
+          const float2 xx = make_float2(x, x);
 #pragma unroll
-          for (int c = 0; c < COUT; ++c) acc[p][c] = fmaf(xin[p * S + ky][ci], wv[c], acc[p][c]);
+          for (int c = 0; c < COUT / 2; ++c) acc2[p][c] = __ffma2_rn(xx, wv[c], acc2[p][c]);
+        }
       }
     }
   }
 
   // ---- epilogue: coalesced store + per-channel sums ---------------------------------------------------------
+  float acc[PY][COUT];
+#pragma unroll
+  for (int p = 0; p < PY; ++p)
+#pragma unroll
+    for (int c = 0; c < COUT / 2; ++c) { acc[p][2 * c] = acc2[p][c].x; acc[p][2 * c + 1] = acc2[p][c].y; }
   float* out_b = a.out + (size_t)b * a.Hout * a.Wout * COUT;
   const int ox = ox0 + lane;
   float s1[COUT], s2[COUT];
@@ -278,11 +288,17 @@ __global__ void __launch_bounds__(C::NT) conv_small_kernel(const ConvArgs a) {
   if (t == 0) a.ticket[b * XFB_TICKET_STRIDE] = 0u;
 }
 
+#ifndef XFB_B12_NW
+#define XFB_B12_NW 4
+#endif
+#ifndef XFB_B13_NW
+#define XFB_B13_NW 4
+#endif
 //                    CIN COUT S PY NW
 using SB10 = SCfg<1, 4, 1, 4, 8>;     // block1.0  480x640            tile 32 x 32
 using SB11 = SCfg<4, 8, 2, 4, 8>;     // block1.1  -> 240x320         tile 32 x 32 (input 65 x 65 x 4)
-using SB12 = SCfg<8, 8, 1, 4, 8>;     // block1.2  240x320            tile 32 x 32
-using SB13 = SCfg<8, 24, 2, 2, 8>;    // block1.3  -> 120x160         tile 32 x 16 (input 33 x 65 x 8)
+using SB12 = SCfg<8, 8, 1, 4, XFB_B12_NW>;     // block1.2  240x320            tile 32 x 4*NW
+using SB13 = SCfg<8, 24, 2, 2, XFB_B13_NW>;    // block1.3  -> 120x160         tile 32 x 2*NW
 
 template <class C, bool IN_BN, bool DIRECT, bool STORE = true, bool FUSE0 = false>
 static cudaError_t run_small(Ctx* c, const ConvArgs& a, int tag) {

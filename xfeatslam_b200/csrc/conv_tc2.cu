@@ -126,6 +126,7 @@ struct ConvTc2Args {
   int tiles_x, tiles;       // tiles per frame
   float out_scale;          // 1 / (activation scale * weight scale), an exact power of two
   unsigned long long* dbg;  // XFB_T2_DEBUG: cycle counters of CTA 0 (32 per layer), else nullptr
+  int pdl;                  // launched with programmatic stream serialization (see the kernel)
 };
 
 // debug: add the cycles since `t0` to counter `slot` (one designated thread per role) and restart the clock
@@ -262,6 +263,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  // Programmatic dependent launch: the NEXT layer's CTAs may take an SM as soon as this CTA leaves it and run their prologue
+  // (barriers, TMEM, slot tables, weight image load) while other SMs still finish this layer; everything that reads or writes data
+  // of the previous kernel sits behind pdl_wait() (= that grid has completed and its writes are visible).
+  if (a.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  auto pdl_wait = [&]() { if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory"); };
 
   if (warp >= 5) {
     // ===================== producers: stage (tile, channel phase) buffers, global loads one unit ahead =====================
@@ -484,6 +490,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
 
     ProdRegs<UNR> ra, rb;
     ProdPos u = {tile_begin, 0, 0, 0};
+    pdl_wait();
     if (u.tile < tile_end) {
       issue(u, ra);
       while (true) {
@@ -522,10 +529,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
         else tma_load_4d(&tmap_in, dst, bar_raw + stage, ph * C::CSTAGE, 2 * ox0 - 2, 2 * oy0 - 2, b);
       }
     };
-    if (USE_RAW && leader)
-      for (int i = 0; i < C::RAW && i < total_its; ++i) raw_load(i);
     if (leader && tile_begin < tile_end) {
-      const unsigned char* wsrc = a.wimg + (size_t)split * C::W_BYTES;
+      const unsigned char* wsrc = a.wimg + (size_t)split * C::W_BYTES;        // (weights do not depend on the previous kernel)
       constexpr uint32_t PH_BYTES = (uint32_t)TAPS * C::W_UNIT_BYTES;
       for (int ph = 0; ph < NPHASE; ++ph) {
         mbar_expect_tx(bar_w + ph, PH_BYTES);
@@ -534,6 +539,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
                    bar_w + ph);
       }
     }
+    pdl_wait();
+    if (USE_RAW && leader)
+      for (int i = 0; i < C::RAW && i < total_its; ++i) raw_load(i);
     __syncwarp();
     const uint64_t da0 = umma_desc_kmajor(smem_u32(sA), C::LBO_A, C::SBO_A);
     const uint64_t db0 = umma_desc_kmajor(smem_u32(sW), C::LBO_B, C::SBO_B);
@@ -595,6 +603,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const ConvTc2Ar
     int n = 0;
     const bool dbg_me = a.dbg != nullptr && blockIdx.x == 0 && t == 0;
     long long t0 = dbg_me ? clock64() : 0;
+    pdl_wait();                                         // (the partial-sum scratch and the ticket counters are shared between layers)
     int run_b = -1, run_cnt = 0;                        // tiles of frame run_b this CTA has written partials for, not yet published
     const int items_per_frame = a.tiles * C::NSPLIT;
 
@@ -936,7 +945,19 @@ static cudaError_t run_tc2(Ctx* c, ConvTc2Args& a, int tag) {
   int grid = c->num_sms - c->num_sms % C::NSPLIT;            // persistent: one CTA per SM, a multiple of the output groups
   if (grid > items) grid = items;                            // (items is a multiple of NSPLIT)
   prof_begin(c, tag);
-  kern<<<grid, T2_THREADS, C::SMEM_BYTES, c->stream>>>(a, *map, *map_in);
+  a.pdl = (c->pdl && !c->prof) ? 1 : 0;                 // (per-kernel event timing wants the launches serialised)
+  if (a.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T2_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, *map, *map_in);
+    if (e != cudaSuccess) return e;
+  } else {
+    kern<<<grid, T2_THREADS, C::SMEM_BYTES, c->stream>>>(a, *map, *map_in);
+  }
   prof_end(c);
   c->launches++;
   return cudaGetLastError();

@@ -82,6 +82,7 @@ struct Ctx {
   float wscale2[L_NUM] = {};      // its epilogue factor 1 / (activation scale * weight scale)
   int conv_tc_version = 2;        // 2 = conv_tc2.cu (default), 1 = conv_tc.cu (XFB_CONV_TC=1: A/B reference)
   int num_sms = 148;
+  bool pdl = true;                // conv_tc2 layers launch with programmatic stream serialization (XFB_PDL=0 switches it off)
   bool b1_fuse = false;           // XFB_B1_FUSE=1: block1.0 recomputed inside block1.1 (measured: 0.212 ms vs 0.201 ms for the two kernels -- a loss, kept as an A/B option)
   struct TmapSlot { alignas(64) unsigned char blob[128]; const void* ptr; int B, H, W; };   // CUtensorMap of a layer's output + what it was encoded for
   TmapSlot tmap[L_NUM] = {};
