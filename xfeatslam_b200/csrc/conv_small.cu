@@ -194,7 +194,10 @@ __global__ void __launch_bounds__(C::NT) conv_small_kernel(const ConvArgs a) {
           const float x = xin[p * S + ky][ci];
           const float2 xx = make_float2(x, x);
 #pragma unroll
-          for (int c = 0; c < COUT / 2; ++c) acc2[p][c] = __ffma2_rn(xx, wv[c], acc2[p][c]);
+          for (int c = 0; c < COUT / 2; ++c) {
+            if (COUT >= 8) acc2[p][c] = __ffma2_rn(xx, wv[c], acc2[p][c]);
+            else { acc2[p][c].x = fmaf(x, wv[c].x, acc2[p][c].x); acc2[p][c].y = fmaf(x, wv[c].y, acc2[p][c].y); }   // (block1.0: measured slower packed)
+          }
         }
       }
     }
