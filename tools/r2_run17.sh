@@ -10,6 +10,9 @@ k=l["roofline"]["kernel_ms_per_batch"]
 print("$1", "value", round(l["value"]), {n:round(v,4) for n,v in k.items() if n.startswith("block1")})
 PY
 }
-run "-DXFB_B12_NW=8 -DXFB_B13_NW=8"
-run "-DXFB_B12_NW=4 -DXFB_B13_NW=4"
-run "-DXFB_B12_NW=2 -DXFB_B13_NW=2"
+run "-DXFB_B11_NW=8"
+run "-DXFB_B11_NW=4"
+run "-DXFB_B11_NW=4 -DXFB_B11_DIRECT=false"
+run "-DXFB_B11_NW=8 -DXFB_B11_DIRECT=false"
+run "-DXFB_B13_DIRECT=false -DXFB_B12_DIRECT=true"
+(cd xfeatslam_b200/csrc && touch conv_small.cu && make > /dev/null 2>&1)

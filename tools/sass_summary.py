@@ -12,7 +12,7 @@ from pathlib import Path
 REPO = Path(__file__).resolve().parents[1]
 SO = REPO / "xfeatslam_b200" / "lib" / "libxfeat_b200.so"
 WANT = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTCCP", "UBLKCP", "UBLKPF", "UTMASTG", "UTMALDG", "UTMACMDFLUSH", "SYNCS", "ELECT",
-        "LDG.E.ENL2.256", "STG.E.ENL2.256", "HMMA", "REDG", "ATOMG"]
+        "LDG.E.ENL2.256", "STG.E.ENL2.256", "FFMA2", "HMMA", "REDG", "ATOMG"]
 
 
 def main():
@@ -37,12 +37,12 @@ def main():
     dem = subprocess.run(["cu++filt"], input="\n".join(kernels), capture_output=True, text=True).stdout.splitlines()
     print("# SASS mnemonics per kernel of `xfeatslam_b200/lib/libxfeat_b200.so` (`cuobjdump -sass`, sm_100a)\n")
     print("`UTCHMMA` = tcgen05.mma, `LDTM` / `STTM` = tcgen05.ld / st, `UTCBAR` = tcgen05.commit, `UBLKCP` = cp.async.bulk, `UBLKPF` = "
-          "cp.async.bulk.prefetch, `UTMASTG` = cp.async.bulk.tensor store (TMA), `SYNCS` = mbarrier ops, `LDG/STG.E.ENL2.256` = 256-bit global access.\n")
+          "cp.async.bulk.prefetch, `UTMASTG` / `UTMALDG` = cp.async.bulk.tensor store / load (TMA), `SYNCS` = mbarrier ops, `FFMA2` = fma.rn.f32x2, `LDG/STG.E.ENL2.256` = 256-bit global access.\n")
     cols = [w for w in WANT if any(k[w] for k in kernels.values())]
     print("| kernel | instructions | " + " | ".join(cols) + " |")
     print("|---|---|" + "---|" * len(cols))
     for (name, c), d in zip(kernels.items(), dem):
-        if not any(c[w] for w in ("UTCHMMA", "LDTM", "UBLKCP", "UTMASTG", "STTM")):
+        if not any(c[w] for w in ("UTCHMMA", "LDTM", "UBLKCP", "UTMASTG", "STTM", "FFMA2")):
             continue
         short = re.sub(r"\((?:int|bool)\)", "", d)
         short = re.sub(r"\((?:xfb::|const |CUtensorMap).*$", "", short).replace("void xfb::", "").replace("xfb::", "")

@@ -291,6 +291,18 @@ __global__ void __launch_bounds__(C::NT) conv_small_kernel(const ConvArgs a) {
   if (t == 0) a.ticket[b * XFB_TICKET_STRIDE] = 0u;
 }
 
+#ifndef XFB_B11_NW
+#define XFB_B11_NW 8
+#endif
+#ifndef XFB_B11_DIRECT
+#define XFB_B11_DIRECT true
+#endif
+#ifndef XFB_B13_DIRECT
+#define XFB_B13_DIRECT true
+#endif
+#ifndef XFB_B12_DIRECT
+#define XFB_B12_DIRECT false
+#endif
 #ifndef XFB_B12_NW
 #define XFB_B12_NW 4
 #endif
@@ -299,7 +311,7 @@ __global__ void __launch_bounds__(C::NT) conv_small_kernel(const ConvArgs a) {
 #endif
 //                    CIN COUT S PY NW
 using SB10 = SCfg<1, 4, 1, 4, 8>;     // block1.0  480x640            tile 32 x 32
-using SB11 = SCfg<4, 8, 2, 4, 8>;     // block1.1  -> 240x320         tile 32 x 32 (input 65 x 65 x 4)
+using SB11 = SCfg<4, 8, 2, 4, XFB_B11_NW>;     // block1.1  -> 240x320         tile 32 x 32 (input 65 x 65 x 4)
 using SB12 = SCfg<8, 8, 1, 4, XFB_B12_NW>;     // block1.2  240x320            tile 32 x 4*NW
 using SB13 = SCfg<8, 24, 2, 2, XFB_B13_NW>;    // block1.3  -> 120x160         tile 32 x 2*NW
 
@@ -359,9 +371,9 @@ cudaError_t launch_conv_small_layer(Ctx* c, int L) {
         return run_small<SB11, true, false, true, true>(c, a, L);
       }
       from(L_B1_0);
-      return run_small<SB11, true, true>(c, a, L);
-    case L_B1_2: from(L_B1_1); return run_small<SB12, true, false>(c, a, L);
-    case L_B1_3: from(L_B1_2); return run_small<SB13, true, true>(c, a, L);
+      return run_small<SB11, true, XFB_B11_DIRECT>(c, a, L);
+    case L_B1_2: from(L_B1_1); return run_small<SB12, true, XFB_B12_DIRECT>(c, a, L);
+    case L_B1_3: from(L_B1_2); return run_small<SB13, true, XFB_B13_DIRECT>(c, a, L);
     default: return cudaErrorInvalidValue;
   }
 }
