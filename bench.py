@@ -593,8 +593,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="frames per launch group (one xfb_extract_batch + one xfb_match_frame_pairs call)")
-    ap.add_argument("--chunks", type=int, default=160, help="launch groups per step: a step processes chunks x batch frames per GPU")
+    ap.add_argument("--batch", type=int, default=64, help="frames per launch group (one xfb_extract_batch + one xfb_match_frame_pairs call)")
+    ap.add_argument("--chunks", type=int, default=80, help="launch groups per step: a step processes chunks x batch frames per GPU")
     ap.add_argument("--diagnose-e2e", action="store_true", help="per-rank split of the end-to-end time: copies only / kernels only / xfb_submit / host time")
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)

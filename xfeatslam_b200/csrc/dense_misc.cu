@@ -230,31 +230,40 @@ cudaError_t launch_pyramid(Ctx* c) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// heatmap_head.2 + sigmoid: one warp per pixel, two channels per lane, shuffle reduction
+// heatmap_head.2 + sigmoid: 16 lanes per pixel (4 channels each: a pixel is one 256-byte line read as 16 x LDG.128), 4 pixels per
+// thread with their loads in flight together, 4 shuffle steps per dot product.  (The first version used a whole warp per pixel.)
 // ------------------------------------------------------------------------------------------------
+constexpr int HO_PIX = 4;      // pixels per 16-lane group
 __global__ void __launch_bounds__(256) heatmap_out_kernel(const float* in, const float* mean, const float* rstd, const float* w,
                                                           const float* bias, int npix, float* out) {
   const int b = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (p >= npix) return;
-  const float2 v = *reinterpret_cast<const float2*>(in + ((size_t)b * npix + p) * 64 + lane * 2);
-  const float2 m = *reinterpret_cast<const float2*>(mean + b * 64 + lane * 2);
-  const float2 r = *reinterpret_cast<const float2*>(rstd + b * 64 + lane * 2);
-  const float2 ww = *reinterpret_cast<const float2*>(w + lane * 2);
-  float s = fmaxf((v.x - m.x) * r.x, 0.f) * ww.x;
-  s = fmaf(fmaxf((v.y - m.y) * r.y, 0.f), ww.y, s);
+  const int sub = threadIdx.x & 15, grp = threadIdx.x >> 4;                    // 16 groups per CTA
+  const int p0 = (blockIdx.x * 16 + grp) * HO_PIX;
+  const float4 m = *reinterpret_cast<const float4*>(mean + b * 64 + sub * 4);
+  const float4 r = *reinterpret_cast<const float4*>(rstd + b * 64 + sub * 4);
+  const float4 ww = *reinterpret_cast<const float4*>(w + sub * 4);
+  float4 v[HO_PIX];
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-  if (lane == 0) {
-    const float z = s + bias[0];
-    out[(size_t)b * npix + p] = 1.0f / (1.0f + expf(-z));
+  for (int i = 0; i < HO_PIX; ++i) {
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p0 + i < npix) v[i] = *reinterpret_cast<const float4*>(in + ((size_t)b * npix + p0 + i) * 64 + sub * 4);
+  }
+  const float bs = bias[0];
+#pragma unroll
+  for (int i = 0; i < HO_PIX; ++i) {
+    float s = fmaxf((v[i].x - m.x) * r.x, 0.f) * ww.x;
+    s = fmaf(fmaxf((v[i].y - m.y) * r.y, 0.f), ww.y, s);
+    s = fmaf(fmaxf((v[i].z - m.z) * r.z, 0.f), ww.z, s);
+    s = fmaf(fmaxf((v[i].w - m.w) * r.w, 0.f), ww.w, s);
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (sub == 0 && p0 + i < npix) out[(size_t)b * npix + p0 + i] = 1.0f / (1.0f + expf(-(s + bs)));
   }
 }
 
 cudaError_t launch_heatmap_out(Ctx* c) {
   const int npix = (c->H >> 3) * (c->W >> 3);
-  dim3 grid((npix + 7) / 8, c->B);
+  dim3 grid((npix + 16 * HO_PIX - 1) / (16 * HO_PIX), c->B);
   prof_begin(c, P_HEATMAP_OUT);
   heatmap_out_kernel<<<grid, 256, 0, c->stream>>>(c->act[L_HM_1], c->bn[L_HM_1].mean, c->bn[L_HM_1].rstd, c->w[L_HM_2], c->bias[L_HM_2],
                                                   npix, c->act[L_HM_2]);
