@@ -480,6 +480,9 @@ void xfb_destroy(xfb_ctx* c) {
       fprintf(stderr, "[xfb] match_mutual CTA(7,3) cycles per launch: total %.0f | MMA lane loop end @%.0f | row warp: stream+bound end @%.0f, drain end @%.0f | "
               "column warp: stream end @%.0f, drain end @%.0f || all CTAs per launch: row entries %.0f verified %.0f, column entries %.0f verified %.0f\n",
               h[20] / m, h[25] / m, h[21] / m, h[22] / m, h[23] / m, h[24] / m, h[26] / m, h[27] / m, h[28] / m, h[29] / m);
+      fprintf(stderr, "[xfb]   MMA lane per launch: wait column block %.0f, wait column accumulator free %.0f, wait row accumulator free %.0f, issue %.0f | "
+              "row warp 0 (half of the blocks): wait accumulator %.0f, work %.0f | column warp 0: wait accumulator %.0f, work %.0f\n",
+              h[52] / m, h[53] / m, h[54] / m, h[55] / m, h[56] / m, h[57] / m, h[58] / m, h[59] / m);
       const char* nm[4] = {"row overflow", "row final", "column overflow", "column final"};
       for (int k = 0; k < 4; ++k) {
         const unsigned long long* d = h + 32 + 5 * k;

@@ -20,12 +20,14 @@
 //     second-largest slice maximum is attained by another column than the largest, so it bounds the row's second-smallest t);
 //     a column is a CANDIDATE when u > (running bound) - (2e + 1)/1024.  The bound only tightens; candidates are queued with the
 //     slice maximum as an upper bound of their u and re-filtered against the FINAL bound before the exact verification.
-//   * Column direction (8 warps): per block and column the maximum over the CTA's 128 rows; rows within (2e + 1)/1024 of it are
-//     queued.  The per-column maxima of all CTAs of a pair meet in a global array (atomicMax); at the end a CTA verifies only the
-//     queued rows that are still within the margin of the GLOBAL maximum, and merges exact (distance, row) keys with a 64-bit
+//   * Column direction (8 warps), ONE pass per block: a row is queued when its value exceeds (the largest value known for the
+//     column) - (2e + 1)/1024, "known" = what the pair's other CTAs have published so far in a global array (atomicMax; the CTAs walk
+//     the column blocks in rotated order, so on average half of them have been there already) and this CTA's own rows up to the
+//     current 32-row part.  Any such bound is <= the final column maximum: no candidate is lost.  At the end a CTA verifies only
+//     the queued rows that are still within the margin of the FINAL maximum, and merges exact (distance, row) keys with a 64-bit
 //     global atomicMin -- the total order (distance, index) of the reference's scan.  The last CTA of a pair writes the column
 //     outputs and resets the scratch.
-//   * Verification: 32 queued pairs at a time, one per lane (the 64-step fp64 chain is paid once per 32).
+//   * Verification: 8 queued pairs at a time, four lanes per pair (all of a lane's row loads in flight at once).
 //
 // Warp roles (576 threads): warp 0 loader, warp 1 TMEM allocator + MMA issuer (one elected lane), warps 2-9 row direction,
 // warps 10-17 column direction (TMEM lane quadrant = warp id % 4).  Vocabulary-node gated searches (group ids) and descriptor
@@ -358,6 +360,10 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
   const int nB = a.nB_dev ? min(a.nB_host, a.nB_dev[setB]) : a.nB_host;
   const int row0 = blockIdx.x * MM_ROWS;
   const int nblk = (row0 < nA) ? (nB + MM_ROWS - 1) / MM_ROWS : 0;                // column blocks
+  // The CTAs of a pair walk the column blocks in ROTATED order (CTA x starts at block x): when a CTA reaches a block, on average half
+  // of the pair's other CTAs have already published their maxima of its columns, so the column direction can test against an
+  // almost final bound in a single pass (see there).  kk = physical block of step k.
+  const int rot = (MUTUAL && nblk > 0) ? (int)(blockIdx.x % (unsigned)nblk) : 0;
   const unsigned char* imgA = reinterpret_cast<const unsigned char*>(a.imgA) + (size_t)setA * a.img_stride_A + (size_t)blockIdx.x * MM_BLK_BYTES;
   const unsigned char* imgB = reinterpret_cast<const unsigned char*>(a.imgB) + (size_t)setB * a.img_stride_B;
   const float* rawA = a.rawA + (size_t)setA * a.raw_stride_A;
@@ -400,7 +406,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
         const int s = k % MM_STAGES;
         if (k >= MM_STAGES) mbar_wait(&sh->bar_empty[s], ((k / MM_STAGES) - 1) & 1);
         mbar_expect_tx(&sh->bar_full[s], MM_BLK_BYTES);
-        bulk_g2s(sB0 + (size_t)s * MM_BLK_BYTES, imgB + (size_t)k * MM_BLK_BYTES, MM_BLK_BYTES, &sh->bar_full[s]);
+        const int kk = (k + rot) % nblk;
+        bulk_g2s(sB0 + (size_t)s * MM_BLK_BYTES, imgB + (size_t)kk * MM_BLK_BYTES, MM_BLK_BYTES, &sh->bar_full[s]);
       }
     }
   } else if (warp == 1) {
@@ -415,23 +422,17 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
 #pragma unroll 1
       for (int k = 0; k < nblk; ++k) {
         const int s = k % MM_STAGES, st = k & 1;
+        long long tt = dbg0 ? clock64() : 0;
         mbar_wait(&sh->bar_full[s], (k / MM_STAGES) & 1);
-        if (k >= 2) {
-          mbar_wait(&sh->bar_acce1[st], ((k >> 1) - 1) & 1);
-          if (MUTUAL) mbar_wait(&sh->bar_acce2[st], ((k >> 1) - 1) & 1);
-        }
+        if (dbg0) { const long long n2 = clock64(); atomicAdd(dbgc + 52, (unsigned long long)(n2 - tt)); tt = n2; }
+        if (k >= 2 && MUTUAL) mbar_wait(&sh->bar_acce2[st], ((k >> 1) - 1) & 1);
+        if (dbg0) { const long long n2 = clock64(); atomicAdd(dbgc + 53, (unsigned long long)(n2 - tt)); tt = n2; }
         tc_fence_after();
         const uint32_t bAddr = smem_u32(sB0 + (size_t)s * MM_BLK_BYTES);
         const uint64_t dB0 = umma_desc_kmajor(bAddr, MM_LBO, MM_SBO);
         const uint64_t dBt = umma_desc_kmajor(bAddr + 9 * MM_LBO, MM_LBO, MM_SBO);          // column tail, then the zero chunk
         const uint32_t d1 = tmem_base + (uint32_t)st * 256u, d2 = d1 + 128u;
-        // D1[row][column] = a.b + rowtail.coltail
-        mm_umma(d1, dA0, dB0, 0u);
-        mm_umma(d1, dA0 + KSTEP, dB0 + KSTEP, 1u);
-        mm_umma(d1, dA0 + 2 * KSTEP, dB0 + 2 * KSTEP, 1u);
-        mm_umma(d1, dA0 + 3 * KSTEP, dB0 + 3 * KSTEP, 1u);
-        mm_umma(d1, dAt, dBt, 1u);
-        umma_commit(&sh->bar_accf1[st]);
+        // the column direction's MMAs go first (its warps also publish to / read from global memory), the row direction's follow
         if (MUTUAL) {
           // D2[column][row]: the same products with the operands swapped
           mm_umma(d2, dB0, dA0, 0u);
@@ -441,7 +442,18 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
           mm_umma(d2, dBt, dAt, 1u);
           umma_commit(&sh->bar_accf2[st]);
         }
+        if (dbg0) { const long long n2 = clock64(); atomicAdd(dbgc + 55, (unsigned long long)(n2 - tt)); tt = n2; }
+        if (k >= 2) { mbar_wait(&sh->bar_acce1[st], ((k >> 1) - 1) & 1); tc_fence_after(); }
+        if (dbg0) { const long long n2 = clock64(); atomicAdd(dbgc + 54, (unsigned long long)(n2 - tt)); tt = n2; }
+        // D1[row][column] = a.b + rowtail.coltail
+        mm_umma(d1, dA0, dB0, 0u);
+        mm_umma(d1, dA0 + KSTEP, dB0 + KSTEP, 1u);
+        mm_umma(d1, dA0 + 2 * KSTEP, dB0 + 2 * KSTEP, 1u);
+        mm_umma(d1, dA0 + 3 * KSTEP, dB0 + 3 * KSTEP, 1u);
+        mm_umma(d1, dAt, dBt, 1u);
+        umma_commit(&sh->bar_accf1[st]);
         umma_commit(&sh->bar_empty[s]);     // the column block may be overwritten once these MMAs have read it
+        if (dbg0) { const long long n2 = clock64(); atomicAdd(dbgc + 55, (unsigned long long)(n2 - tt)); }
       }
       if (dbg0) atomicAdd(dbgc + 25, (unsigned long long)(clock64() - t_start));
     }
@@ -512,9 +524,12 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
       };
 #pragma unroll 1
       for (int k = group; k < nblk; k += 2) {
+        const bool tme = dbg0 && ew == 0 && lane == 0;
+        long long tt = tme ? clock64() : 0;
         mbar_wait(&sh->bar_accf1[group], (uint32_t)(k >> 1) & 1u);
         __syncwarp();
         tc_fence_after();
+        if (tme) { const long long n2 = clock64(); atomicAdd(dbgc + 56, (unsigned long long)(n2 - tt)); tt = n2; }
         float v[32];
         if (k == group) {
           // seed the running top-2 from this block before collecting candidates from it
@@ -532,9 +547,11 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
           const float tau = bound();
           mm_ld32(tq + (uint32_t)part * 32u, v);
           const float m = mm_max32(v);
-          uint32_t mask = mm_mask32(v, tau);
+          // once the running bound is tight most slices hold no candidate for ANY of the warp's 32 rows (the slice maximum says so)
+          uint32_t mask = 0u;
+          if (__any_sync(0xffffffffu, m > tau)) mask = mm_mask32(v, tau);
           if (wild && ok) mask = 0xffffffffu;
-          const int j0 = k * MM_ROWS + part * 32;
+          const int j0 = ((k + rot) % nblk) * MM_ROWS + part * 32;
           if (j0 + 32 > nB) mask &= (nB > j0) ? (0xffffffffu >> (32 - (nB - j0))) : 0u;     // padded columns
           if (k != group) {            // (the seeding block's maxima are already in)
             const float lo = fminf(m1, m);
@@ -547,6 +564,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
         __syncwarp();
         if (lane == 0) mbar_arrive(&sh->bar_acce1[group]);
         sTau[group * MM_ROWS + ln] = bound();          // what an overflow drain of this group filters with
+        if (tme) atomicAdd(dbgc + 57, (unsigned long long)(clock64() - tt));
       }
       // ---- the stream is over: merge the two groups' slice maxima into the final bound of every row ----
       sM[group * MM_ROWS + ln] = make_float2(m1, m2);
@@ -562,37 +580,50 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
       drain(true);
       if (dbg0 && ew == 0 && lane == 0) atomicAdd(dbgc + 22, (unsigned long long)(clock64() - t_start));
     } else if (MUTUAL) {
-      // ===== column direction: lane = column of the block =====
+      // ===== column direction: lane = column of the block.  ONE pass over the accumulator: a row is a candidate when its value
+      // exceeds (the largest value known for the column) - margin, where "known" = the maximum the pair's other CTAs have published
+      // so far (prefetched one block ahead; the rotated block order makes it nearly final on average) and this CTA's own rows up to
+      // and including the current 32-row part.  Any such bound is <= the final column maximum, so no true candidate is lost; the
+      // final filter of the drain compares with the final maximum.  Most parts then hold no candidate for any of the warp's 32
+      // columns and skip the mask altogether.
       const int rows_ok = min(MM_ROWS, nA - row0);
+      unsigned int gnext = 0u;
+      if (group < nblk) { const int j1 = ((group + rot) % nblk) * MM_ROWS + ln; if (j1 < nB) gnext = __ldcg(colG + j1); }
 #pragma unroll 1
       for (int k = group; k < nblk; k += 2) {
-        const int j = k * MM_ROWS + ln;
+        const int j = ((k + rot) % nblk) * MM_ROWS + ln;
         const bool colok = j < nB;
+        float run = mm_unord(gnext);                      // (-inf when nobody has published yet)
+        gnext = 0u;
+        if (k + 2 < nblk) { const int j2 = ((k + 2 + rot) % nblk) * MM_ROWS + ln; if (j2 < nB) gnext = __ldcg(colG + j2); }
+        const bool tme = dbg0 && ew == 8 && lane == 0;
+        long long tt = tme ? clock64() : 0;
         mbar_wait(&sh->bar_accf2[group], (uint32_t)(k >> 1) & 1u);
         __syncwarp();
         tc_fence_after();
+        if (tme) { const long long n2 = clock64(); atomicAdd(dbgc + 58, (unsigned long long)(n2 - tt)); tt = n2; }
         float v[32];
-        float cmax = -CUDART_INF_F;
+        float own = -CUDART_INF_F;
 #pragma unroll 1
         for (int part = 0; part < 4; ++part) {
           mm_ld32(tq + (uint32_t)part * 32u, v);
-          cmax = fmaxf(cmax, mm_max32(v));
-        }
-        if (colok) atomicMax(colG + j, mm_ord(cmax));
-        const float thr = cmax - margin_col;
-#pragma unroll 1
-        for (int part = 0; part < 4; ++part) {
-          mm_ld32(tq + (uint32_t)part * 32u, v);
-          uint32_t mask = mm_mask32(v, thr);
+          const float m = mm_max32(v);
+          own = fmaxf(own, m);
+          run = fmaxf(run, m);
+          const float thr = run - margin_col;
+          uint32_t mask = 0u;
+          if (__any_sync(0xffffffffu, m > thr)) mask = mm_mask32(v, thr);
           if (wild_set) mask = 0xffffffffu;
           const int r0 = part * 32;
           if (r0 + 32 > rows_ok) mask &= (rows_ok > r0) ? (0xffffffffu >> (32 - (rows_ok - r0))) : 0u;   // padded rows
           if (!colok) mask = 0u;
-          append(mask, r0, 1, j, 0, cmax);
+          append(mask, r0, 1, j, 0, m);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sh->bar_acce2[group]);
+        if (colok) atomicMax(colG + j, mm_ord(own));
+        if (tme) atomicAdd(dbgc + 59, (unsigned long long)(clock64() - tt));
       }
       if (dbg0 && ew == 8 && lane == 0) atomicAdd(dbgc + 23, (unsigned long long)(clock64() - t_start));
       // The final filter compares every queued row with the pair's per-column maximum over ALL CTAs so far: a dependent L2 load per
