@@ -97,6 +97,36 @@ def test_discrete_stages_bit_exact_on_reference_maps(xfb_small, name):
     assert np.all(post["kpts"][n:] == 0) and np.all(post["desc"][n:] == 0) and np.all(post["scores"][n:] == 0)
 
 
+def test_nms_plateau_lists_every_pixel():
+    """A plateau above the threshold: every pixel of it equals its 5x5 maximum, so a whole 64 x 16 NMS tile (1024 pixels) lands on the
+    kernel's candidate list (its scoring loop then runs more than one round).  Synthetic dense maps through the same debug entry as
+    above, expected values from the oracle's restatement of XFextractor::NMS / the score (src/XFextractor.cc:219-248, :277-282)."""
+    rng = np.random.RandomState(5)
+    H, W, nfeat = 64, 96, 4096
+    K1h = (rng.rand(H, W).astype(np.float32) * 0.04).astype(np.float32)          # background below the 0.05 threshold
+    K1h[8:56, 16:88] = np.float32(0.3)                                           # the plateau: 48 x 72 pixels
+    K1h[3, 5] = np.float32(0.9)                                                  # and an ordinary isolated peak
+    H1 = rng.rand(H // 8, W // 8).astype(np.float32)
+    feats = rng.randn(H // 8, W // 8, 64).astype(np.float32)
+    from xfeatslam_b200.capi import XFeatB200
+    ctx = XFeatB200(max_h=H, max_w=W, max_batch=1, max_topk=nfeat)
+    post = ctx.debug_post(feats, H1, K1h, nfeat)
+    ctx.close()
+    K1h_t = torch.from_numpy(K1h)[None, None]; H1_t = torch.from_numpy(H1)[None, None]
+    mk = xo.nms(K1h_t, 0.05, 5)
+    sn = xo.interpolate_sparse2d(K1h_t, mk, H, W, "nearest"); sb = xo.interpolate_sparse2d(H1_t, mk, H, W, "bilinear")
+    sc = (sn * sb).squeeze(-1).masked_fill(torch.all(mk == 0, -1), -1)
+    assert mk.shape[1] >= 48 * 72
+    order = xo.canonical_order(sc, mk, W)[:nfeat]
+    kp_ref = mk[0].numpy()[order]; sc_ref = sc[0].numpy()[order]
+    valid = sc_ref > 0
+    kp_ref, sc_ref = kp_ref[valid], sc_ref[valid]
+    n = post["n_valid"]
+    assert n == len(kp_ref) and n > 3000
+    assert np.array_equal(post["kpts"][:n].astype(np.int64), kp_ref)
+    assert np.array_equal(post["scores"][:n], sc_ref)
+
+
 @pytest.mark.parametrize("name,tol_common", [("vga_top4096", 0.99), ("vga_top1000", 0.98), ("hd720_top1000", 0.98)])
 def test_end_to_end_against_reference_golden(name, tol_common):
     from xfeatslam_b200.capi import XFeatB200
