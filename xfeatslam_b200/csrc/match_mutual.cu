@@ -425,26 +425,13 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
         long long tt = dbg0 ? clock64() : 0;
         mbar_wait(&sh->bar_full[s], (k / MM_STAGES) & 1);
         if (dbg0) { const long long n2 = clock64(); atomicAdd(dbgc + 52, (unsigned long long)(n2 - tt)); tt = n2; }
-        if (k >= 2 && MUTUAL) mbar_wait(&sh->bar_acce2[st], ((k >> 1) - 1) & 1);
-        if (dbg0) { const long long n2 = clock64(); atomicAdd(dbgc + 53, (unsigned long long)(n2 - tt)); tt = n2; }
+        if (k >= 2) mbar_wait(&sh->bar_acce1[st], ((k >> 1) - 1) & 1);
+        if (dbg0) { const long long n2 = clock64(); atomicAdd(dbgc + 54, (unsigned long long)(n2 - tt)); tt = n2; }
         tc_fence_after();
         const uint32_t bAddr = smem_u32(sB0 + (size_t)s * MM_BLK_BYTES);
         const uint64_t dB0 = umma_desc_kmajor(bAddr, MM_LBO, MM_SBO);
         const uint64_t dBt = umma_desc_kmajor(bAddr + 9 * MM_LBO, MM_LBO, MM_SBO);          // column tail, then the zero chunk
         const uint32_t d1 = tmem_base + (uint32_t)st * 256u, d2 = d1 + 128u;
-        // the column direction's MMAs go first (its warps also publish to / read from global memory), the row direction's follow
-        if (MUTUAL) {
-          // D2[column][row]: the same products with the operands swapped
-          mm_umma(d2, dB0, dA0, 0u);
-          mm_umma(d2, dB0 + KSTEP, dA0 + KSTEP, 1u);
-          mm_umma(d2, dB0 + 2 * KSTEP, dA0 + 2 * KSTEP, 1u);
-          mm_umma(d2, dB0 + 3 * KSTEP, dA0 + 3 * KSTEP, 1u);
-          mm_umma(d2, dBt, dAt, 1u);
-          umma_commit(&sh->bar_accf2[st]);
-        }
-        if (dbg0) { const long long n2 = clock64(); atomicAdd(dbgc + 55, (unsigned long long)(n2 - tt)); tt = n2; }
-        if (k >= 2) { mbar_wait(&sh->bar_acce1[st], ((k >> 1) - 1) & 1); tc_fence_after(); }
-        if (dbg0) { const long long n2 = clock64(); atomicAdd(dbgc + 54, (unsigned long long)(n2 - tt)); tt = n2; }
         // D1[row][column] = a.b + rowtail.coltail
         mm_umma(d1, dA0, dB0, 0u);
         mm_umma(d1, dA0 + KSTEP, dB0 + KSTEP, 1u);
@@ -452,6 +439,20 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_kernel(const MatchTcArgs a) 
         mm_umma(d1, dA0 + 3 * KSTEP, dB0 + 3 * KSTEP, 1u);
         mm_umma(d1, dAt, dBt, 1u);
         umma_commit(&sh->bar_accf1[st]);
+        if (MUTUAL) {
+          if (dbg0) { const long long n2 = clock64(); atomicAdd(dbgc + 55, (unsigned long long)(n2 - tt)); tt = n2; }
+          if (k >= 2) { mbar_wait(&sh->bar_acce2[st], ((k >> 1) - 1) & 1); tc_fence_after(); }
+          if (dbg0) { const long long n2 = clock64(); atomicAdd(dbgc + 53, (unsigned long long)(n2 - tt)); tt = n2; }
+          // D2[column][row]: the same products with the operands swapped.  ORDER MATTERS: D2 is committed last, so "the column
+          // direction has seen its last accumulator" implies that EVERY MMA has finished reading the ring of column blocks -- the
+          // column warps reuse that ring for their snapshot of the column maxima after the stream.
+          mm_umma(d2, dB0, dA0, 0u);
+          mm_umma(d2, dB0 + KSTEP, dA0 + KSTEP, 1u);
+          mm_umma(d2, dB0 + 2 * KSTEP, dA0 + 2 * KSTEP, 1u);
+          mm_umma(d2, dB0 + 3 * KSTEP, dA0 + 3 * KSTEP, 1u);
+          mm_umma(d2, dBt, dAt, 1u);
+          umma_commit(&sh->bar_accf2[st]);
+        }
         umma_commit(&sh->bar_empty[s]);     // the column block may be overwritten once these MMAs have read it
         if (dbg0) { const long long n2 = clock64(); atomicAdd(dbgc + 55, (unsigned long long)(n2 - tt)); }
       }
