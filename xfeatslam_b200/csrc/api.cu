@@ -460,8 +460,8 @@ void xfb_destroy(xfb_ctx* c) {
       if (!q[0]) continue;
       const double n = (double)q[0], tl = q[16] ? (double)q[16] : 1.0, st = q[5] ? (double)q[5] : 1.0;
       fprintf(stderr, "[xfb t2] %-16s launches %llu | CTA0 cycles/launch %.0f, tiles/launch %.1f | producer per stage: wait_free %.0f work %.0f fence+arrive %.0f | "
-              "mma per tile: wait_in %.0f wait_acce %.0f issue %.0f wait_w(total/launch) %.0f | epilogue per tile: wait_accf %.0f ld+store %.0f stats %.0f "
-              "part+fence %.0f ticket %.0f fold+loop %.0f\n",
+              "mma per tile: wait_in %.0f wait_acce %.0f issue %.0f wait_w(total/launch) %.0f | epilogue per tile: wait_accf %.0f tmem ld %.0f "
+              "staging stores + TMA issue %.0f column sums + partials %.0f staging-tile barrier %.0f publish + loop %.0f\n",
               kLayers[L].ref_name, q[0], q[1] / n, tl / n, q[2] / st, q[3] / st, q[4] / st, q[6] / tl, q[7] / tl, q[8] / tl, q[9] / n, q[10] / tl, q[11] / tl,
               q[12] / tl, q[13] / tl, q[14] / tl, q[15] / tl);
     }

@@ -15,8 +15,10 @@
 //   * Persistent CTAs (one per SM), each walking a CONTIGUOUS range of 128-pixel output tiles; the layer's weights are
 //     loaded into shared memory ONCE per CTA and stay resident (layers whose weight image exceeds shared memory split their
 //     output channels over CTAs: NSPLIT).  Three pipeline stages run concurrently on different tiles:
-//        7 producer warps   stage tile i+1: LDG.256 (issued one unit AHEAD, software-pipelined in registers) -> BN / ReLU ->
-//                           hi / lo split -> STS.128 into a ring of NBUF (tile, channel phase) buffers,
+//        7 producer warps   stage tile i+1: raw fp32 input -> BN / ReLU -> hi / lo split -> STS.128 into a ring of NBUF (tile, channel
+//                           phase) buffers.  The raw input comes either through registers (LDG.256 issued one unit AHEAD, software
+//                           pipelined) or, for the layers with shared memory to spare (T2Cfg::RAW), from a ring of RAW raw boxes that
+//                           the MMA warp's elected lane fills by TMA tensor loads RAW buffers ahead,
 //        1 MMA warp         multiplies tile i (one elected lane; accumulator = TMEM stage i & 1),
 //        4 epilogue warps   drain tile i-1: tcgen05.ld -> scale -> 128B-swizzled staging tile in shared memory ->
 //                           ONE TMA tensor store per 32-channel half (cp.async.bulk.tensor, clipped at the image border by
@@ -27,6 +29,8 @@
 //   * Train-mode BatchNorm statistics: per-tile partial sums -> global scratch with plain stores; a CTA publishes them ONCE per
 //     frame it touched (its tile range is contiguous: one or two frames) with a barrier + one fence + one ticket atomic; the
 //     CTA that completes a frame folds the frame's partials in fixed order (double).
+//   * Programmatic dependent launch: the kernel is launched with programmatic stream serialization; everything that touches the
+//     previous kernel's data sits behind griddepcontrol.wait, so the prologue overlaps the previous layer's tail.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
