@@ -40,3 +40,22 @@ def test_conv_layer_roofline_arithmetic():
     ms = line["roofline"]["kernel_ms_per_step"]                     # one launch of every layer per step
     r = bench.conv_layer_roofline(ms, 480, 640, 32, {"bf16_tflops": 1604.2, "hbm_gbs": 6521.1, "source": "measured"}, split_cost=6.0, split_name="3xTF32")
     assert 1.5 < r["measured_ms"] < 1.9 and 0.44 < r["roof_ms"] < 0.48 and 0.24 < r["frac"] < 0.30
+
+
+def test_committed_round2_line_carries_the_contract():
+    """profiles/r02_bench_n1.json is the line `python bench.py` printed on the B200: every key of the contract, a sustained timed
+    region, clean clocks, the roofline / cpu_baseline / e2e objects."""
+    line = json.loads((REPO / "profiles" / "r02_bench_n1.json").read_text())
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+                "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert key in line, key
+    assert line["unit"] == "frames/s" and line["higher_is_better"] is True and line["scaling"] == "weak" and line["vs_baseline"] is None
+    assert line["config"]["workload"].startswith("vga_640x480") and "model" not in line["config"]
+    assert line["run"]["timed_region_s"] >= 2.0                                   # VERDICT item 5
+    r = line["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-6 and r["traffic"] > 0
+    e = line["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] != line["value"]
+    assert line["gpu_launches"] > 0 and line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    c = line["clocks"]
+    assert c["sm_mhz"] >= 0.9 * c["sm_max_mhz"] and not any(x in c["reasons"] for x in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"))
